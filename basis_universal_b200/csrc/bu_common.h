@@ -1,0 +1,67 @@
+// bu_common.h -- host/device portability macros and tiny integer/float helpers.
+//
+// Every arithmetic helper here is written so that nvcc (--fmad=false, IEEE div/sqrt) and g++ (x86-64, SSE2 scalar
+// math, -ffp-contract=off) produce bit-identical results: bit-exact UASTC output depends on it (hard part 1).
+// The same headers are compiled twice: by nvcc into the product library, and by g++ into the host-emulation library that
+// the CPU-only tests use to check the algorithm against the compiled reference without a GPU.
+#pragma once
+#include <stdint.h>
+#include <math.h>
+#include <string.h>
+
+#if defined(__CUDACC__)
+#define BU_HD __host__ __device__
+#define BU_FI __host__ __device__ __forceinline__
+#else
+#define BU_HD
+#define BU_FI inline
+#endif
+
+namespace bu {
+
+BU_FI int clampi(int v, int lo, int hi) { return v < lo ? lo : (v > hi ? hi : v); }
+BU_FI int clamp255i(int v) { return v < 0 ? 0 : (v > 255 ? 255 : v); }
+BU_FI int iabsi(int v) { return v < 0 ? -v : v; }
+BU_FI int mini(int a, int b) { return a < b ? a : b; }
+BU_FI int maxi(int a, int b) { return a > b ? a : b; }
+BU_FI uint32_t minu(uint32_t a, uint32_t b) { return a < b ? a : b; }
+BU_FI uint32_t maxu(uint32_t a, uint32_t b) { return a > b ? a : b; }
+BU_FI uint64_t minu64(uint64_t a, uint64_t b) { return a < b ? a : b; }
+// Same comparison forms as the reference's minimumf/maximumf/clampf/saturate (transcoder/basisu.h:136-145): NaN handling follows.
+BU_FI float minf_(float a, float b) { return (a < b) ? a : b; }
+BU_FI float maxf_(float a, float b) { return (a > b) ? a : b; }
+BU_FI float clampf_(float v, float lo, float hi) { if (v < lo) v = lo; else if (v > hi) v = hi; return v; }
+BU_FI float saturatef_(float v) { return clampf_(v, 0.0f, 1.0f); }
+
+// float -> uint8 with x86 cvttss2si semantics for the one place the reference casts a possibly-NaN float
+// (bc7enc.cpp:1660, hy == ly): NaN / out-of-int-range -> 0x80000000 -> low byte 0.
+BU_FI uint8_t f2u8_x86(float v)
+{
+	if (!(v == v)) return 0;
+	if (v >= 2147483648.0f || v < -2147483648.0f) return 0;
+	return (uint8_t)(int)v;
+}
+
+// Packed RGBA8 pixel helpers (R in the low byte, as the bytes lie in memory on a little-endian machine).
+BU_FI uint32_t px_c(uint32_t p, uint32_t c) { return (p >> (c * 8)) & 255u; }
+BU_FI uint32_t px_make(uint32_t r, uint32_t g, uint32_t b, uint32_t a) { return r | (g << 8) | (b << 16) | (a << 24); }
+BU_FI uint32_t px_set(uint32_t p, uint32_t c, uint32_t v) { return (p & ~(255u << (c * 8))) | (v << (c * 8)); }
+
+// ASTC LDR weight interpolation, linear (non-sRGB) decode mode: transcoder_uastc.h:79 astc_interpolate(srgb=false),
+// identical to bc7enc.cpp:177 astc_interpolate_linear.
+BU_FI uint32_t astc_lerp(uint32_t l, uint32_t h, uint32_t w)
+{
+	l = (l << 8) | l;
+	h = (h << 8) | h;
+	return ((l * (64 - w) + h * w + 32) >> 6) >> 8;
+}
+
+BU_FI uint32_t sq_diff(int a, int b) { int d = a - b; return (uint32_t)(d * d); }
+BU_FI uint32_t dist_rgb(uint32_t p, uint32_t q)
+{
+	return sq_diff((int)px_c(p, 0), (int)px_c(q, 0)) + sq_diff((int)px_c(p, 1), (int)px_c(q, 1)) + sq_diff((int)px_c(p, 2), (int)px_c(q, 2));
+}
+BU_FI uint32_t dist_rgba(uint32_t p, uint32_t q) { return dist_rgb(p, q) + sq_diff((int)px_c(p, 3), (int)px_c(q, 3)); }
+BU_FI uint32_t dist_la(uint32_t p, uint32_t q) { return sq_diff((int)px_c(p, 0), (int)px_c(q, 0)) + sq_diff((int)px_c(p, 3), (int)px_c(q, 3)); }
+
+} // namespace bu

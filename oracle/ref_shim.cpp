@@ -1,0 +1,240 @@
+// oracle/ref_shim.cpp -- TEST INFRASTRUCTURE ONLY (never linked into the product library).
+//
+// Thin extern "C" veneer over the UNMODIFIED reference encoder, compiled from the sources where they
+// lie under /root/reference by oracle/Makefile into oracle/_ref/libbasisu_ref.so.  It exposes the four
+// hot-path seams of SURVEY.md section 8(b) with plain pointers so tests/ and bench.py's cpu_baseline /
+// --impl reference legs can drive the reference through ctypes:
+//
+//   ref_encode_uastc_blocks  -> basisu::encode_uastc            (encoder/basisu_uastc_enc.h:68)
+//   ref_uastc_rdo            -> basisu::uastc_rdo               (encoder/basisu_uastc_enc.h:139)
+//   ref_compress_image       -> basisu::basis_compress          (encoder/basisu_comp.h:1259)
+//   ref_etc1s_*              -> basisu_frontend / etc1_optimizer (encoder/basisu_frontend.h:115-156)
+//
+// Nothing in this file restates reference logic; it only marshals arguments.
+#include "encoder/basisu_comp.h"
+#include "encoder/basisu_enc.h"
+#include "encoder/basisu_uastc_enc.h"
+#include "encoder/basisu_bc7enc.h"
+#include "encoder/basisu_etc.h"
+#include "encoder/basisu_frontend.h"
+#include "encoder/basisu_gpu_texture.h"
+#include "transcoder/basisu_transcoder.h"
+
+#include <atomic>
+#include <thread>
+#include <vector>
+#include <cstring>
+
+#define REF_API extern "C" __attribute__((visibility("default")))
+
+using namespace basisu;
+
+static std::atomic<bool> g_inited(false);
+
+REF_API void ref_init()
+{
+	if (!g_inited.exchange(true))
+		basisu_encoder_init(false, false);
+}
+
+// Encodes n 4x4 RGBA blocks (64 B each, [y][x], R first) to n UASTC blocks (16 B each) with `threads`
+// host threads (block ranges are independent, so the split does not affect the bytes).
+REF_API void ref_encode_uastc_blocks(const uint8_t* pBlocks, uint32_t n, uint8_t* pOut, uint32_t flags, uint32_t threads)
+{
+	ref_init();
+	if (threads <= 1)
+	{
+		for (uint32_t i = 0; i < n; i++)
+			encode_uastc(pBlocks + (size_t)i * 64, *reinterpret_cast<basist::uastc_block*>(pOut + (size_t)i * 16), flags);
+		return;
+	}
+	std::atomic<uint32_t> next(0);
+	const uint32_t chunk = 256; // same chunking as comp.cpp:2005
+	std::vector<std::thread> pool;
+	for (uint32_t t = 0; t < threads; t++)
+		pool.emplace_back([&]() {
+			for (;;)
+			{
+				const uint32_t first = next.fetch_add(chunk);
+				if (first >= n) break;
+				const uint32_t last = std::min(n, first + chunk);
+				for (uint32_t i = first; i < last; i++)
+					encode_uastc(pBlocks + (size_t)i * 64, *reinterpret_cast<basist::uastc_block*>(pOut + (size_t)i * 16), flags);
+			}
+		});
+	for (auto& th : pool) th.join();
+}
+
+// In-place RDO post-pass. total_jobs has the meaning of uastc_enc.h:139 (comp.cpp:2078 passes min(4, threads)).
+REF_API int ref_uastc_rdo(uint32_t n, uint8_t* pBlocks, const uint8_t* pBlock_pixels, float lambda, uint32_t dict_size,
+	float max_allowed_rms_increase_ratio, float skip_block_rms_thresh, float max_smooth_block_std_dev, float smooth_block_max_error_scale,
+	uint32_t flags, uint32_t total_jobs, uint32_t threads)
+{
+	ref_init();
+	uastc_rdo_params p;
+	p.m_lambda = lambda;
+	p.m_lz_dict_size = dict_size;
+	p.m_max_allowed_rms_increase_ratio = max_allowed_rms_increase_ratio;
+	p.m_skip_block_rms_thresh = skip_block_rms_thresh;
+	p.m_max_smooth_block_std_dev = max_smooth_block_std_dev;
+	p.m_smooth_block_max_error_scale = smooth_block_max_error_scale;
+	job_pool pool(threads ? threads : 1);
+	return uastc_rdo(n, reinterpret_cast<basist::uastc_block*>(pBlocks), reinterpret_cast<const color_rgba*>(pBlock_pixels), p, flags, &pool, total_jobs) ? 1 : 0;
+}
+
+// Whole-image compress through the reference's public C-style API. Returns a malloc'd buffer (free with ref_free).
+// fmt: 0 = ETC1S, 1 = UASTC LDR 4x4 (basist::basis_tex_format).
+REF_API void* ref_compress_image(uint32_t fmt, const uint8_t* pRGBA, uint32_t w, uint32_t h, uint32_t flags_and_quality, float rdo_quality, size_t* pSize)
+{
+	ref_init();
+	return basis_compress((basist::basis_tex_format)fmt, pRGBA, w, h, w, flags_and_quality, rdo_quality, pSize, nullptr);
+}
+
+REF_API void ref_free(void* p) { basis_free_data(p); }
+
+// Decodes n UASTC blocks to RGBA (64 B per block) with the reference transcoder.
+REF_API int ref_unpack_uastc_blocks(const uint8_t* pBlocks, uint32_t n, uint8_t* pPixels)
+{
+	ref_init();
+	for (uint32_t i = 0; i < n; i++)
+		if (!basist::unpack_uastc(*reinterpret_cast<const basist::uastc_block*>(pBlocks + (size_t)i * 16), reinterpret_cast<basist::color32*>(pPixels + (size_t)i * 64), false))
+			return 0;
+	return 1;
+}
+
+// ---- fine-grained hooks used by the per-function differential tests ------------------------------------------
+
+// color_cell_compression (bc7enc.cpp:1364) in its UASTC configuration (mode 255, ASTC endpoint range, linear metric).
+// weight_table: 1,2,3 = g_bc7_weights{1,2,3}, 4 = g_astc_weights4, 5 = g_astc_weights5.
+REF_API uint64_t ref_color_cell_compression(const uint8_t* pPixels, uint32_t num_pixels, uint32_t weight_table, uint32_t endpoint_range, uint32_t has_alpha,
+	uint32_t uber_level, uint32_t ls_passes, uint8_t* pLow4, uint8_t* pHigh4, uint8_t* pSelectors)
+{
+	ref_init();
+	static const uint32_t* s_w[6] = { nullptr, basist::g_bc7_weights1, basist::g_bc7_weights2, basist::g_bc7_weights3, basist::g_astc_weights4, basist::g_astc_weights5 };
+	static const float* s_wx[6] = { nullptr, g_bc7_weights1x, g_bc7_weights2x, g_bc7_weights3x, g_astc_weights4x, g_astc_weights5x };
+
+	color_cell_compressor_params cp;
+	memset(&cp, 0, sizeof(cp));
+	cp.m_num_pixels = num_pixels;
+	cp.m_pPixels = reinterpret_cast<const basist::color_quad_u8*>(pPixels);
+	cp.m_num_selector_weights = 1u << weight_table;
+	cp.m_pSelector_weights = s_w[weight_table];
+	cp.m_pSelector_weightsx = reinterpret_cast<const bc7enc_vec4F*>(s_wx[weight_table]);
+	cp.m_astc_endpoint_range = endpoint_range;
+	cp.m_weights[0] = cp.m_weights[1] = cp.m_weights[2] = cp.m_weights[3] = 1;
+	cp.m_has_alpha = has_alpha != 0;
+
+	bc7enc_compress_block_params comp;
+	memset(&comp, 0, sizeof(comp));
+	comp.m_max_partitions_mode1 = 64;
+	comp.m_least_squares_passes = ls_passes;
+	comp.m_weights[0] = comp.m_weights[1] = comp.m_weights[2] = comp.m_weights[3] = 1;
+	comp.m_uber_level = uber_level;
+
+	color_cell_compressor_results res;
+	uint8_t sel_temp[16];
+	memset(&res, 0, sizeof(res));
+	res.m_pSelectors = pSelectors;
+	res.m_pSelectors_temp = sel_temp;
+
+	const uint64_t err = color_cell_compression(255, &cp, &res, &comp);
+	memcpy(pLow4, res.m_astc_low_endpoint.m_c, 4);
+	memcpy(pHigh4, res.m_astc_high_endpoint.m_c, 4);
+	return err;
+}
+
+// ---- ETC1S ---------------------------------------------------------------------------------------------------
+
+// Per-block ETC1S encode exactly as basisu_frontend::init_etc1_images does on the CPU (frontend.cpp:733-822):
+// etc1_optimizer with the quality the comp_level maps to, perceptual metric selectable, ETC1S constraint on.
+REF_API void ref_etc1s_encode_blocks(const uint8_t* pBlocks, uint32_t n, uint8_t* pOut8, uint32_t perceptual, uint32_t comp_level)
+{
+	ref_init();
+	for (uint32_t i = 0; i < n; i++)
+	{
+		etc1_optimizer optimizer;
+		etc1_optimizer::params optimizer_params;
+		etc1_optimizer::results optimizer_results;
+
+		if (comp_level == 0)
+			optimizer_params.m_quality = cETCQualityFast;
+		else if (comp_level == 1)
+			optimizer_params.m_quality = cETCQualityMedium;
+		else if (comp_level == BASISU_MAX_ETC1S_COMPRESSION_LEVEL)
+			optimizer_params.m_quality = cETCQualityUber;
+
+		optimizer_params.m_num_src_pixels = 16;
+		optimizer_params.m_pSrc_pixels = reinterpret_cast<const color_rgba*>(pBlocks + (size_t)i * 64);
+		optimizer_params.m_perceptual = perceptual != 0;
+
+		uint8_t selectors[16];
+		optimizer_results.m_pSelectors = selectors;
+		optimizer_results.m_n = 16;
+
+		optimizer.init(optimizer_params, optimizer_results);
+		optimizer.compute(); // the frontend treats a false return as an internal invariant failure (frontend.cpp:800)
+
+		etc_block& blk = *reinterpret_cast<etc_block*>(pOut8 + (size_t)i * 8);
+		memset(&blk, 0, sizeof(blk));
+		blk.set_block_color5_etc1s(optimizer_results.m_block_color_unscaled);
+		blk.set_inten_tables_etc1s(optimizer_results.m_block_inten_table);
+		blk.set_flip_bit(true);
+
+		for (uint32_t y = 0; y < 4; y++)
+			for (uint32_t x = 0; x < 4; x++)
+				blk.set_selector(x, y, selectors[x + y * 4]);
+	}
+}
+
+// etc_block::determine_selectors (etc.h:374) given one (rgb5, inten) per block: the CPU meaning of opencl_determine_selectors.
+REF_API void ref_etc1s_determine_selectors(const uint8_t* pBlocks, uint32_t n, const uint8_t* pRGB5_inten /*4 B per block*/, uint8_t* pOut8, uint32_t perceptual)
+{
+	ref_init();
+	for (uint32_t i = 0; i < n; i++)
+	{
+		etc_block& blk = *reinterpret_cast<etc_block*>(pOut8 + (size_t)i * 8);
+		memset(&blk, 0, sizeof(blk));
+		const uint8_t* p = pRGB5_inten + (size_t)i * 4;
+		blk.set_block_color5_etc1s(color_rgba(p[0], p[1], p[2], 255));
+		blk.set_inten_tables_etc1s(p[3]);
+		blk.set_flip_bit(true);
+		blk.determine_selectors(reinterpret_cast<const color_rgba*>(pBlocks + (size_t)i * 64), perceptual != 0);
+	}
+}
+
+// Decodes n ETC1 blocks with the reference (unpack_etc1, etc.h / etc.cpp).
+REF_API void ref_unpack_etc1_blocks(const uint8_t* pBlocks8, uint32_t n, uint8_t* pPixels)
+{
+	ref_init();
+	for (uint32_t i = 0; i < n; i++)
+		unpack_etc1(*reinterpret_cast<const etc_block*>(pBlocks8 + (size_t)i * 8), reinterpret_cast<color_rgba*>(pPixels + (size_t)i * 64));
+}
+
+REF_API uint32_t ref_color_distance(uint32_t perceptual, const uint8_t* a, const uint8_t* b, uint32_t alpha)
+{
+	return color_distance(perceptual != 0, color_rgba(a[0], a[1], a[2], a[3]), color_rgba(b[0], b[1], b[2], b[3]), alpha != 0);
+}
+
+// Field dump of a packed UASTC block (basist::unpack_uastc, transcoder.cpp:15282) for test diagnostics:
+// out[0]=mode [1]=pattern [2]=bc1_hint0 [3]=bc1_hint1 [4]=etc1 flip [5]=diff [6]=inten0 [7]=inten1 [8]=bias [9]=etc2 hints
+// [10]=ccs [11..28]=endpoints [29..60]=weights
+REF_API int ref_uastc_fields(const uint8_t* pBlock, uint8_t* out)
+{
+	ref_init();
+	basist::unpacked_uastc_block u;
+	memset(&u, 0, sizeof(u));
+	if (!basist::unpack_uastc(*reinterpret_cast<const basist::uastc_block*>(pBlock), u, false, true))
+		return 0;
+	memset(out, 0, 61);
+	out[0] = (uint8_t)u.m_mode; out[1] = (uint8_t)u.m_common_pattern; out[2] = u.m_bc1_hint0; out[3] = u.m_bc1_hint1;
+	out[4] = u.m_etc1_flip; out[5] = u.m_etc1_diff; out[6] = (uint8_t)u.m_etc1_inten0; out[7] = (uint8_t)u.m_etc1_inten1;
+	out[8] = (uint8_t)u.m_etc1_bias; out[9] = (uint8_t)u.m_etc2_hints;
+	if (u.m_mode != 8)
+	{
+		out[10] = (uint8_t)u.m_astc.m_ccs;
+		memcpy(out + 11, u.m_astc.m_endpoints, 18);
+		memcpy(out + 29, u.m_astc.m_weights, 32);
+	}
+	else { out[11] = u.m_solid_color.r; out[12] = u.m_solid_color.g; out[13] = u.m_solid_color.b; out[14] = u.m_solid_color.a; out[15]=(uint8_t)u.m_etc1_r; out[16]=(uint8_t)u.m_etc1_g; out[17]=(uint8_t)u.m_etc1_b; out[18]=(uint8_t)u.m_etc1_selector; }
+	return 1;
+}

@@ -1,0 +1,166 @@
+"""Shared test helpers: synthetic inputs, 4x4 block marshalling, ctypes loaders for the checkers.
+
+The reference .so (oracle/_ref/libbasisu_ref.so) and the host-emulation .so (tests/hostemu/_build) are TEST
+infrastructure; the product package never imports this module.
+"""
+import ctypes
+import os
+import subprocess
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+REF_SO = os.path.join(ROOT, "oracle", "_ref", "libbasisu_ref.so")
+EMU_SO = os.path.join(ROOT, "tests", "hostemu", "_build", "libbu_hostemu.so")
+GOLDEN = os.path.join(ROOT, "tests", "golden")
+
+
+def synth(n, seed, h=None):
+    """SURVEY.md 9.6 generator: n x n (or h x n) RGBA8 image."""
+    h = n if h is None else h
+    rng = np.random.default_rng(seed)
+    y, x = np.mgrid[0:h, 0:n].astype(np.float32)
+    r = 127.5 + 100 * np.sin(x / 97.0) * np.cos(y / 131.0)
+    g = 127.5 + 100 * np.sin((x + y) / 61.0)
+    b = 127.5 + 100 * np.cos(x / 23.0) * np.sin(y / 17.0)
+    rgb = np.stack([r, g, b], -1) + rng.normal(0, 12, size=(h, n, 3)).astype(np.float32)
+    a = 255 * ((np.sin(x / 257.0) * np.sin(y / 311.0)) > -0.3).astype(np.float32)
+    a = np.where(((x // 64 + y // 64) % 7) == 0, 128 + 100 * np.sin(x / 11.0), a)
+    return np.concatenate([rgb, a[..., None]], -1).clip(0, 255).astype(np.uint8)
+
+
+def image_to_blocks(img):
+    """(H, W, 4) uint8, H and W multiples of 4 -> (nblocks, 64) uint8 in raster block order, [y][x] RGBA per block
+    (pixel_block layout, encoder/basisu_enc.h:4156)."""
+    h, w, _ = img.shape
+    assert h % 4 == 0 and w % 4 == 0
+    return np.ascontiguousarray(img.reshape(h // 4, 4, w // 4, 4, 4).transpose(0, 2, 1, 3, 4).reshape(-1, 64))
+
+
+def edge_case_blocks(seed=7):
+    """Blocks that hit the special paths: solid, solid-but-alpha, LA, LA opaque, two-colour, gradients, random, 1-texel outliers."""
+    rng = np.random.default_rng(seed)
+    out = []
+
+    def blk(f):
+        b = np.zeros((4, 4, 4), np.uint8)
+        for y in range(4):
+            for x in range(4):
+                b[y, x] = f(x, y)
+        out.append(b.reshape(64))
+
+    for c in [(0, 0, 0, 255), (255, 255, 255, 255), (0, 0, 0, 0), (13, 200, 77, 255), (13, 200, 77, 9), (1, 1, 1, 255), (254, 255, 0, 128)]:
+        blk(lambda x, y: c)
+    blk(lambda x, y: (x * 60, x * 60, x * 60, 255))                      # opaque luminance ramp
+    blk(lambda x, y: (x * 60, x * 60, x * 60, 255 - y * 70))             # LA block
+    blk(lambda x, y: (40, 40, 40, 255 if (x + y) & 1 else 0))            # LA, binary alpha
+    blk(lambda x, y: (255, 0, 0, 255) if x < 2 else (0, 0, 255, 255))    # two colours, partition friendly
+    blk(lambda x, y: (255, 0, 0, 255) if y < 2 else (0, 255, 0, 255))
+    blk(lambda x, y: (x * 80, y * 80, 128, 255))
+    blk(lambda x, y: (x * 80, y * 80, 128, 64 + x * 40))
+    blk(lambda x, y: (200, 200, 200, 255) if (x, y) != (3, 3) else (0, 0, 0, 255))
+    blk(lambda x, y: (200, 10, 30, 255) if (x, y) != (0, 0) else (200, 10, 30, 254))
+    blk(lambda x, y: (x * 85, x * 85, x * 85, x * 85))
+    blk(lambda x, y: (17 * (x + 4 * y) % 256, 255 - 17 * (x + 4 * y) % 256, (x * y * 20) % 256, 255))
+    for _ in range(24):
+        out.append(rng.integers(0, 256, 64, dtype=np.uint8))
+    for _ in range(8):   # random opaque
+        b = rng.integers(0, 256, (16, 4), dtype=np.uint8); b[:, 3] = 255; out.append(b.reshape(64))
+    for _ in range(8):   # low-variance noise around a colour
+        base = rng.integers(20, 235, 4); b = (base + rng.integers(-6, 7, (16, 4))).clip(0, 255).astype(np.uint8); b[:, 3] = 255; out.append(b.reshape(64))
+    for _ in range(8):   # random LA
+        l = rng.integers(0, 256, 16, dtype=np.uint8); a = rng.integers(0, 256, 16, dtype=np.uint8)
+        out.append(np.stack([l, l, l, a], -1).reshape(64))
+    return np.ascontiguousarray(np.stack(out))
+
+
+def _ptr(a):
+    return a.ctypes.data_as(ctypes.c_void_p)
+
+
+def build_ref():
+    if not os.path.exists(REF_SO) and os.path.isdir("/root/reference/encoder"):
+        subprocess.check_call(["make", "-C", os.path.join(ROOT, "oracle"), "-j8", "ref"], stdout=subprocess.DEVNULL)
+    return os.path.exists(REF_SO)
+
+
+def build_emu():
+    src = os.path.join(ROOT, "tests", "hostemu", "hostemu.cpp")
+    deps = [src] + [os.path.join(ROOT, "basis_universal_b200", "csrc", f) for f in os.listdir(os.path.join(ROOT, "basis_universal_b200", "csrc")) if f.startswith("bu_") or f.endswith(".inc")]
+    if not os.path.exists(EMU_SO) or any(os.path.getmtime(d) > os.path.getmtime(EMU_SO) for d in deps):
+        subprocess.check_call([os.path.join(ROOT, "tests", "hostemu", "build.sh")])
+    return os.path.exists(EMU_SO)
+
+
+class Ref:
+    """ctypes view of oracle/_ref/libbasisu_ref.so (the compiled, unmodified reference)."""
+
+    def __init__(self):
+        self.lib = ctypes.CDLL(REF_SO)
+        self.lib.ref_init()
+        self.lib.ref_color_cell_compression.restype = ctypes.c_uint64
+        self.lib.ref_compress_image.restype = ctypes.c_void_p
+        self.lib.ref_compress_image.argtypes = [ctypes.c_uint32, ctypes.c_void_p, ctypes.c_uint32, ctypes.c_uint32, ctypes.c_uint32, ctypes.c_float, ctypes.c_void_p]
+        self.lib.ref_free.argtypes = [ctypes.c_void_p]
+        self.lib.ref_uastc_rdo.argtypes = [ctypes.c_uint32, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_float, ctypes.c_uint32, ctypes.c_float, ctypes.c_float, ctypes.c_float, ctypes.c_float, ctypes.c_uint32, ctypes.c_uint32, ctypes.c_uint32]
+
+    def encode_uastc(self, blocks, flags, threads=8):
+        blocks = np.ascontiguousarray(blocks, np.uint8)
+        out = np.zeros((blocks.shape[0], 16), np.uint8)
+        self.lib.ref_encode_uastc_blocks(_ptr(blocks), ctypes.c_uint32(blocks.shape[0]), _ptr(out), ctypes.c_uint32(flags), ctypes.c_uint32(threads))
+        return out
+
+    def unpack_uastc(self, ublocks):
+        ublocks = np.ascontiguousarray(ublocks, np.uint8)
+        out = np.zeros((ublocks.shape[0], 64), np.uint8)
+        ok = self.lib.ref_unpack_uastc_blocks(_ptr(ublocks), ctypes.c_uint32(ublocks.shape[0]), _ptr(out))
+        assert ok
+        return out
+
+    def ccc(self, px, wtab, rng, has_alpha, uber, ls):
+        px = np.ascontiguousarray(px, np.uint8)
+        lo = np.zeros(4, np.uint8); hi = np.zeros(4, np.uint8); sel = np.zeros(16, np.uint8)
+        err = self.lib.ref_color_cell_compression(_ptr(px), ctypes.c_uint32(px.shape[0]), ctypes.c_uint32(wtab), ctypes.c_uint32(rng), ctypes.c_uint32(has_alpha), ctypes.c_uint32(uber), ctypes.c_uint32(ls), _ptr(lo), _ptr(hi), _ptr(sel))
+        return err, lo, hi, sel[:px.shape[0]]
+
+    def compress_image(self, fmt, img, flags_and_quality, rdo_quality=0.0):
+        img = np.ascontiguousarray(img, np.uint8)
+        size = ctypes.c_size_t(0)
+        p = self.lib.ref_compress_image(fmt, _ptr(img), img.shape[1], img.shape[0], flags_and_quality, ctypes.c_float(rdo_quality), ctypes.byref(size))
+        assert p
+        data = ctypes.string_at(p, size.value)
+        self.lib.ref_free(p)
+        return data
+
+
+class Emu:
+    """ctypes view of the host-emulation build of the device code."""
+
+    def __init__(self):
+        self.lib = ctypes.CDLL(EMU_SO)
+        self.lib.emu_color_cell_compression.restype = ctypes.c_uint64
+
+    def encode_uastc(self, blocks, flags, threads=8):
+        blocks = np.ascontiguousarray(blocks, np.uint8)
+        out = np.zeros((blocks.shape[0], 16), np.uint8)
+        self.lib.emu_encode_uastc_blocks(_ptr(blocks), ctypes.c_uint32(blocks.shape[0]), _ptr(out), ctypes.c_uint32(flags), ctypes.c_uint32(threads))
+        return out
+
+    def ccc(self, px, wtab, rng, has_alpha, uber, ls):
+        px = np.ascontiguousarray(px, np.uint8)
+        lo = np.zeros(4, np.uint8); hi = np.zeros(4, np.uint8); sel = np.zeros(16, np.uint8)
+        err = self.lib.emu_color_cell_compression(_ptr(px), ctypes.c_uint32(px.shape[0]), ctypes.c_uint32(wtab), ctypes.c_uint32(rng), ctypes.c_uint32(has_alpha), ctypes.c_uint32(uber), ctypes.c_uint32(ls), _ptr(lo), _ptr(hi), _ptr(sel))
+        return err, lo, hi, sel[:px.shape[0]]
+
+
+def uastc_fields(ref, block16):
+    """Human-readable field dump of one packed UASTC block via the reference unpacker (diagnostics)."""
+    out = np.zeros(61, np.uint8)
+    b = np.ascontiguousarray(block16, np.uint8)
+    ok = ref.lib.ref_uastc_fields(_ptr(b), _ptr(out))
+    if not ok:
+        return None
+    names = ["mode", "pattern", "bc1h0", "bc1h1", "flip", "diff", "inten0", "inten1", "bias", "etc2", "ccs"]
+    d = {n: int(out[i]) for i, n in enumerate(names)}
+    d["ep"] = out[11:29].tolist()
+    d["w"] = out[29:61].tolist()
+    return d
