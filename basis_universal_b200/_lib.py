@@ -1,0 +1,61 @@
+"""ctypes binding of libbasisu_b200.so -- the same C ABI (include/basisu_b200.h) a C++ host links against.
+There is no CPU fallback: a missing library or missing GPU raises."""
+import ctypes
+import os
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libbasisu_b200.so")
+
+_lib = None
+
+
+class B200Error(RuntimeError):
+    pass
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise B200Error(f"{LIB_PATH} is missing: build it with `python -m basis_universal_b200.build` (there is no CPU fallback)")
+        L = ctypes.CDLL(LIB_PATH)
+        vp, u32, i32 = ctypes.c_void_p, ctypes.c_uint32, ctypes.c_int
+        L.b200_device_count.restype = i32
+        L.b200_create_context.restype = vp
+        L.b200_create_context.argtypes = [i32]
+        L.b200_destroy_context.argtypes = [vp]
+        L.b200_last_error.restype = ctypes.c_char_p
+        L.b200_last_error.argtypes = [vp]
+        L.b200_last_kernel_ms.restype = ctypes.c_float
+        L.b200_last_kernel_ms.argtypes = [vp]
+        L.b200_last_launch_count.restype = u32
+        L.b200_last_launch_count.argtypes = [vp]
+        for name in ("b200_uastc_encode_blocks", "b200_uastc_encode_blocks_device"):
+            f = getattr(L, name)
+            f.restype = i32
+            f.argtypes = [vp, vp, u32, vp, u32]
+        L.b200_uastc_rdo.restype = i32
+        L.b200_uastc_rdo.argtypes = [vp, u32, vp, vp, vp, u32, u32]
+        L.b200_etc1s_set_pixel_blocks.restype = i32
+        L.b200_etc1s_set_pixel_blocks.argtypes = [vp, u32, vp]
+        L.b200_etc1s_encode_blocks.restype = i32
+        L.b200_etc1s_encode_blocks.argtypes = [vp, vp, i32, u32]
+        L.b200_etc1s_encode_pixel_clusters.restype = i32
+        L.b200_etc1s_encode_pixel_clusters.argtypes = [vp, vp, u32, vp, ctypes.c_uint64, vp, vp, i32, u32]
+        L.b200_etc1s_refine_endpoint_clusterization.restype = i32
+        L.b200_etc1s_refine_endpoint_clusterization.argtypes = [vp, vp, u32, vp, vp, vp, i32]
+        L.b200_etc1s_find_optimal_selector_clusters_for_each_block.restype = i32
+        L.b200_etc1s_find_optimal_selector_clusters_for_each_block.argtypes = [vp, vp, u32, vp, vp, vp, i32]
+        L.b200_etc1s_determine_selectors.restype = i32
+        L.b200_etc1s_determine_selectors.argtypes = [vp, vp, vp, i32]
+        _lib = L
+    return _lib
+
+
+EXPORTS = [
+    "b200_device_count", "b200_create_context", "b200_destroy_context", "b200_last_error",
+    "b200_uastc_encode_blocks", "b200_uastc_encode_blocks_device", "b200_uastc_rdo",
+    "b200_etc1s_set_pixel_blocks", "b200_etc1s_encode_blocks", "b200_etc1s_encode_pixel_clusters",
+    "b200_etc1s_refine_endpoint_clusterization", "b200_etc1s_find_optimal_selector_clusters_for_each_block",
+    "b200_etc1s_determine_selectors", "b200_last_kernel_ms", "b200_last_launch_count",
+]

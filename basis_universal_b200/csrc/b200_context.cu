@@ -1,0 +1,50 @@
+// b200_context.cu -- context lifetime and error reporting for libbasisu_b200.so (include/basisu_b200.h).
+#include "b200_internal.h"
+
+static char g_create_err[256] = "";
+
+extern "C" int b200_device_count(void)
+{
+	int n = 0;
+	const cudaError_t e = cudaGetDeviceCount(&n);
+	if (e != cudaSuccess) { snprintf(g_create_err, sizeof(g_create_err), "cudaGetDeviceCount: %s", cudaGetErrorString(e)); return -1; }
+	return n;
+}
+
+extern "C" b200_context* b200_create_context(int device_index)
+{
+	const int n = b200_device_count();
+	if (n <= 0) { if (n == 0) snprintf(g_create_err, sizeof(g_create_err), "no CUDA device: libbasisu_b200 has no CPU fallback"); return nullptr; }
+	if (device_index < 0 || device_index >= n) { snprintf(g_create_err, sizeof(g_create_err), "device index %d out of range (0..%d)", device_index, n - 1); return nullptr; }
+	cudaError_t e = cudaSetDevice(device_index);
+	if (e != cudaSuccess) { snprintf(g_create_err, sizeof(g_create_err), "cudaSetDevice: %s", cudaGetErrorString(e)); return nullptr; }
+	b200_context* ctx = new b200_context();
+	memset(ctx, 0, sizeof(*ctx));
+	ctx->device = device_index;
+	if ((e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking)) != cudaSuccess ||
+		(e = cudaEventCreate(&ctx->ev0)) != cudaSuccess || (e = cudaEventCreate(&ctx->ev1)) != cudaSuccess)
+	{
+		snprintf(g_create_err, sizeof(g_create_err), "stream/event creation: %s", cudaGetErrorString(e));
+		delete ctx;
+		return nullptr;
+	}
+	return ctx;
+}
+
+extern "C" void b200_destroy_context(b200_context* ctx)
+{
+	if (!ctx) return;
+	cudaSetDevice(ctx->device);
+	cudaStreamSynchronize(ctx->stream);
+	void* bufs[] = { ctx->d_in, ctx->d_out, ctx->d_meta, ctx->d_cands, ctx->d_slots, ctx->d_etc_blocks };
+	for (void* p : bufs) if (p) cudaFree(p);
+	for (void* p : ctx->d_aux) if (p) cudaFree(p);
+	cudaEventDestroy(ctx->ev0);
+	cudaEventDestroy(ctx->ev1);
+	cudaStreamDestroy(ctx->stream);
+	delete ctx;
+}
+
+extern "C" const char* b200_last_error(const b200_context* ctx) { return ctx ? ctx->err : g_create_err; }
+extern "C" float b200_last_kernel_ms(const b200_context* ctx) { return ctx ? ctx->last_ms : 0.0f; }
+extern "C" uint32_t b200_last_launch_count(const b200_context* ctx) { return ctx ? ctx->launches : 0; }

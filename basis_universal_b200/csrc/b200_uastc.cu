@@ -1,0 +1,202 @@
+// b200_uastc.cu -- UASTC LDR 4x4 block encoder kernels for sm_100a and their C-ABI entry points.
+//
+// Pipeline, all buffers resident in HBM:
+//   k_classify_rank   1 thread / block   : 128-bit loads of the 64 B block, class bits, solid-colour fast path (packs the
+//                                          block directly), partition ranking for the estimated-partition modes
+//   k_candidates      1 thread / (block, candidate slot) : endpoint/selector fit of one (mode, variant), UASTC decode error,
+//                                          BC7-transcode error -> 64 B candidate record
+//   k_finish          1 thread / block   : windowed arg-min over the block's candidates, BC1/ETC2-EAC/ETC1 hints, bit packing
+// Build: nvcc -gencode arch=compute_100a,code=sm_100a --fmad=false (no FMA contraction: the reference is built for baseline
+// x86-64, and bit-exactness includes its float/double rounding; SURVEY.md section 7 hard part 1).
+#include "b200_internal.h"
+#include "bu_slots.h"
+
+using namespace bu;
+
+__device__ const bu_tables d_tables =
+#include "uastc_tables.inc"
+;
+
+struct block_meta { block_class k; block_ranks ranks; }; // 16 B
+
+__device__ __forceinline__ void load_block(const uint4* __restrict__ blocks, uint32_t i, uint32_t* px)
+{
+	const uint4* p = blocks + (size_t)i * 4;
+#pragma unroll
+	for (int r = 0; r < 4; r++)
+	{
+		const uint4 v = __ldg(p + r);
+		px[r * 4 + 0] = v.x; px[r * 4 + 1] = v.y; px[r * 4 + 2] = v.z; px[r * 4 + 3] = v.w;
+	}
+}
+
+__global__ void __launch_bounds__(128) k_classify_rank(const uint4* __restrict__ blocks, uint32_t n, block_meta* __restrict__ meta, uint4* __restrict__ out, level_opts o)
+{
+	const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= n) return;
+	uint32_t px[16];
+	load_block(blocks, i, px);
+	block_meta m;
+	m.k = classify_block(px, o.la_only_transparent != 0);
+	if (m.k.solid)
+	{
+		uint8_t b[16];
+		pack_solid_block(&d_tables, px[0], b);
+		uint4 v;
+		v.x = b[0] | (b[1] << 8) | (b[2] << 16) | ((uint32_t)b[3] << 24);
+		v.y = b[4] | (b[5] << 8) | (b[6] << 16) | ((uint32_t)b[7] << 24);
+		v.z = b[8] | (b[9] << 8) | (b[10] << 16) | ((uint32_t)b[11] << 24);
+		v.w = b[12] | (b[13] << 8) | (b[14] << 16) | ((uint32_t)b[15] << 24);
+		out[i] = v;
+		for (int j = 0; j < 12; j++) m.ranks.r[j] = 0;
+	}
+	else
+		rank_block(&d_tables, o, m.k, px, m.ranks);
+	meta[i] = m;
+}
+
+// gridDim.y = slot index; candidates are stored slot-major so a warp writes 32 consecutive 64 B records.
+__global__ void __launch_bounds__(128) k_candidates(const uint4* __restrict__ blocks, uint32_t n, const block_meta* __restrict__ meta,
+	candidate* __restrict__ cands, const slot_desc* __restrict__ slots, uint32_t first_slot, level_opts o)
+{
+	const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= n) return;
+	const uint32_t si = first_slot + blockIdx.y;
+	const slot_desc s = slots[si];
+	const block_meta m = meta[i];
+	candidate* dst = cands + (size_t)si * n + i;
+	if (m.k.solid || !slot_active(s, m.k, o))
+	{
+		reinterpret_cast<uint32_t*>(dst)[0] = 0; // valid = 0
+		return;
+	}
+	uint32_t px[16];
+	load_block(blocks, i, px);
+	candidate c;
+	run_slot(&d_tables, o, s, m.k, m.ranks, px, c);
+	const uint4* src = reinterpret_cast<const uint4*>(&c);
+	uint4* d4 = reinterpret_cast<uint4*>(dst);
+	d4[0] = src[0]; d4[1] = src[1]; d4[2] = src[2]; d4[3] = src[3];
+}
+
+__global__ void __launch_bounds__(128) k_finish(const uint4* __restrict__ blocks, uint32_t n, const block_meta* __restrict__ meta,
+	const candidate* __restrict__ cands, uint32_t nslots, uint4* __restrict__ out, level_opts o, int level, uint32_t flags)
+{
+	const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= n) return;
+	const block_meta m = meta[i];
+	if (m.k.solid) return;
+
+	uint32_t ue[MAX_SLOTS], be[MAX_SLOTS];
+	uint8_t modes[MAX_SLOTS], idx[MAX_SLOTS];
+	uint32_t cnt = 0;
+	for (uint32_t s = 0; s < nslots; s++)
+	{
+		const candidate* c = cands + (size_t)s * n + i;
+		const uint32_t head = reinterpret_cast<const uint32_t*>(c)[0];
+		if (!(head >> 24)) continue; // valid byte
+		ue[cnt] = c->uastc_err; be[cnt] = c->bc7_err; modes[cnt] = (uint8_t)(head & 0xFF); idx[cnt] = (uint8_t)s;
+		cnt++;
+	}
+	const int best = select_candidate(cnt, ue, be, modes, flags);
+
+	candidate c;
+	{
+		const uint4* src = reinterpret_cast<const uint4*>(cands + (size_t)idx[best] * n + i);
+		uint4* d4 = reinterpret_cast<uint4*>(&c);
+		d4[0] = src[0]; d4[1] = src[1]; d4[2] = src[2]; d4[3] = src[3];
+	}
+	uint32_t px[16];
+	load_block(blocks, i, px);
+	uint8_t b[16];
+	finish_block(&d_tables, o, level, flags, px, c, b);
+	uint4 v;
+	v.x = b[0] | (b[1] << 8) | (b[2] << 16) | ((uint32_t)b[3] << 24);
+	v.y = b[4] | (b[5] << 8) | (b[6] << 16) | ((uint32_t)b[7] << 24);
+	v.z = b[8] | (b[9] << 8) | (b[10] << 16) | ((uint32_t)b[11] << 24);
+	v.w = b[12] | (b[13] << 8) | (b[14] << 16) | ((uint32_t)b[15] << 24);
+	out[i] = v;
+}
+
+// ---- host side -----------------------------------------------------------------------------------------------------------
+
+static bool uastc_encode_chunk(b200_context* ctx, const uint4* dBlocks, uint32_t n, uint4* dOut, uint32_t flags)
+{
+	const int level = clampi((int)(flags & 7), 0, 4);
+	const level_opts o = make_level_opts(level);
+	slot_desc slots[MAX_SLOTS];
+	const uint32_t nslots = build_slots(o, slots);
+
+	if (!ctx->reserve(ctx->d_meta, ctx->meta_cap, (size_t)n * sizeof(block_meta))) return false;
+	if (!ctx->reserve(ctx->d_cands, ctx->cands_cap, (size_t)n * nslots * sizeof(candidate))) return false;
+	if (!ctx->reserve(ctx->d_slots, ctx->slots_cap, sizeof(slot_desc) * MAX_SLOTS)) return false;
+	B200_CUDA_OK(ctx, cudaMemcpyAsync(ctx->d_slots, slots, sizeof(slot_desc) * nslots, cudaMemcpyHostToDevice, ctx->stream));
+
+	const uint32_t tpb = 128, gx = (n + tpb - 1) / tpb;
+	block_meta* meta = static_cast<block_meta*>(ctx->d_meta);
+	candidate* cands = static_cast<candidate*>(ctx->d_cands);
+
+	k_classify_rank<<<gx, tpb, 0, ctx->stream>>>(dBlocks, n, meta, dOut, o);
+	ctx->launches++;
+	// gridDim.y is limited to 65535; nslots <= 176.
+	k_candidates<<<dim3(gx, nslots), tpb, 0, ctx->stream>>>(dBlocks, n, meta, cands, static_cast<const slot_desc*>(ctx->d_slots), 0, o);
+	ctx->launches++;
+	k_finish<<<gx, tpb, 0, ctx->stream>>>(dBlocks, n, meta, cands, nslots, dOut, o, level, flags);
+	ctx->launches++;
+	B200_CUDA_OK(ctx, cudaGetLastError());
+	return true;
+}
+
+// Blocks per pass: bounds the candidate scratch (slots * 64 B per block) while keeping every launch many waves deep.
+static uint32_t uastc_chunk_blocks(uint32_t flags)
+{
+	const int level = clampi((int)(flags & 7), 0, 4);
+	return (level == 4) ? (1u << 18) : (1u << 20);
+}
+
+extern "C" int b200_uastc_encode_blocks_device(b200_context* ctx, const void* dBlocks, uint32_t num_blocks, void* dOut, uint32_t flags)
+{
+	if (!ctx) return 0;
+	if (!ctx->activate()) return 0;
+	ctx->launches = 0;
+	if (!num_blocks) { ctx->last_ms = 0; return 1; }
+	B200_CUDA_OK(ctx, cudaEventRecord(ctx->ev0, ctx->stream));
+	const uint32_t chunk = uastc_chunk_blocks(flags);
+	for (uint32_t first = 0; first < num_blocks; first += chunk)
+	{
+		const uint32_t n = (num_blocks - first < chunk) ? (num_blocks - first) : chunk;
+		if (!uastc_encode_chunk(ctx, static_cast<const uint4*>(dBlocks) + (size_t)first * 4, n, static_cast<uint4*>(dOut) + first, flags)) return 0;
+	}
+	B200_CUDA_OK(ctx, cudaEventRecord(ctx->ev1, ctx->stream));
+	B200_CUDA_OK(ctx, cudaStreamSynchronize(ctx->stream));
+	B200_CUDA_OK(ctx, cudaEventElapsedTime(&ctx->last_ms, ctx->ev0, ctx->ev1));
+	return 1;
+}
+
+extern "C" int b200_uastc_encode_blocks(b200_context* ctx, const void* pBlocks, uint32_t num_blocks, void* pOut, uint32_t flags)
+{
+	if (!ctx) return 0;
+	if (!ctx->activate()) return 0;
+	ctx->launches = 0;
+	if (!num_blocks) { ctx->last_ms = 0; return 1; }
+	if (!pBlocks || !pOut) { ctx->fail("b200_uastc_encode_blocks: null buffer"); return 0; }
+	if (!ctx->reserve(ctx->d_in, ctx->in_cap, (size_t)num_blocks * 64)) return 0;
+	if (!ctx->reserve(ctx->d_out, ctx->out_cap, (size_t)num_blocks * 16)) return 0;
+
+	float total_ms = 0;
+	const uint32_t chunk = uastc_chunk_blocks(flags);
+	// Copies and kernels are issued chunk by chunk on one stream; the copy engine runs ahead of / behind the SMs.
+	B200_CUDA_OK(ctx, cudaMemcpyAsync(ctx->d_in, pBlocks, (size_t)num_blocks * 64, cudaMemcpyHostToDevice, ctx->stream));
+	B200_CUDA_OK(ctx, cudaEventRecord(ctx->ev0, ctx->stream));
+	for (uint32_t first = 0; first < num_blocks; first += chunk)
+	{
+		const uint32_t n = (num_blocks - first < chunk) ? (num_blocks - first) : chunk;
+		if (!uastc_encode_chunk(ctx, static_cast<const uint4*>(ctx->d_in) + (size_t)first * 4, n, static_cast<uint4*>(ctx->d_out) + first, flags)) return 0;
+	}
+	B200_CUDA_OK(ctx, cudaEventRecord(ctx->ev1, ctx->stream));
+	B200_CUDA_OK(ctx, cudaMemcpyAsync(pOut, ctx->d_out, (size_t)num_blocks * 16, cudaMemcpyDeviceToHost, ctx->stream));
+	B200_CUDA_OK(ctx, cudaStreamSynchronize(ctx->stream));
+	B200_CUDA_OK(ctx, cudaEventElapsedTime(&total_ms, ctx->ev0, ctx->ev1));
+	ctx->last_ms = total_ms;
+	return 1;
+}

@@ -1,0 +1,109 @@
+/* basisu_b200.h -- C ABI of libbasisu_b200.so: the B200 (sm_100a) implementation of basis_universal's per-block
+ * encode hot path (UASTC LDR 4x4 and the ETC1S frontend's per-block stages).
+ *
+ * Plain pointers and sizes only; no C++ or torch types cross this boundary.  Every entry point names the reference
+ * interface it replaces (paths relative to the BinomialLLC/basis_universal tree); INTEGRATION.md shows the call-site
+ * patches.  Block layouts are the reference's own:
+ *   source block  = basisu::pixel_block, 64 B, [y][x] RGBA8, R first          (encoder/basisu_enc.h:4156)
+ *   UASTC block   = basist::uastc_block, 16 B                                   (transcoder/basisu_transcoder_uastc.h:198)
+ *   ETC1 block    = basisu::etc_block, 8 B, big-endian bitfield                 (encoder/basisu_etc.h:91)
+ *
+ * Error model mirrors the reference's OpenCL seam (encoder/basisu_opencl.h:24-141): functions return 1 on success and
+ * 0 on failure; on failure the caller may fall back to its own CPU code.  b200_last_error() describes the failure.
+ * There is NO CPU fallback inside this library: without a usable CUDA device every call fails loudly.
+ */
+#ifndef BASISU_B200_H
+#define BASISU_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct b200_context b200_context;
+
+/* Number of usable CUDA devices (>= 0), or -1 if the CUDA runtime cannot be initialised.
+ * Replaces: basisu::opencl_init / opencl_is_available (encoder/basisu_opencl.h:24-27). */
+int b200_device_count(void);
+
+/* One context = one device + one stream + its scratch buffers; use one per host thread.
+ * Replaces: opencl_create_context / opencl_destroy_context (encoder/basisu_opencl.h:30-33). */
+b200_context* b200_create_context(int device_index);
+void b200_destroy_context(b200_context* ctx);
+
+/* Human-readable description of the last failure on this context (never NULL). ctx may be NULL for creation failures. */
+const char* b200_last_error(const b200_context* ctx);
+
+/* ---- UASTC LDR 4x4 ------------------------------------------------------------------------------------------------ */
+
+/* Encodes num_blocks source blocks to UASTC. Batch form of
+ *     void basisu::encode_uastc(const uint8_t* pRGBAPixels, basist::uastc_block& out, uint32_t flags)
+ * (encoder/basisu_uastc_enc.h:68), replacing the job-pool loop at encoder/basisu_comp.cpp:2006-2064.
+ * `flags` is the reference's flag word unchanged: low 3 bits = cPackUASTCLevel*, plus the cPackUASTCFavor... and cPackUASTCETC1... bits
+ * (encoder/basisu_uastc_enc.h:24-63).  Output bytes are bit-identical to the reference's.
+ * pBlocks / pOut are HOST pointers; copies to and from the device happen inside the call. */
+int b200_uastc_encode_blocks(b200_context* ctx, const void* pBlocks, uint32_t num_blocks, void* pOut, uint32_t flags);
+
+/* Same, with DEVICE pointers (inputs already resident in HBM, outputs left there). Work is enqueued on the context's
+ * stream and the call returns after the stream has been synchronised. */
+int b200_uastc_encode_blocks_device(b200_context* ctx, const void* dBlocks, uint32_t num_blocks, void* dOut, uint32_t flags);
+
+/* RDO post-pass, in place. Same contract as
+ *     bool basisu::uastc_rdo(uint32_t num_blocks, basist::uastc_block* pBlocks, const color_rgba* pBlock_pixels,
+ *                            const uastc_rdo_params& params, uint32_t flags, job_pool*, uint32_t total_jobs)
+ * (encoder/basisu_uastc_enc.h:139; called at encoder/basisu_comp.cpp:2076). `total_jobs` chunks the block range
+ * exactly as the reference does (uastc_enc.cpp:4116-4154), because the result depends on it. */
+typedef struct b200_uastc_rdo_params
+{
+	uint32_t lz_dict_size;                /* uastc_rdo_params::m_lz_dict_size */
+	float lambda;                         /* m_lambda */
+	float max_allowed_rms_increase_ratio; /* m_max_allowed_rms_increase_ratio */
+	float skip_block_rms_thresh;          /* m_skip_block_rms_thresh */
+	uint32_t endpoint_refinement;         /* m_endpoint_refinement */
+	float max_smooth_block_std_dev;       /* m_max_smooth_block_std_dev */
+	float smooth_block_max_error_scale;   /* m_smooth_block_max_error_scale */
+	uint32_t lz_literal_cost;             /* m_lz_literal_cost */
+} b200_uastc_rdo_params;
+int b200_uastc_rdo(b200_context* ctx, uint32_t num_blocks, void* pBlocks, const void* pBlock_pixels,
+	const b200_uastc_rdo_params* params, uint32_t flags, uint32_t total_jobs);
+
+/* ---- ETC1S frontend per-block stages: the reference's existing GPU seam, symbol for symbol ------------------------------ */
+/* Packed argument structs are the reference's (encoder/basisu_opencl.h:36-135), restated in C. */
+
+#pragma pack(push, 1)
+typedef struct b200_pixel_cluster { uint64_t total_pixels; uint64_t first_pixel_index; } b200_pixel_cluster; /* cl_pixel_cluster, opencl.h:49 */
+typedef struct b200_block_info { uint16_t first_cluster_ofs; uint16_t num_clusters; uint16_t cur_cluster_index; uint8_t cur_cluster_etc_inten; } b200_block_info; /* cl_block_info_struct, opencl.h:70 */
+typedef struct b200_endpoint_cluster { uint8_t unscaled_r, unscaled_g, unscaled_b, unscaled_a; uint8_t etc_inten; uint16_t cluster_index; } b200_endpoint_cluster; /* cl_endpoint_cluster_struct, opencl.h:81 */
+typedef struct b200_fosc_block { uint8_t etc_r, etc_g, etc_b, etc_a; uint32_t first_selector; uint32_t num_selectors; } b200_fosc_block; /* fosc_block_struct, opencl.h:104 */
+typedef struct b200_fosc_selector { uint32_t packed_selectors; } b200_fosc_selector; /* fosc_selector_struct, opencl.h:98 */
+#pragma pack(pop)
+
+/* opencl_set_pixel_blocks (opencl.h:46): uploads the slice's source blocks once; later calls read them from HBM. */
+int b200_etc1s_set_pixel_blocks(b200_context* ctx, uint32_t total_blocks, const void* pPixel_blocks);
+/* opencl_encode_etc1s_blocks (opencl.h:47): per-block ETC1S optimisation, total_perms in {4,16,64,165}. */
+int b200_etc1s_encode_blocks(b200_context* ctx, void* pOutput_blocks, int perceptual, uint32_t total_perms);
+/* opencl_encode_etc1s_pixel_clusters (opencl.h:58). */
+int b200_etc1s_encode_pixel_clusters(b200_context* ctx, void* pOutput_blocks, uint32_t total_clusters, const b200_pixel_cluster* pClusters,
+	uint64_t total_pixels, const void* pPixels, const uint32_t* pPixel_weights, int perceptual, uint32_t total_perms);
+/* opencl_refine_endpoint_clusterization (opencl.h:90). */
+int b200_etc1s_refine_endpoint_clusterization(b200_context* ctx, const b200_block_info* pPixel_block_info, uint32_t total_clusters,
+	const b200_endpoint_cluster* pCluster_info, const uint32_t* pSorted_block_indices, uint32_t* pOutput_cluster_indices, int perceptual);
+/* opencl_find_optimal_selector_clusters_for_each_block (opencl.h:113). */
+int b200_etc1s_find_optimal_selector_clusters_for_each_block(b200_context* ctx, const b200_fosc_block* pInput_block_info, uint32_t total_input_selectors,
+	const b200_fosc_selector* pInput_selectors, const uint32_t* pSelector_cluster_indices, uint32_t* pOutput_selector_cluster_indices, int perceptual);
+/* opencl_determine_selectors (opencl.h:137). */
+int b200_etc1s_determine_selectors(b200_context* ctx, const void* pInput_etc_color5_and_inten, void* pOutput_blocks, int perceptual);
+
+/* ---- instrumentation ------------------------------------------------------------------------------------------------- */
+
+/* Device time in milliseconds of the kernels of the last successful encode call on this context (CUDA events on the
+ * context's stream), and the number of kernel launches it issued. */
+float b200_last_kernel_ms(const b200_context* ctx);
+uint32_t b200_last_launch_count(const b200_context* ctx);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* BASISU_B200_H */
