@@ -22,7 +22,8 @@ extern "C" b200_context* b200_create_context(int device_index)
 	memset(ctx, 0, sizeof(*ctx));
 	ctx->device = device_index;
 	if ((e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking)) != cudaSuccess ||
-		(e = cudaEventCreate(&ctx->ev0)) != cudaSuccess || (e = cudaEventCreate(&ctx->ev1)) != cudaSuccess)
+		(e = cudaEventCreate(&ctx->ev0)) != cudaSuccess || (e = cudaEventCreate(&ctx->ev1)) != cudaSuccess ||
+		(e = cudaEventCreate(&ctx->ev_t0)) != cudaSuccess || (e = cudaEventCreate(&ctx->ev_t1)) != cudaSuccess)
 	{
 		snprintf(g_create_err, sizeof(g_create_err), "stream/event creation: %s", cudaGetErrorString(e));
 		delete ctx;
@@ -41,6 +42,9 @@ extern "C" void b200_destroy_context(b200_context* ctx)
 	for (void* p : ctx->d_aux) if (p) cudaFree(p);
 	cudaEventDestroy(ctx->ev0);
 	cudaEventDestroy(ctx->ev1);
+	cudaEventDestroy(ctx->ev_t0);
+	cudaEventDestroy(ctx->ev_t1);
+	for (uint32_t i = 0; i < ctx->stage_ev_count; i++) cudaEventDestroy(ctx->stage_ev[i]);
 	cudaStreamDestroy(ctx->stream);
 	delete ctx;
 }
@@ -48,3 +52,22 @@ extern "C" void b200_destroy_context(b200_context* ctx)
 extern "C" const char* b200_last_error(const b200_context* ctx) { return ctx ? ctx->err : g_create_err; }
 extern "C" float b200_last_kernel_ms(const b200_context* ctx) { return ctx ? ctx->last_ms : 0.0f; }
 extern "C" uint32_t b200_last_launch_count(const b200_context* ctx) { return ctx ? ctx->launches : 0; }
+
+extern "C" float b200_last_stage_ms(const b200_context* ctx, uint32_t stage) { return (ctx && stage < 3) ? ctx->stage_ms[stage] : 0.0f; }
+
+extern "C" int b200_timer_start(b200_context* ctx)
+{
+	if (!ctx || !ctx->activate()) return 0;
+	B200_CUDA_OK(ctx, cudaEventRecord(ctx->ev_t0, ctx->stream));
+	return 1;
+}
+
+extern "C" float b200_timer_stop_ms(b200_context* ctx)
+{
+	if (!ctx || !ctx->activate()) return -1.0f;
+	float ms = -1.0f;
+	if (cudaEventRecord(ctx->ev_t1, ctx->stream) != cudaSuccess) return -1.0f;
+	if (cudaEventSynchronize(ctx->ev_t1) != cudaSuccess) return -1.0f;
+	if (cudaEventElapsedTime(&ms, ctx->ev_t0, ctx->ev_t1) != cudaSuccess) return -1.0f;
+	return ms;
+}

@@ -10,7 +10,9 @@ struct b200_context
 {
 	int device;
 	cudaStream_t stream;
-	cudaEvent_t ev0, ev1;
+	cudaEvent_t ev0, ev1, ev_t0, ev_t1;
+	cudaEvent_t stage_ev[64 * 4]; uint32_t stage_ev_count, stage_ev_used; // 4 events per chunk: before k0, k1, k2, after k2
+	float stage_ms[3];
 	float last_ms;
 	uint32_t launches;
 	char err[256];
@@ -33,6 +35,28 @@ struct b200_context
 		cudaError_t e = cudaSetDevice(device);
 		if (e != cudaSuccess) { fail_cuda("cudaSetDevice", e); return false; }
 		return true;
+	}
+	cudaEvent_t* chunk_events() // 4 events for the next chunk, or nullptr when the pool is exhausted
+	{
+		if (stage_ev_used + 4 > 64 * 4) return nullptr;
+		while (stage_ev_count < stage_ev_used + 4)
+		{
+			if (cudaEventCreate(&stage_ev[stage_ev_count]) != cudaSuccess) return nullptr;
+			stage_ev_count++;
+		}
+		cudaEvent_t* e = stage_ev + stage_ev_used;
+		stage_ev_used += 4;
+		return e;
+	}
+	void collect_stage_times()
+	{
+		stage_ms[0] = stage_ms[1] = stage_ms[2] = 0;
+		for (uint32_t c = 0; c + 4 <= stage_ev_used; c += 4)
+			for (int s = 0; s < 3; s++)
+			{
+				float ms = 0;
+				if (cudaEventElapsedTime(&ms, stage_ev[c + s], stage_ev[c + s + 1]) == cudaSuccess) stage_ms[s] += ms;
+			}
 	}
 	bool reserve(void*& p, size_t& cap, size_t bytes)
 	{

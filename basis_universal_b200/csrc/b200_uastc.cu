@@ -136,13 +136,18 @@ static bool uastc_encode_chunk(b200_context* ctx, const uint4* dBlocks, uint32_t
 	block_meta* meta = static_cast<block_meta*>(ctx->d_meta);
 	candidate* cands = static_cast<candidate*>(ctx->d_cands);
 
+	cudaEvent_t* ev = ctx->chunk_events();
+	if (ev) cudaEventRecord(ev[0], ctx->stream);
 	k_classify_rank<<<gx, tpb, 0, ctx->stream>>>(dBlocks, n, meta, dOut, o);
 	ctx->launches++;
+	if (ev) cudaEventRecord(ev[1], ctx->stream);
 	// gridDim.y is limited to 65535; nslots <= 176.
 	k_candidates<<<dim3(gx, nslots), tpb, 0, ctx->stream>>>(dBlocks, n, meta, cands, static_cast<const slot_desc*>(ctx->d_slots), 0, o);
 	ctx->launches++;
+	if (ev) cudaEventRecord(ev[2], ctx->stream);
 	k_finish<<<gx, tpb, 0, ctx->stream>>>(dBlocks, n, meta, cands, nslots, dOut, o, level, flags);
 	ctx->launches++;
+	if (ev) cudaEventRecord(ev[3], ctx->stream);
 	B200_CUDA_OK(ctx, cudaGetLastError());
 	return true;
 }
@@ -159,6 +164,7 @@ extern "C" int b200_uastc_encode_blocks_device(b200_context* ctx, const void* dB
 	if (!ctx) return 0;
 	if (!ctx->activate()) return 0;
 	ctx->launches = 0;
+	ctx->stage_ev_used = 0;
 	if (!num_blocks) { ctx->last_ms = 0; return 1; }
 	B200_CUDA_OK(ctx, cudaEventRecord(ctx->ev0, ctx->stream));
 	const uint32_t chunk = uastc_chunk_blocks(flags);
@@ -170,6 +176,7 @@ extern "C" int b200_uastc_encode_blocks_device(b200_context* ctx, const void* dB
 	B200_CUDA_OK(ctx, cudaEventRecord(ctx->ev1, ctx->stream));
 	B200_CUDA_OK(ctx, cudaStreamSynchronize(ctx->stream));
 	B200_CUDA_OK(ctx, cudaEventElapsedTime(&ctx->last_ms, ctx->ev0, ctx->ev1));
+	ctx->collect_stage_times();
 	return 1;
 }
 
@@ -178,6 +185,7 @@ extern "C" int b200_uastc_encode_blocks(b200_context* ctx, const void* pBlocks, 
 	if (!ctx) return 0;
 	if (!ctx->activate()) return 0;
 	ctx->launches = 0;
+	ctx->stage_ev_used = 0;
 	if (!num_blocks) { ctx->last_ms = 0; return 1; }
 	if (!pBlocks || !pOut) { ctx->fail("b200_uastc_encode_blocks: null buffer"); return 0; }
 	if (!ctx->reserve(ctx->d_in, ctx->in_cap, (size_t)num_blocks * 64)) return 0;
@@ -198,5 +206,6 @@ extern "C" int b200_uastc_encode_blocks(b200_context* ctx, const void* pBlocks, 
 	B200_CUDA_OK(ctx, cudaStreamSynchronize(ctx->stream));
 	B200_CUDA_OK(ctx, cudaEventElapsedTime(&total_ms, ctx->ev0, ctx->ev1));
 	ctx->last_ms = total_ms;
+	ctx->collect_stage_times();
 	return 1;
 }

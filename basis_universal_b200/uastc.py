@@ -67,6 +67,22 @@ class Encoder:
     def last_launch_count(self):
         return int(self._lib.b200_last_launch_count(self._ctx))
 
+    def stage_ms(self, stage):
+        return float(self._lib.b200_last_stage_ms(self._ctx, int(stage)))
+
+    def timer_start(self):
+        self._check(self._lib.b200_timer_start(self._ctx), "b200_timer_start")
+
+    def timer_stop_ms(self):
+        ms = float(self._lib.b200_timer_stop_ms(self._ctx))
+        self._check(ms >= 0, "b200_timer_stop_ms")
+        return ms
+
+    def encode_uastc_host_ptr(self, host_in_ptr, num_blocks, host_out_ptr, flags=cPackUASTCLevelDefault):
+        """Host-pointer form for callers that own (ideally pinned) buffers: H2D, kernels and D2H all happen inside the call."""
+        ok = self._lib.b200_uastc_encode_blocks(self._ctx, ctypes.c_void_p(host_in_ptr), int(num_blocks), ctypes.c_void_p(host_out_ptr), int(flags))
+        self._check(ok, "b200_uastc_encode_blocks")
+
     def encode_uastc(self, blocks, flags=cPackUASTCLevelDefault, out=None):
         """blocks: (N, 64) uint8 host array of pixel_blocks -> (N, 16) uint8 UASTC blocks (host). Copies are inside the call."""
         blocks = np.ascontiguousarray(blocks, np.uint8)

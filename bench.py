@@ -1,0 +1,266 @@
+#!/usr/bin/env python
+"""bench.py -- Mtexels/s of the UASTC LDR 4x4 encode hot path (BASELINE.json configs[1]: synthetic 4096x4096 RGBA,
+UASTC level 2) on N B200s, one process per GPU.
+
+  python bench.py --gpus 1 --steps K --warmup W              (N>1: launched by torch.distributed.run, one rank per GPU)
+  python bench.py --impl reference --gpus N --steps K --warmup W   (reference CPU encoder on the host cores, rank 0 only)
+
+A step = one pass of the hot path over one 4096^2 image (1 048 576 blocks) per rank; weak scaling (each rank owns its own
+tile: UASTC blocks are independent, there is no data-path collective).  `value` is device-timed with inputs resident in
+HBM; `e2e` is the same work through the host-pointer C-ABI call (pinned host buffers, H2D + kernels + D2H inside the
+timed region).  `roofline` reports the dominant kernel against the HBM roofline using SURVEY.md 8(d)'s algorithmic
+80 B/block; the kernel is ALU-bound, so the fraction is small by construction.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+IMAGE_DIM = 4096
+LEVEL = 2                      # cPackUASTCLevelDefault
+BLOCKS = (IMAGE_DIM // 4) ** 2
+TEXELS = IMAGE_DIM * IMAGE_DIM
+ALGO_BYTES_PER_BLOCK = 64 + 16  # read 64 B/block, write 16 B/block
+ROTATING_INPUTS = 4            # 4 x 64 MiB distinct inputs > 126 MB L2
+
+
+def synth(n, seed):
+    """SURVEY.md 9.6 generator (same code as tests/util.py; duplicated so bench.py has no test imports)."""
+    rng = np.random.default_rng(seed)
+    y, x = np.mgrid[0:n, 0:n].astype(np.float32)
+    r = 127.5 + 100 * np.sin(x / 97.0) * np.cos(y / 131.0)
+    g = 127.5 + 100 * np.sin((x + y) / 61.0)
+    b = 127.5 + 100 * np.cos(x / 23.0) * np.sin(y / 17.0)
+    rgb = np.stack([r, g, b], -1) + rng.normal(0, 12, size=(n, n, 3)).astype(np.float32)
+    a = 255 * ((np.sin(x / 257.0) * np.sin(y / 311.0)) > -0.3).astype(np.float32)
+    a = np.where(((x // 64 + y // 64) % 7) == 0, 128 + 100 * np.sin(x / 11.0), a)
+    return np.concatenate([rgb, a[..., None]], -1).clip(0, 255).astype(np.uint8)
+
+
+def to_blocks(img):
+    h, w, _ = img.shape
+    return np.ascontiguousarray(img.reshape(h // 4, 4, w // 4, 4, 4).transpose(0, 2, 1, 3, 4).reshape(-1, 64))
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured"
+        except Exception:
+            pass
+    return 6650.0, "fallback"
+
+
+class ClockSampler(threading.Thread):
+    """Samples nvidia-smi clocks / throttle reasons for one GPU while the timed region runs."""
+
+    Q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index = index
+        self.stop_flag = threading.Event()
+        self.samples = []
+
+    def run(self):
+        while not self.stop_flag.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits"],
+                                     capture_output=True, text=True, timeout=5).stdout.strip()
+                f = [s.strip() for s in out.split(",")]
+                if len(f) >= 6:
+                    self.samples.append(f)
+            except Exception:
+                pass
+            self.stop_flag.wait(0.2)
+
+    def summary(self):
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unsampled"]}
+        sm = sorted(int(s[0]) for s in self.samples if s[0].isdigit())
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(s[2 + i].lower().startswith("active") for s in self.samples)]
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": int(self.samples[0][1]) if self.samples[0][1].isdigit() else None,
+                "reasons": reasons, "samples": len(self.samples)}
+
+
+def cpu_reference_run(blocks, threads):
+    """Times the compiled, unmodified reference (oracle/_ref) on `blocks` with `threads` host threads. Returns seconds."""
+    import ctypes
+    so = os.path.join(ROOT, "oracle", "_ref", "libbasisu_ref.so")
+    if not os.path.exists(so):
+        if os.path.isdir("/root/reference/encoder"):
+            subprocess.check_call(["make", "-C", os.path.join(ROOT, "oracle"), "-j8", "ref"], stdout=subprocess.DEVNULL)
+        else:
+            raise RuntimeError("oracle/_ref/libbasisu_ref.so missing and /root/reference not present")
+    lib = ctypes.CDLL(so)
+    lib.ref_init()
+    out = np.empty((blocks.shape[0], 16), np.uint8)
+    t0 = time.perf_counter()
+    lib.ref_encode_uastc_blocks(blocks.ctypes.data_as(ctypes.c_void_p), ctypes.c_uint32(blocks.shape[0]), out.ctypes.data_as(ctypes.c_void_p),
+                                ctypes.c_uint32(LEVEL), ctypes.c_uint32(threads))
+    return time.perf_counter() - t0, out
+
+
+def cpu_sample_blocks(blocks, cores):
+    """Bounded sample of the workload for the CPU arm: ~10-30 core-seconds... scaled so a step stays within a few seconds."""
+    n = blocks.shape[0] if cores >= 32 else blocks.shape[0] // 8
+    return blocks[:n], f"first {n} of {blocks.shape[0]} blocks ({n * 16 / 1e6:.2f} Mtexel) of the synthetic 4096^2 image, seed 1234"
+
+
+def config_dict(world):
+    return {"workload": "synthetic 4096x4096 RGBA8 (SURVEY 9.6 generator, seed 1234+rank), UASTC LDR 4x4 level 2, no RDO",
+            "blocks_per_step_per_gpu": BLOCKS, "texels_per_step_per_gpu": TEXELS,
+            "parallelism": f"{world} independent tile(s), one per GPU, no collective",
+            "l2": f"{ROTATING_INPUTS} rotating 64 MiB inputs (> 126 MB L2) plus 1.8 GB of candidate scratch streamed per step"}
+
+
+def run_reference(args, rank, world):
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    blocks = to_blocks(synth(IMAGE_DIM, 1234))
+    sample, desc = cpu_sample_blocks(blocks, cores)
+    for _ in range(args.warmup):
+        cpu_reference_run(sample[: max(4096, sample.shape[0] // 16)], cores)
+    t = 0.0
+    for _ in range(args.steps):
+        dt, _ = cpu_reference_run(sample, cores)
+        t += dt
+    mtex = sample.shape[0] * 16 * args.steps / 1e6 / t
+    line = {"impl": "reference", "metric": "Mtexels/sec encoded (4K RGBA UASTC LDR level 2)", "value": mtex, "unit": "Mtexel/s",
+            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8/f32/f64", "data": "synthetic",
+            "config": config_dict(args.gpus),
+            "cpu_baseline": {"value": mtex, "unit": "Mtexel/s", "cores": cores, "kind": "reference", "sample": desc},
+            "e2e": {"value": mtex, "unit": "Mtexel/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+def run_gpu(args, rank, local_rank, world):
+    import torch
+    from basis_universal_b200 import uastc
+
+    torch.cuda.set_device(local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist_mod
+        dist = dist_mod
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    enc = uastc.Encoder(local_rank)
+    # Distinct inputs per rank and per rotation slot; device-resident for `value`, pinned host copies for `e2e`.
+    host_in = []
+    for k in range(ROTATING_INPUTS):
+        t = torch.from_numpy(to_blocks(synth(IMAGE_DIM, 1234 + rank + 1000 * k)))
+        host_in.append(t.pin_memory())
+    dev_in = [t.cuda() for t in host_in]
+    dev_out = torch.empty((BLOCKS, 16), dtype=torch.uint8, device="cuda")
+    host_out = torch.empty((BLOCKS, 16), dtype=torch.uint8).pin_memory()
+    torch.cuda.synchronize()
+
+    def barrier():
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- value: inputs resident in HBM --------------------------------------------------------------------------
+    for w in range(args.warmup):
+        enc.encode_uastc_device(dev_in[w % ROTATING_INPUTS].data_ptr(), BLOCKS, dev_out.data_ptr(), LEVEL)
+    sampler = ClockSampler(local_rank)
+    barrier()
+    sampler.start()
+    launches = 0
+    stage = [0.0, 0.0, 0.0]
+    enc.timer_start()
+    for s in range(args.steps):
+        enc.encode_uastc_device(dev_in[s % ROTATING_INPUTS].data_ptr(), BLOCKS, dev_out.data_ptr(), LEVEL)
+        launches += enc.last_launch_count
+        for i in range(3):
+            stage[i] += enc.stage_ms(i)
+    dev_ms = enc.timer_stop_ms()
+    barrier()
+    sampler.stop_flag.set()
+    sampler.join(2)
+
+    # ---- e2e: host buffers through the public host-pointer call ----------------------------------------------------
+    for w in range(min(args.warmup, 3)):
+        enc.encode_uastc_host_ptr(host_in[w % ROTATING_INPUTS].data_ptr(), BLOCKS, host_out.data_ptr(), LEVEL)
+    barrier()
+    enc.timer_start()
+    t0 = time.perf_counter()
+    for s in range(args.steps):
+        enc.encode_uastc_host_ptr(host_in[s % ROTATING_INPUTS].data_ptr(), BLOCKS, host_out.data_ptr(), LEVEL)
+    e2e_dev_ms = enc.timer_stop_ms()
+    e2e_wall_ms = 1e3 * (time.perf_counter() - t0)
+    barrier()
+    e2e_ms = max(e2e_dev_ms, e2e_wall_ms)  # the host-visible time includes the final D2H completion
+
+    times = torch.tensor([dev_ms, e2e_ms], dtype=torch.float64, device="cuda")
+    if dist is not None:
+        dist.all_reduce(times, op=dist.ReduceOp.MAX)
+    dev_ms_max, e2e_ms_max = (float(v) for v in times.cpu())
+
+    if rank == 0:
+        peak, peak_kind = measured_peaks()
+        k1_ms = stage[1] / args.steps
+        achieved = ALGO_BYTES_PER_BLOCK * BLOCKS / (k1_ms * 1e-3) / 1e9
+        value = world * TEXELS * args.steps / 1e6 / (dev_ms_max * 1e-3)
+        e2e_value = world * TEXELS * args.steps / 1e6 / (e2e_ms_max * 1e-3)
+        cores = os.cpu_count() or 1
+        sample, desc = cpu_sample_blocks(to_blocks(synth(IMAGE_DIM, 1234)), cores)
+        cpu_t, cpu_out = cpu_reference_run(sample, cores)
+        # parity spot check while we are here: the reference's bytes for the sample equal the GPU's
+        enc.encode_uastc_device(dev_in[0].data_ptr(), BLOCKS, dev_out.data_ptr(), LEVEL)
+        gpu_sample = dev_out[: sample.shape[0]].cpu().numpy()
+        parity = bool(np.array_equal(gpu_sample, cpu_out))
+        line = {"metric": "Mtexels/sec encoded (4K RGBA UASTC LDR level 2)", "value": value, "unit": "Mtexel/s", "n_gpus": world,
+                "steps": args.steps, "warmup": args.warmup, "ms_per_step": dev_ms_max / args.steps, "higher_is_better": True,
+                "scaling": "weak", "vs_baseline": None, "dtype": "u8/f32/f64", "data": "synthetic", "config": config_dict(world),
+                "clocks": sampler.summary(),
+                "e2e": {"value": e2e_value, "unit": "Mtexel/s", "h2d_bytes_per_step": BLOCKS * 64, "d2h_bytes_per_step": BLOCKS * 16,
+                        "ms_per_step": e2e_ms_max / args.steps},
+                "gpu_launches": launches,
+                "stage_ms_per_step": {"classify_rank": stage[0] / args.steps, "candidates": k1_ms, "finish": stage[2] / args.steps},
+                "roofline": {"bound": "hbm", "kernel": "k_candidates", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                             "traffic": None, "peak_source": peak_kind,
+                             "note": "algorithmic 80 B/block (SURVEY 8d); kernel is ALU/latency-bound, see DESIGN.md section 5"},
+                "cpu_baseline": {"value": sample.shape[0] * 16 / 1e6 / cpu_t, "unit": "Mtexel/s", "cores": cores, "kind": "reference", "sample": desc},
+                "bit_exact_vs_reference_on_cpu_sample": parity}
+        print(json.dumps(line), flush=True)
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+    if world != args.gpus and args.gpus > 1:
+        print(f"bench.py: --gpus {args.gpus} needs torch.distributed.run with {args.gpus} ranks (got WORLD_SIZE={world})", file=sys.stderr)
+        sys.exit(2)
+    run_gpu(args, rank, local_rank, world)
+
+
+if __name__ == "__main__":
+    main()

@@ -103,6 +103,14 @@ int b200_etc1s_determine_selectors(b200_context* ctx, const void* pInput_etc_col
 float b200_last_kernel_ms(const b200_context* ctx);
 uint32_t b200_last_launch_count(const b200_context* ctx);
 
+/* Per-stage device time of the last UASTC encode call, summed over its chunks (CUDA events around each kernel on the
+ * context's stream): stage 0 = classify/rank, 1 = candidate generation + scoring, 2 = select/hints/pack. */
+float b200_last_stage_ms(const b200_context* ctx, uint32_t stage);
+
+/* Event pair on the context's stream for timing a span of calls (e.g. K benchmark steps) on the device. */
+int b200_timer_start(b200_context* ctx);
+float b200_timer_stop_ms(b200_context* ctx); /* synchronises the stream; < 0 on error */
+
 #ifdef __cplusplus
 }
 #endif

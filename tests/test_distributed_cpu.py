@@ -1,0 +1,52 @@
+"""world_size-2 gloo test (CPU) of the N>1 host logic: each rank owns a contiguous block-row range, encodes nothing here
+(no GPU) but proves the partition is a disjoint cover and that per-rank unit counts reduce to the whole job, which is what
+bench.py reports as `value` = all units / max-over-ranks time."""
+import os
+import socket
+
+import numpy as np
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from basis_universal_b200 import sharding
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, nbx, nby, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    first, last = sharding.block_range(nbx, nby, rank, world)
+    owned = torch.zeros(nbx * nby, dtype=torch.int32)
+    owned[first:last] = 1
+    dist.all_reduce(owned)                       # every block owned exactly once
+    units = torch.tensor([float((last - first) * 16)])
+    t = torch.tensor([0.5 + rank])               # fake per-rank step time
+    dist.all_reduce(units)                       # whole-job texels
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)     # max over ranks
+    if rank == 0:
+        q.put((bool((owned == 1).all()), float(units.item()), float(t.item())))
+    dist.destroy_process_group()
+
+
+def test_two_rank_block_row_sharding_gloo():
+    world, nbx, nby = 2, 37, 51
+    ctx = mp.get_context("spawn")
+    q = ctx.SimpleQueue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, world, port, nbx, nby, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(120)
+        assert p.exitcode == 0
+    ok, units, tmax = q.get()
+    assert ok and units == nbx * nby * 16 and tmax == 1.5
