@@ -36,7 +36,7 @@ struct cell_fit
 
 // ---- evaluate one endpoint pair (bc7enc.cpp:822) -------------------------------------------------------------------
 
-BU_HD inline void cell_evaluate(const bu_tables* T, const cell_cfg& cfg, const uint32_t* px, uint32_t n, const uint8_t* lo, const uint8_t* hi, cell_fit& fit)
+BU_NI inline void cell_evaluate(const bu_tables* T, const cell_cfg& cfg, const uint32_t* px, uint32_t n, const uint8_t* lo, const uint8_t* hi, cell_fit& fit)
 {
 	const uint8_t* su = T->sorted_unq + cfg.slot * 256;
 	const uint32_t N = 1u << cfg.wbits;
@@ -114,7 +114,7 @@ BU_FI bool cell_same_endpoints(const cell_fit& fit, const uint8_t* lo, const uin
 	return true;
 }
 
-BU_HD inline uint64_t cell_try_endpoints(const bu_tables* T, const cell_cfg& cfg, const uint32_t* px, uint32_t n, const float* xl_in, const float* xh_in, cell_fit& fit)
+BU_NI inline uint64_t cell_try_endpoints(const bu_tables* T, const cell_cfg& cfg, const uint32_t* px, uint32_t n, const float* xl_in, const float* xh_in, cell_fit& fit)
 {
 	float xl[4], xh[4];
 	uint8_t lo0[4], hi0[4];
@@ -158,7 +158,7 @@ BU_HD inline uint64_t cell_try_endpoints(const bu_tables* T, const cell_cfg& cfg
 
 // ---- least squares endpoints for fixed selectors (bc7enc.cpp:394/460) ----------------------------------------------------
 
-BU_HD inline void cell_least_squares(const bu_tables* T, const cell_cfg& cfg, const uint32_t* px, uint32_t n, const uint8_t* sel, float* xl, float* xh)
+BU_NI inline void cell_least_squares(const bu_tables* T, const cell_cfg& cfg, const uint32_t* px, uint32_t n, const uint8_t* sel, float* xl, float* xh)
 {
 	const float* wx = T->weightsx + cfg.wbits * 32 * 4;
 	const int nc = cfg.has_alpha ? 4 : 3;
@@ -227,7 +227,7 @@ BU_FI const uint8_t* cell_one_colour_table(const bu_tables* T, const cell_cfg& c
 	return nullptr;
 }
 
-BU_HD inline uint64_t cell_one_colour(const bu_tables* T, const cell_cfg& cfg, const uint8_t* tab, uint32_t sel, uint32_t alpha_index,
+BU_NI inline uint64_t cell_one_colour(const bu_tables* T, const cell_cfg& cfg, const uint8_t* tab, uint32_t sel, uint32_t alpha_index,
 	const uint32_t* px, uint32_t n, const uint32_t* c4, uint8_t* lo, uint8_t* hi)
 {
 	const uint8_t* su = T->sorted_unq + cfg.slot * 256;
@@ -264,7 +264,7 @@ BU_HD inline void cell_finish(const bu_tables* T, const cell_cfg& cfg, const cel
 	for (uint32_t i = 0; i < n; i++) out.sel[i] = fit.sel[i];
 }
 
-BU_HD inline void cell_compress(const bu_tables* T, const cell_cfg& cfg, const uint32_t* px, uint32_t n, cell_result& out)
+BU_NI inline void cell_compress(const bu_tables* T, const cell_cfg& cfg, const uint32_t* px, uint32_t n, cell_result& out)
 {
 	cell_fit fit;
 	fit.err = UINT64_MAX;
@@ -390,7 +390,7 @@ BU_HD inline void cell_compress(const bu_tables* T, const cell_cfg& cfg, const u
 	if (go && cfg.uber > 0)
 	{
 		// Selector perturbation (bc7enc.cpp:1567-1677): bump the extreme selectors inward, refit.
-		uint8_t base[16], trial[16];
+		uint8_t base[16] = { 0 }, trial[16] = { 0 };
 		uint32_t min_sel = 256, max_sel = 0;
 		const uint32_t top = (1u << cfg.wbits) - 1;
 		for (uint32_t i = 0; i < n; i++) { base[i] = fit.sel[i]; min_sel = minu(min_sel, base[i]); max_sel = maxu(max_sel, base[i]); }
@@ -455,7 +455,7 @@ BU_HD inline void cell_compress(const bu_tables* T, const cell_cfg& cfg, const u
 // Integer only. The reference's early-out on best_err_so_far only truncates sums that already exceed the running best, so
 // returning the full sum leaves every comparison made by the partition rankers unchanged.
 
-BU_HD inline uint64_t cell_estimate(const bu_tables* T, uint32_t wbits, uint32_t comps, const uint32_t* px, uint32_t n)
+BU_NI inline uint64_t cell_estimate(const bu_tables* T, uint32_t wbits, uint32_t comps, const uint32_t* px, uint32_t n)
 {
 	const uint32_t N = 1u << wbits;
 	const uint8_t* wt = T->weights + wbits * 32;

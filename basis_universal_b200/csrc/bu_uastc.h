@@ -139,7 +139,7 @@ BU_HD inline uint64_t estimate_pattern_error(const bu_tables* T, const uint8_t* 
 
 // kind: 2 = two-subset common patterns (30), 3 = three-subset (11), 7 = BC7-3/ASTC-2 patterns (19).
 // Writes the best `want` (<= 8) pattern indices in ascending error order, first-strictly-less wins among equals.
-BU_HD inline void rank_partitions(const bu_tables* T, uint32_t kind, uint32_t wbits, uint32_t comps, const uint32_t* px, uint32_t want, uint8_t* out)
+BU_NI inline void rank_partitions(const bu_tables* T, uint32_t kind, uint32_t wbits, uint32_t comps, const uint32_t* px, uint32_t want, uint8_t* out)
 {
 	const uint32_t total = (kind == 2) ? 30u : (kind == 3) ? 11u : 19u;
 	const uint8_t* base = (kind == 2) ? T->bc7_part2 : (kind == 3) ? T->bc7_part3 : T->astc_pat73;
@@ -188,7 +188,7 @@ BU_FI void candidate_clear(candidate& c, uint32_t mode)
 }
 
 // Single-subset, single-plane modes 0,1,5,10,12,14,15,18 (uastc_enc.cpp:470, 558, 1140, 1818, 2096, 2335, 2422).
-BU_HD inline void gen_one_subset(const bu_tables* T, uint32_t mode, const level_opts& o, const uint32_t* px, candidate& out)
+BU_NI inline void gen_one_subset(const bu_tables* T, uint32_t mode, const level_opts& o, const uint32_t* px, candidate& out)
 {
 	candidate_clear(out, mode);
 	const bool rgba = T->mode_comps[mode] == 4, la = T->mode_comps[mode] == 2;
@@ -217,7 +217,7 @@ BU_HD inline void gen_one_subset(const bu_tables* T, uint32_t mode, const level_
 }
 
 // Two/three-subset modes 2,3,4,7,9,16 for a given common pattern (uastc_enc.cpp:673, 823, 992, 1357, 1596).
-BU_HD inline void gen_multi_subset(const bu_tables* T, uint32_t mode, uint32_t pattern, const level_opts& o, const uint32_t* px, candidate& out)
+BU_NI inline void gen_multi_subset(const bu_tables* T, uint32_t mode, uint32_t pattern, const level_opts& o, const uint32_t* px, candidate& out)
 {
 	candidate_clear(out, mode);
 	out.pattern = (uint8_t)pattern;
@@ -282,7 +282,7 @@ BU_HD inline void gen_multi_subset(const bu_tables* T, uint32_t mode, uint32_t p
 }
 
 // Dual-plane modes 6,11,13,17 for a given rotation / second-plane component (uastc_enc.cpp:1223, 1905, 2182).
-BU_HD inline void gen_dual_plane(const bu_tables* T, uint32_t mode, uint32_t rot, const level_opts& o, const uint32_t* px, candidate& out)
+BU_NI inline void gen_dual_plane(const bu_tables* T, uint32_t mode, uint32_t rot, const level_opts& o, const uint32_t* px, candidate& out)
 {
 	candidate_clear(out, mode);
 	const cell_cfg cfg = mode_cell_cfg(T, mode, o, false); // both planes are fitted as RGB cells
@@ -347,7 +347,7 @@ BU_HD inline void gen_dual_plane(const bu_tables* T, uint32_t mode, uint32_t rot
 
 // ---- decode a candidate to texels (transcoder.cpp:15743 unpack_uastc from an astc_block_desc) ------------------------------
 
-BU_HD inline void decode_candidate(const bu_tables* T, const candidate& c, uint32_t* out)
+BU_NI inline void decode_candidate(const bu_tables* T, const candidate& c, uint32_t* out)
 {
 	const uint32_t mode = c.mode;
 	const uint32_t subsets = T->mode_subsets[mode], comps = T->mode_comps[mode], planes = T->mode_planes[mode];
@@ -398,7 +398,7 @@ BU_HD inline void decode_candidate(const bu_tables* T, const candidate& c, uint3
 struct pbit_fit { uint8_t lo[4], hi[4]; uint32_t p0, p1; };
 
 // determine_unique_pbits (transcoder.cpp:15950): independent p-bit per endpoint.
-BU_HD inline void fit_unique_pbits(uint32_t total_comps, uint32_t comp_bits, const float* xl, const float* xh, pbit_fit& f)
+BU_NI inline void fit_unique_pbits(uint32_t total_comps, uint32_t comp_bits, const float* xl, const float* xh, pbit_fit& f)
 {
 	const uint32_t total_bits = comp_bits + 1;
 	const int iscalep = (1 << total_bits) - 1;
@@ -429,7 +429,7 @@ BU_HD inline void fit_unique_pbits(uint32_t total_comps, uint32_t comp_bits, con
 }
 
 // determine_shared_pbits (transcoder.cpp:15897): one p-bit for both endpoints.
-BU_HD inline void fit_shared_pbits(uint32_t total_comps, uint32_t comp_bits, const float* xl, const float* xh, pbit_fit& f)
+BU_NI inline void fit_shared_pbits(uint32_t total_comps, uint32_t comp_bits, const float* xl, const float* xh, pbit_fit& f)
 {
 	const uint32_t total_bits = comp_bits + 1;
 	const int iscalep = (1 << total_bits) - 1;
@@ -465,7 +465,7 @@ BU_FI uint32_t bc7_dq_p(uint32_t v, uint32_t pbit, uint32_t bits) { const uint32
 BU_FI uint32_t bc7_dq(uint32_t v, uint32_t bits) { v <<= (8 - bits); return v | (v >> bits); }
 BU_FI uint32_t bc7_lerp(uint32_t l, uint32_t h, uint32_t w) { return (l * (64 - w) + h * w + 32) >> 6; }
 
-BU_HD inline void decode_bc7_transcode(const bu_tables* T, const candidate& c, uint32_t* out)
+BU_NI inline void decode_bc7_transcode(const bu_tables* T, const candidate& c, uint32_t* out)
 {
 	const uint32_t mode = c.mode;
 	const uint32_t range = T->mode_endpoint_range[mode];
@@ -702,7 +702,7 @@ BU_HD inline void score_candidate(const bu_tables* T, const uint32_t* src, block
 // ---- final choice among a block's candidates (uastc_enc.cpp:3397-3549) ------------------------------------------------------
 // errs: (uastc_err, bc7_err) pairs in candidate order; modes: UASTC mode per candidate. Returns the chosen index.
 
-BU_HD inline int select_candidate(uint32_t n, const uint32_t* uastc_err, const uint32_t* bc7_err, const uint8_t* modes, uint32_t flags)
+BU_NI inline int select_candidate(uint32_t n, const uint32_t* uastc_err, const uint32_t* bc7_err, const uint8_t* modes, uint32_t flags)
 {
 	if (n == 1) return 0;
 	const bool favor_uastc = (flags & 8) != 0;              // cPackUASTCFavorUASTCError

@@ -18,7 +18,7 @@ namespace bu {
 // uastc_enc.cpp:267-339: per plane and subset, if the anchor texel's weight has its MSB set, invert that subset's weights in
 // that plane and swap the endpoints that plane controls.
 
-BU_HD inline void canonicalize(const bu_tables* T, const candidate& c, uint8_t* ep, uint8_t* w)
+BU_NI inline void canonicalize(const bu_tables* T, const candidate& c, uint8_t* ep, uint8_t* w)
 {
 	const uint32_t mode = c.mode;
 	const uint32_t subsets = T->mode_subsets[mode], comps = T->mode_comps[mode], planes = T->mode_planes[mode];
@@ -59,7 +59,7 @@ BU_HD inline void canonicalize(const bu_tables* T, const candidate& c, uint8_t* 
 
 struct bc1_logical { uint32_t c0, c1; uint32_t sel; }; // 565 colours (c0 = "low"/first field) and 16 2-bit raw selectors
 
-BU_HD inline void bc1_decode(const bc1_logical& b, uint32_t* out)
+BU_NI inline void bc1_decode(const bc1_logical& b, uint32_t* out)
 {
 	const uint32_t l = b.c0, h = b.c1;
 	uint32_t r0 = (l >> 11) & 31, g0 = (l >> 5) & 63, b0 = l & 31, r1 = (h >> 11) & 31, g1 = (h >> 5) & 63, b1 = h & 31;
@@ -82,7 +82,7 @@ BU_HD inline void bc1_decode(const bc1_logical& b, uint32_t* out)
 }
 
 // transcoder.cpp:17857
-BU_HD inline void bc1_find_sels(const uint32_t* px, uint32_t lr, uint32_t lg, uint32_t lb, uint32_t hr, uint32_t hg, uint32_t hb, uint8_t* sels)
+BU_NI inline void bc1_find_sels(const uint32_t* px, uint32_t lr, uint32_t lg, uint32_t lb, uint32_t hr, uint32_t hg, uint32_t hb, uint8_t* sels)
 {
 	uint32_t br[4], bg[4], bb[4];
 	br[0] = (lr << 3) | (lr >> 2); bg[0] = (lg << 2) | (lg >> 4); bb[0] = (lb << 3) | (lb >> 2);
@@ -102,7 +102,7 @@ BU_HD inline void bc1_find_sels(const uint32_t* px, uint32_t lr, uint32_t lg, ui
 }
 
 // transcoder.cpp:17922. Returns false when the normal equations are singular.
-BU_HD inline bool bc1_least_squares(const uint32_t* px, const uint8_t* sels, float* xl, float* xh)
+BU_NI inline bool bc1_least_squares(const uint32_t* px, const uint8_t* sels, float* xl, float* xh)
 {
 	uint32_t uq00[3] = { 0, 0, 0 }, ut[3] = { 0, 0, 0 };
 	const uint32_t wv[4] = { 0x000009, 0x010204, 0x040201, 0x090000 };
@@ -139,7 +139,7 @@ BU_FI uint32_t to_5(uint32_t v) { v = v * 31 + 128; return (v + (v >> 8)) >> 8; 
 BU_FI uint32_t to_6(uint32_t v) { v = v * 63 + 128; return (v + (v >> 8)) >> 8; }
 
 // encode_bc1 (transcoder.cpp:18047) with flags = 0 (use_sels == false) or cEncodeBC1UseSelectors (raw selectors supplied).
-BU_HD inline void bc1_encode(const bu_tables* T, const uint32_t* px, bool use_sels, uint32_t raw_sels_in, bc1_logical& out)
+BU_NI inline void bc1_encode(const bu_tables* T, const uint32_t* px, bool use_sels, uint32_t raw_sels_in, bc1_logical& out)
 {
 	int avg[3] = { -1, 0, 0 };
 	int lr = 0, lg = 0, lb = 0, hr = 0, hg = 0, hb = 0;
@@ -271,7 +271,7 @@ BU_FI uint32_t pack565_scaled(uint32_t r, uint32_t g, uint32_t b)
 }
 
 // compute_bc1_hints (uastc_enc.cpp:2535). ep/w are the canonical endpoints/weights of the chosen candidate.
-BU_HD inline void compute_bc1_hints(const bu_tables* T, uint32_t mode, const uint8_t* ep, const uint8_t* w, const uint32_t* src, const uint32_t* dec, bool& hint0, bool& hint1)
+BU_NI inline void compute_bc1_hints(const bu_tables* T, uint32_t mode, const uint8_t* ep, const uint8_t* w, const uint32_t* src, const uint32_t* dec, bool& hint0, bool& hint1)
 {
 	hint0 = false; hint1 = false;
 	const bool has0 = T->mode_has_bc1_hint0[mode] != 0, has1 = T->mode_has_bc1_hint1[mode] != 0;
@@ -343,7 +343,7 @@ BU_HD inline void compute_bc1_hints(const bu_tables* T, uint32_t mode, const uin
 
 // ---- ETC2 EAC A8 hint (uastc_enc.cpp:3019, base_search_rad = 0) ------------------------------------------------------------
 
-BU_HD inline void compute_eac_hint(const bu_tables* T, const uint32_t* dec, uint32_t mul_rad, uint32_t table_mask, uint32_t& out_table, uint32_t& out_mul)
+BU_NI inline void compute_eac_hint(const bu_tables* T, const uint32_t* dec, uint32_t mul_rad, uint32_t table_mask, uint32_t& out_table, uint32_t& out_mul)
 {
 	uint32_t mn = 255, mx = 0;
 	for (int i = 0; i < 16; i++) { const uint32_t a = px_c(dec[i], 3); if (a < mn) mn = a; if (a > mx) mx = a; }
@@ -411,7 +411,7 @@ BU_FI int gray_distance2(uint32_t p, int r, int g, int b)
 }
 
 // uastc_enc.cpp:2668
-BU_HD inline bool etc1_estimate_flipped(const uint32_t* px)
+BU_NI inline bool etc1_estimate_flipped(const uint32_t* px)
 {
 	int upper[3], lower[3], left[3], right[3];
 	for (uint32_t c = 0; c < 3; c++)
@@ -519,7 +519,7 @@ BU_HD inline etc1_search_opts etc1_search_setup(const bu_tables* T, uint32_t mod
 }
 
 // One (flip, individ) trial group: all bias iterations, best kept with first-strictly-less.
-BU_HD inline void etc1_hint_group(const bu_tables* T, const etc1_search_opts& o, uint32_t flip, uint32_t individ,
+BU_NI inline void etc1_hint_group(const bu_tables* T, const etc1_search_opts& o, uint32_t flip, uint32_t individ,
 	const ycc* src_y, const ycc* dec_y, const uint32_t* dec, etc1_hint& best)
 {
 	const uint8_t sorted_bias[32] = { 13, 0, 22, 29, 27, 12, 26, 9, 30, 31, 8, 10, 25, 2, 23, 5, 15, 7, 3, 11, 6, 17, 28, 18, 1, 19, 20, 21, 24, 4, 14, 16 };
@@ -645,7 +645,7 @@ BU_HD inline void etc1_hint_group(const bu_tables* T, const etc1_search_opts& o,
 
 struct etc1_solid { uint32_t diff, inten, selector, r, g, b; };
 
-BU_HD inline etc1_solid etc1_pack_solid(const bu_tables* T, uint32_t colour)
+BU_NI inline etc1_solid etc1_pack_solid(const bu_tables* T, uint32_t colour)
 {
 	const uint32_t next_comp[4] = { 1, 2, 0, 1 };
 	uint32_t best_err = 0xFFFFFFFFu, best_i = 0, best_x = 0, best_c1 = 0, best_c2 = 0;
@@ -701,7 +701,7 @@ BU_FI void bw_put(bit_writer& b, uint64_t code, uint32_t n)
 	b.ofs += n;
 }
 
-BU_HD inline void pack_solid_block(const bu_tables* T, uint32_t colour, uint8_t* out16)
+BU_NI inline void pack_solid_block(const bu_tables* T, uint32_t colour, uint8_t* out16)
 {
 	bit_writer b; b.lo = 0; b.hi = 0; b.ofs = 0;
 	bw_put(b, T->mode_huff[8 * 2], T->mode_huff[8 * 2 + 1]);
@@ -713,7 +713,7 @@ BU_HD inline void pack_solid_block(const bu_tables* T, uint32_t colour, uint8_t*
 }
 
 // ep/w: canonical endpoints and weights (canonicalize()).
-BU_HD inline void pack_block(const bu_tables* T, const candidate& c, const uint8_t* ep, const uint8_t* w, const etc1_hint& etc1,
+BU_NI inline void pack_block(const bu_tables* T, const candidate& c, const uint8_t* ep, const uint8_t* w, const etc1_hint& etc1,
 	uint32_t eac_table, uint32_t eac_mul, bool bc1_hint0, bool bc1_hint1, uint8_t* out16)
 {
 	const uint32_t mode = c.mode;
