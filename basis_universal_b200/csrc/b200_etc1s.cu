@@ -1,0 +1,339 @@
+// b200_etc1s.cu -- CUDA (sm_100a) implementations of the five ETC1S frontend stages behind the reference's GPU seam
+// (encoder/basisu_opencl.h:46-141; kernels in bin/ocl_kernels.cl) and their C-ABI entry points (include/basisu_b200.h).
+//
+//   k_etc1s_encode_blocks       1 thread / block                       opencl_encode_etc1s_blocks          (cl:984)
+//   k_etc1s_pixel_clusters      1 WARP / cluster, lanes stride texels  opencl_encode_etc1s_pixel_clusters  (cl:1013)
+//   k_etc1s_refine              1 thread / block, cluster-sorted order opencl_refine_endpoint_clusterization (cl:1063)
+//   k_etc1s_fosc                1 WARP / block, lanes stride selectors opencl_find_optimal_selector_clusters_for_each_block (cl:1159)
+//   k_etc1s_determine_selectors 1 thread / block                       opencl_determine_selectors          (cl:1227)
+//
+// The reference launches one work-item per block/cluster with fully serial inner loops. Where the serial loop is a sum or an
+// arg-min over many items (cluster texels, codebook entries) it is spread over the 32 lanes of a warp here: the sums are
+// integer (exact in any order) and the arg-min rules are reproduced as lexicographic (error, index) minima.
+#include "b200_internal.h"
+#include "bu_etc1s.h"
+
+using namespace bu;
+
+#include "b200_tables.cuh"
+
+__device__ __forceinline__ void load_block16(const uint4* __restrict__ blocks, uint32_t i, uint32_t* px)
+{
+	const uint4* p = blocks + (size_t)i * 4;
+#pragma unroll
+	for (int r = 0; r < 4; r++)
+	{
+		const uint4 v = __ldg(p + r);
+		px[r * 4 + 0] = v.x; px[r * 4 + 1] = v.y; px[r * 4 + 2] = v.z; px[r * 4 + 3] = v.w;
+	}
+}
+
+__global__ void __launch_bounds__(128) k_etc1s_encode_blocks(const uint4* __restrict__ blocks, uint32_t n, uint64_t* __restrict__ out, int perceptual, uint32_t total_perms)
+{
+	const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= n) return;
+	uint32_t px[16];
+	load_block16(blocks, i, px);
+	out[i] = etc1s_encode_block(&d_tables, perceptual != 0, total_perms, px);
+}
+
+__global__ void __launch_bounds__(128) k_etc1s_determine_selectors(const uint4* __restrict__ blocks, uint32_t n, const uint32_t* __restrict__ color5_inten, uint64_t* __restrict__ out, int perceptual)
+{
+	const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= n) return;
+	uint32_t px[16];
+	load_block16(blocks, i, px);
+	out[i] = etc1s_determine_selectors(&d_tables, perceptual != 0, px, color5_inten[i]);
+}
+
+// ---- pixel clusters: one warp per cluster ---------------------------------------------------------------------------------
+
+__device__ __forceinline__ uint64_t warp_sum_u64(uint64_t v)
+{
+#pragma unroll
+	for (int m = 16; m >= 1; m >>= 1)
+	{
+		uint32_t lo = (uint32_t)v, hi = (uint32_t)(v >> 32);
+		lo = __shfl_xor_sync(0xffffffffu, lo, m); hi = __shfl_xor_sync(0xffffffffu, hi, m);
+		v += ((uint64_t)hi << 32) | lo;
+	}
+	return v;
+}
+
+// Weighted error of base colour (r5,g5,b5) against the cluster's texels for every non-pruned intensity table; returns the
+// best (first strictly smaller) table and its error. Uniform across the warp.
+__device__ void cluster_evaluate(const bu_tables* T, bool perceptual, const uint32_t* __restrict__ px, const uint32_t* __restrict__ wts, uint64_t n,
+	uint32_t lane, uint32_t spread, uint32_t r5, uint32_t g5, uint32_t b5, etc1s_solution& best)
+{
+	uint64_t trial_err = (uint64_t)INT64_MAX;
+	uint32_t trial_inten = 0;
+	bool valid = false;
+	for (uint32_t inten = 0; inten < 8; inten++)
+	{
+		if (!T->eval_dist[inten * 256 + spread]) continue;
+		uint32_t colors[4];
+		etc1s_block_colors(T, r5, g5, b5, inten, colors);
+		uint64_t total = 0;
+		for (uint64_t i = lane; i < n; i += 32)
+		{
+			const uint32_t p = px[i];
+			uint32_t be = etc_color_distance(perceptual, p, colors[0]);
+			be = min(be, etc_color_distance(perceptual, p, colors[1]));
+			be = min(be, etc_color_distance(perceptual, p, colors[2]));
+			be = min(be, etc_color_distance(perceptual, p, colors[3]));
+			total += (uint64_t)be * (uint64_t)wts[i];
+		}
+		total = warp_sum_u64(total);
+		if (total < trial_err) { trial_err = total; trial_inten = inten; valid = true; }
+	}
+	if (trial_err < best.err) { best.err = trial_err; best.r5 = r5; best.g5 = g5; best.b5 = b5; best.inten = trial_inten; best.valid = valid ? 1u : 0u; }
+}
+
+__global__ void __launch_bounds__(128) k_etc1s_pixel_clusters(const b200_pixel_cluster* __restrict__ clusters, uint32_t total_clusters,
+	const uint32_t* __restrict__ pixels, const uint32_t* __restrict__ weights, uint64_t* __restrict__ out, int perceptual_i, uint32_t total_perms)
+{
+	const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+	if (warp >= total_clusters) return;
+	const bu_tables* T = &d_tables;
+	const bool perceptual = perceptual_i != 0;
+	const uint64_t n = clusters[warp].total_pixels;
+	const uint32_t* px = pixels + clusters[warp].first_pixel_index;
+	const uint32_t* wts = weights + clusters[warp].first_pixel_index;
+
+	uint32_t mn[3] = { 255, 255, 255 }, mx[3] = { 0, 0, 0 };
+	uint64_t sum[3] = { 0, 0, 0 }, tw = 0;
+	for (uint64_t i = lane; i < n; i += 32)
+	{
+		const uint32_t p = px[i];
+		const uint64_t w = wts[i];
+		for (uint32_t c = 0; c < 3; c++)
+		{
+			const uint32_t v = px_c(p, c);
+			mn[c] = min(mn[c], v); mx[c] = max(mx[c], v); sum[c] += w * v;
+		}
+		tw += w;
+	}
+	for (int c = 0; c < 3; c++)
+	{
+#pragma unroll
+		for (int m = 16; m >= 1; m >>= 1)
+		{
+			mn[c] = min(mn[c], __shfl_xor_sync(0xffffffffu, mn[c], m));
+			mx[c] = max(mx[c], __shfl_xor_sync(0xffffffffu, mx[c], m));
+		}
+		sum[c] = warp_sum_u64(sum[c]);
+	}
+	tw = warp_sum_u64(tw);
+
+	float avg[3];
+	for (int c = 0; c < 3; c++) avg[c] = (float)sum[c] / (float)tw;
+	const uint32_t spread = (uint32_t)max(max((int)mx[0] - (int)mn[0], (int)mx[1] - (int)mn[1]), (int)mx[2] - (int)mn[2]);
+	const float k = 31 / 255.0f;
+	const uint32_t r0 = (uint32_t)clampi((int)(avg[0] * k + .5f), 0, 31), g0 = (uint32_t)clampi((int)(avg[1] * k + .5f), 0, 31), b0 = (uint32_t)clampi((int)(avg[2] * k + .5f), 0, 31);
+
+	etc1s_solution best;
+	best.err = UINT64_MAX; best.r5 = best.g5 = best.b5 = best.inten = 0; best.lsb_plane = best.msb_plane = 0; best.valid = 0;
+	cluster_evaluate(T, perceptual, px, wts, n, lane, spread, r0, g0, b0, best);
+	if (best.err != 0)
+		for (uint32_t perm = 0; perm < total_perms; perm++)
+		{
+			uint32_t r1, g1, b1;
+			if (!etc1s_cluster_fit_step(T, best, avg, perm, r1, g1, b1)) continue;
+			cluster_evaluate(T, perceptual, px, wts, n, lane, spread, r1, g1, b1, best);
+			if (best.err == 0) break;
+		}
+	if (lane == 0) out[warp] = etc1s_pack(best.r5, best.g5, best.b5, best.inten, 0, 0); // the kernel defines no selectors for clusters
+}
+
+// ---- refine_endpoint_clusterization ------------------------------------------------------------------------------------------
+
+__global__ void __launch_bounds__(128) k_etc1s_refine(const uint4* __restrict__ blocks, uint32_t n, const b200_block_info* __restrict__ info,
+	const b200_endpoint_cluster* __restrict__ clusters, const uint32_t* __restrict__ sorted, uint32_t* __restrict__ out, int perceptual_i)
+{
+	const uint32_t gid = blockIdx.x * blockDim.x + threadIdx.x;
+	if (gid >= n) return;
+	const uint32_t bi = sorted[gid];
+	const bool perceptual = perceptual_i != 0;
+	uint32_t px[16];
+	load_block16(blocks, bi, px);
+	const b200_block_info in = info[bi];
+	uint64_t best_err = UINT64_MAX;
+	uint32_t best_index = 0;
+	for (uint32_t k = 0; k < in.num_clusters; k++)
+	{
+		const b200_endpoint_cluster c = clusters[(uint32_t)in.first_cluster_ofs + k];
+		if (c.etc_inten > in.cur_cluster_etc_inten) continue;
+		const uint64_t e = etc1s_block_error(&d_tables, perceptual, px, c.unscaled_r, c.unscaled_g, c.unscaled_b, c.etc_inten);
+		if (e < best_err || (c.cluster_index == in.cur_cluster_index && e == best_err))
+		{
+			best_err = e;
+			best_index = c.cluster_index;
+			if (!best_err) break;
+		}
+	}
+	out[bi] = best_index;
+}
+
+// ---- find_optimal_selector_clusters_for_each_block: one warp per block -------------------------------------------------------
+
+__global__ void __launch_bounds__(128) k_etc1s_fosc(const uint4* __restrict__ blocks, uint32_t n, const b200_fosc_block* __restrict__ info,
+	const uint32_t* __restrict__ selectors, const uint32_t* __restrict__ cluster_indices, uint32_t* __restrict__ out, int perceptual_i)
+{
+	__shared__ uint32_t s_err[4][64]; // per warp: [selector 0..3][texel] errors
+	const uint32_t warp_in_cta = threadIdx.x >> 5, lane = threadIdx.x & 31;
+	const uint32_t bi = blockIdx.x * (blockDim.x >> 5) + warp_in_cta;
+	if (bi >= n) return;
+	const bool perceptual = perceptual_i != 0;
+	const b200_fosc_block in = info[bi];
+	uint32_t colors[4];
+	etc1s_block_colors(&d_tables, in.etc_r, in.etc_g, in.etc_b, in.etc_a, colors);
+	// 64 table entries, two per lane: entry e = sel * 16 + texel
+	const uint32_t* bp = reinterpret_cast<const uint32_t*>(blocks) + (size_t)bi * 16;
+	for (uint32_t e = lane; e < 64; e += 32)
+		s_err[warp_in_cta][e] = etc_color_distance(perceptual, __ldg(bp + (e & 15)), colors[e >> 4]);
+	__syncwarp();
+
+	const uint32_t* tab = s_err[warp_in_cta];
+	const uint32_t* sel = selectors + in.first_selector;
+	uint64_t best_err = UINT64_MAX;
+	uint32_t best_index = 0xFFFFFFFFu;
+	for (uint32_t k = lane; k < in.num_selectors; k += 32)
+	{
+		uint32_t s = __ldg(sel + k);
+		uint64_t total = 0;
+#pragma unroll
+		for (int i = 0; i < 16; i++, s >>= 2) total += tab[(s & 3) * 16 + i];
+		if (total < best_err) { best_err = total; best_index = k; } // ascending k per lane: strict < keeps the earliest
+	}
+#pragma unroll
+	for (int m = 16; m >= 1; m >>= 1)
+	{
+		uint32_t lo = (uint32_t)best_err, hi = (uint32_t)(best_err >> 32);
+		lo = __shfl_xor_sync(0xffffffffu, lo, m); hi = __shfl_xor_sync(0xffffffffu, hi, m);
+		const uint64_t oe = ((uint64_t)hi << 32) | lo;
+		const uint32_t oi = __shfl_xor_sync(0xffffffffu, best_index, m);
+		if (oe < best_err || (oe == best_err && oi < best_index)) { best_err = oe; best_index = oi; }
+	}
+	if (lane == 0)
+	{
+		if (best_index == 0xFFFFFFFFu) best_index = 0; // num_selectors == 0: the kernel reads entry 0 (cl:1216)
+		out[bi] = cluster_indices[in.first_selector + best_index];
+	}
+}
+
+// ---- C ABI ------------------------------------------------------------------------------------------------------------------
+
+#define ETC_CHECK_BLOCKS(ctx, name) do { if (!(ctx)) return 0; if (!(ctx)->activate()) return 0; \
+	if (!(ctx)->d_etc_blocks || !(ctx)->etc_total_blocks) { (ctx)->fail(name ": b200_etc1s_set_pixel_blocks has not been called"); return 0; } } while (0)
+
+static bool upload(b200_context* ctx, int slot, const void* host, size_t bytes)
+{
+	if (!ctx->reserve(ctx->d_aux[slot], ctx->aux_cap[slot], bytes ? bytes : 16)) return false;
+	if (bytes)
+	{
+		const cudaError_t e = cudaMemcpyAsync(ctx->d_aux[slot], host, bytes, cudaMemcpyHostToDevice, ctx->stream);
+		if (e != cudaSuccess) { ctx->fail_cuda("cudaMemcpyAsync(H2D)", e); return false; }
+	}
+	return true;
+}
+
+static int finish(b200_context* ctx, void* host_out, int slot, size_t bytes)
+{
+	B200_CUDA_OK(ctx, cudaGetLastError());
+	B200_CUDA_OK(ctx, cudaEventRecord(ctx->ev1, ctx->stream));
+	B200_CUDA_OK(ctx, cudaMemcpyAsync(host_out, ctx->d_aux[slot], bytes, cudaMemcpyDeviceToHost, ctx->stream));
+	B200_CUDA_OK(ctx, cudaStreamSynchronize(ctx->stream));
+	B200_CUDA_OK(ctx, cudaEventElapsedTime(&ctx->last_ms, ctx->ev0, ctx->ev1));
+	return 1;
+}
+
+extern "C" int b200_etc1s_set_pixel_blocks(b200_context* ctx, uint32_t total_blocks, const void* pPixel_blocks)
+{
+	if (!ctx) return 0;
+	if (!ctx->activate()) return 0;
+	if (!total_blocks || !pPixel_blocks) { ctx->fail("b200_etc1s_set_pixel_blocks: empty input"); return 0; }
+	if (!ctx->reserve(ctx->d_etc_blocks, ctx->etc_blocks_cap, (size_t)total_blocks * 64)) return 0;
+	B200_CUDA_OK(ctx, cudaMemcpyAsync(ctx->d_etc_blocks, pPixel_blocks, (size_t)total_blocks * 64, cudaMemcpyHostToDevice, ctx->stream));
+	B200_CUDA_OK(ctx, cudaStreamSynchronize(ctx->stream));
+	ctx->etc_total_blocks = total_blocks;
+	return 1;
+}
+
+extern "C" int b200_etc1s_encode_blocks(b200_context* ctx, void* pOutput_blocks, int perceptual, uint32_t total_perms)
+{
+	ETC_CHECK_BLOCKS(ctx, "b200_etc1s_encode_blocks");
+	if (total_perms > 165) { ctx->fail("b200_etc1s_encode_blocks: total_perms > 165"); return 0; }
+	const uint32_t n = ctx->etc_total_blocks;
+	if (!ctx->reserve(ctx->d_aux[0], ctx->aux_cap[0], (size_t)n * 8)) return 0;
+	ctx->launches = 1;
+	B200_CUDA_OK(ctx, cudaEventRecord(ctx->ev0, ctx->stream));
+	k_etc1s_encode_blocks<<<(n + 127) / 128, 128, 0, ctx->stream>>>(static_cast<const uint4*>(ctx->d_etc_blocks), n, static_cast<uint64_t*>(ctx->d_aux[0]), perceptual, total_perms);
+	return finish(ctx, pOutput_blocks, 0, (size_t)n * 8);
+}
+
+extern "C" int b200_etc1s_encode_pixel_clusters(b200_context* ctx, void* pOutput_blocks, uint32_t total_clusters, const b200_pixel_cluster* pClusters,
+	uint64_t total_pixels, const void* pPixels, const uint32_t* pPixel_weights, int perceptual, uint32_t total_perms)
+{
+	if (!ctx) return 0;
+	if (!ctx->activate()) return 0;
+	if (!total_clusters) return 1;
+	if (total_perms > 165) { ctx->fail("b200_etc1s_encode_pixel_clusters: total_perms > 165"); return 0; }
+	if (!upload(ctx, 1, pClusters, (size_t)total_clusters * sizeof(b200_pixel_cluster))) return 0;
+	if (!upload(ctx, 2, pPixels, (size_t)total_pixels * 4)) return 0;
+	if (!upload(ctx, 3, pPixel_weights, (size_t)total_pixels * 4)) return 0;
+	if (!ctx->reserve(ctx->d_aux[0], ctx->aux_cap[0], (size_t)total_clusters * 8)) return 0;
+	ctx->launches = 1;
+	B200_CUDA_OK(ctx, cudaEventRecord(ctx->ev0, ctx->stream));
+	const uint32_t warps_per_cta = 4;
+	k_etc1s_pixel_clusters<<<(total_clusters + warps_per_cta - 1) / warps_per_cta, warps_per_cta * 32, 0, ctx->stream>>>(
+		static_cast<const b200_pixel_cluster*>(ctx->d_aux[1]), total_clusters, static_cast<const uint32_t*>(ctx->d_aux[2]),
+		static_cast<const uint32_t*>(ctx->d_aux[3]), static_cast<uint64_t*>(ctx->d_aux[0]), perceptual, total_perms);
+	return finish(ctx, pOutput_blocks, 0, (size_t)total_clusters * 8);
+}
+
+extern "C" int b200_etc1s_refine_endpoint_clusterization(b200_context* ctx, const b200_block_info* pPixel_block_info, uint32_t total_clusters,
+	const b200_endpoint_cluster* pCluster_info, const uint32_t* pSorted_block_indices, uint32_t* pOutput_cluster_indices, int perceptual)
+{
+	ETC_CHECK_BLOCKS(ctx, "b200_etc1s_refine_endpoint_clusterization");
+	const uint32_t n = ctx->etc_total_blocks;
+	if (!upload(ctx, 1, pPixel_block_info, (size_t)n * sizeof(b200_block_info))) return 0;
+	if (!upload(ctx, 2, pCluster_info, (size_t)total_clusters * sizeof(b200_endpoint_cluster))) return 0;
+	if (!upload(ctx, 3, pSorted_block_indices, (size_t)n * 4)) return 0;
+	if (!ctx->reserve(ctx->d_aux[0], ctx->aux_cap[0], (size_t)n * 4)) return 0;
+	ctx->launches = 1;
+	B200_CUDA_OK(ctx, cudaEventRecord(ctx->ev0, ctx->stream));
+	k_etc1s_refine<<<(n + 127) / 128, 128, 0, ctx->stream>>>(static_cast<const uint4*>(ctx->d_etc_blocks), n, static_cast<const b200_block_info*>(ctx->d_aux[1]),
+		static_cast<const b200_endpoint_cluster*>(ctx->d_aux[2]), static_cast<const uint32_t*>(ctx->d_aux[3]), static_cast<uint32_t*>(ctx->d_aux[0]), perceptual);
+	return finish(ctx, pOutput_cluster_indices, 0, (size_t)n * 4);
+}
+
+extern "C" int b200_etc1s_find_optimal_selector_clusters_for_each_block(b200_context* ctx, const b200_fosc_block* pInput_block_info, uint32_t total_input_selectors,
+	const b200_fosc_selector* pInput_selectors, const uint32_t* pSelector_cluster_indices, uint32_t* pOutput_selector_cluster_indices, int perceptual)
+{
+	ETC_CHECK_BLOCKS(ctx, "b200_etc1s_find_optimal_selector_clusters_for_each_block");
+	const uint32_t n = ctx->etc_total_blocks;
+	if (!upload(ctx, 1, pInput_block_info, (size_t)n * sizeof(b200_fosc_block))) return 0;
+	if (!upload(ctx, 2, pInput_selectors, (size_t)total_input_selectors * 4)) return 0;
+	if (!upload(ctx, 3, pSelector_cluster_indices, (size_t)total_input_selectors * 4)) return 0;
+	if (!ctx->reserve(ctx->d_aux[0], ctx->aux_cap[0], (size_t)n * 4)) return 0;
+	ctx->launches = 1;
+	B200_CUDA_OK(ctx, cudaEventRecord(ctx->ev0, ctx->stream));
+	const uint32_t warps_per_cta = 4;
+	k_etc1s_fosc<<<(n + warps_per_cta - 1) / warps_per_cta, warps_per_cta * 32, 0, ctx->stream>>>(static_cast<const uint4*>(ctx->d_etc_blocks), n,
+		static_cast<const b200_fosc_block*>(ctx->d_aux[1]), static_cast<const uint32_t*>(ctx->d_aux[2]), static_cast<const uint32_t*>(ctx->d_aux[3]),
+		static_cast<uint32_t*>(ctx->d_aux[0]), perceptual);
+	return finish(ctx, pOutput_selector_cluster_indices, 0, (size_t)n * 4);
+}
+
+extern "C" int b200_etc1s_determine_selectors(b200_context* ctx, const void* pInput_etc_color5_and_inten, void* pOutput_blocks, int perceptual)
+{
+	ETC_CHECK_BLOCKS(ctx, "b200_etc1s_determine_selectors");
+	const uint32_t n = ctx->etc_total_blocks;
+	if (!upload(ctx, 1, pInput_etc_color5_and_inten, (size_t)n * 4)) return 0;
+	if (!ctx->reserve(ctx->d_aux[0], ctx->aux_cap[0], (size_t)n * 8)) return 0;
+	ctx->launches = 1;
+	B200_CUDA_OK(ctx, cudaEventRecord(ctx->ev0, ctx->stream));
+	k_etc1s_determine_selectors<<<(n + 127) / 128, 128, 0, ctx->stream>>>(static_cast<const uint4*>(ctx->d_etc_blocks), n, static_cast<const uint32_t*>(ctx->d_aux[1]),
+		static_cast<uint64_t*>(ctx->d_aux[0]), perceptual);
+	return finish(ctx, pOutput_blocks, 0, (size_t)n * 8);
+}

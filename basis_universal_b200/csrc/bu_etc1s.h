@@ -1,0 +1,180 @@
+// bu_etc1s.h -- ETC1S frontend per-block stages: the arithmetic behind the reference's GPU seam (encoder/basisu_opencl.h:46-141).
+//
+// The contract of each `opencl_*` entry point is what its OpenCL C kernel computes (bin/ocl_kernels.cl); the functions here
+// are bit-exact with those kernels (integer arithmetic throughout, except the block average: one u64->f32 divide and
+// `(int)(avg * (31/255.0f) + .5f)` roundings, reproduced without FMA contraction):
+//   etc1s_optimise            etc1s_optimizer_init / _internal_cluster_fit / _evaluate_solution   cl:772-982
+//   refine / fosc / selectors the three integer kernels                                            cl:1063, 1159, 1227
+// Early-outs in the kernels only drop partial sums that have already lost (`>=` against the running best), so they are
+// omitted; argmin rules (first strictly smaller; the block's own cluster wins ties) are kept.
+#pragma once
+#include "bu_common.h"
+#include "bu_tables.h"
+
+namespace bu {
+
+// basisu::color_distance (encoder/basisu_enc.h:1141), RGB only; identical to the .cl restatement (cl:71).
+BU_FI uint32_t etc_color_distance(bool perceptual, uint32_t a, uint32_t b)
+{
+	const int dr = (int)px_c(a, 0) - (int)px_c(b, 0), dg = (int)px_c(a, 1) - (int)px_c(b, 1), db = (int)px_c(a, 2) - (int)px_c(b, 2);
+	if (perceptual)
+	{
+		const int dl = dr * 14 + dg * 45 + db * 5;
+		const int dcr = dr * 64 - dl, dcb = db * 64 - dl;
+		return ((uint32_t)(dl * dl) >> 5) + ((((uint32_t)(dcr * dcr) >> 5) * 26u) >> 7) + ((((uint32_t)(dcb * dcb) >> 5) * 3u) >> 7);
+	}
+	return (uint32_t)(dr * dr + dg * dg + db * db);
+}
+
+// get_block_colors5 (cl:510): 5-bit base -> four 8-bit block colours of intensity table `inten`.
+BU_FI void etc1s_block_colors(const bu_tables* T, uint32_t r5, uint32_t g5, uint32_t b5, uint32_t inten, uint32_t* colors)
+{
+	const int r = (int)((r5 << 3) | (r5 >> 2)), g = (int)((g5 << 3) | (g5 >> 2)), b = (int)((b5 << 3) | (b5 >> 2));
+	for (int s = 0; s < 4; s++)
+	{
+		const int m = T->etc1_inten[inten * 4 + s];
+		colors[s] = px_make(clamp255i(r + m), clamp255i(g + m), clamp255i(b + m), 255);
+	}
+}
+
+// ETC1S block bytes (etc.h:91 big-endian bitfield): flip = 1, diff = 1, delta = 0, both subblocks share `inten`.
+// raw_sel[i] are RAW ETC1 selector codes (0..3) for texel i = x + 4y (etc_block_pack_raw_selectors, cl:700).
+BU_FI uint64_t etc1s_pack(uint32_t r5, uint32_t g5, uint32_t b5, uint32_t inten, uint32_t lsb_plane, uint32_t msb_plane)
+{
+	// returned as the 8 bytes in memory order packed little-endian into a u64
+	const uint64_t b0 = r5 << 3, b1 = g5 << 3, b2 = b5 << 3, b3 = (inten << 5) | (inten << 2) | 3;
+	const uint64_t b4 = (msb_plane >> 8) & 255, b5_ = msb_plane & 255, b6 = (lsb_plane >> 8) & 255, b7 = lsb_plane & 255;
+	return b0 | (b1 << 8) | (b2 << 16) | (b3 << 24) | (b4 << 32) | (b5_ << 40) | (b6 << 48) | (b7 << 56);
+}
+
+struct etc1s_solution
+{
+	uint64_t err;
+	uint32_t r5, g5, b5, inten;
+	uint32_t lsb_plane, msb_plane; // raw selector bit planes, bit index = x*4+y (only maintained for 16-texel blocks)
+	uint32_t valid;
+};
+
+// One candidate base colour against all (non-pruned) intensity tables, 16-texel block (cl:772). Updates `best` if strictly better.
+BU_HD inline void etc1s_evaluate_block(const bu_tables* T, bool perceptual, const uint32_t* px, uint32_t spread, uint32_t r5, uint32_t g5, uint32_t b5, etc1s_solution& best)
+{
+	uint64_t trial_err = (uint64_t)INT64_MAX;
+	uint32_t trial_inten = 0, trial_lsb = 0, trial_msb = 0;
+	bool valid = false;
+	for (uint32_t inten = 0; inten < 8; inten++)
+	{
+		if (!T->eval_dist[inten * 256 + spread]) continue;
+		uint32_t colors[4];
+		etc1s_block_colors(T, r5, g5, b5, inten, colors);
+		uint64_t total = 0;
+		uint32_t lsb = 0, msb = 0;
+		for (int i = 0; i < 16; i++)
+		{
+			// selector index s -> raw ETC1 code {3,2,0,1}[s]; first strictly smaller error wins (cl:800-825)
+			uint32_t be = etc_color_distance(perceptual, px[i], colors[0]), raw = 3;
+			uint32_t e = etc_color_distance(perceptual, px[i], colors[1]); if (e < be) { be = e; raw = 2; }
+			e = etc_color_distance(perceptual, px[i], colors[2]); if (e < be) { be = e; raw = 0; }
+			e = etc_color_distance(perceptual, px[i], colors[3]); if (e < be) { be = e; raw = 1; }
+			total += be;
+			const uint32_t bit = (uint32_t)((i & 3) * 4 + (i >> 2));
+			lsb |= (raw & 1) << bit; msb |= (raw >> 1) << bit;
+		}
+		if (total < trial_err) { trial_err = total; trial_inten = inten; trial_lsb = lsb; trial_msb = msb; valid = true; }
+	}
+	if (trial_err < best.err)
+	{
+		best.err = trial_err; best.r5 = r5; best.g5 = g5; best.b5 = b5; best.inten = trial_inten;
+		best.lsb_plane = trial_lsb; best.msb_plane = trial_msb; best.valid = valid ? 1u : 0u;
+	}
+}
+
+// Next base colour proposed by the cluster fit for selector-count permutation `perm` (cl:944-973). Returns false if the
+// permutation leaves the colour unchanged (all clamped deltas zero).
+BU_FI bool etc1s_cluster_fit_step(const bu_tables* T, const etc1s_solution& best, const float* avg, uint32_t perm, uint32_t& r1, uint32_t& g1, uint32_t& b1)
+{
+	const int br = (int)((best.r5 << 3) | (best.r5 >> 2)), bg = (int)((best.g5 << 3) | (best.g5 >> 2)), bb = (int)((best.b5 << 3) | (best.b5 >> 2));
+	int dr = 0, dg = 0, db = 0;
+	for (int q = 0; q < 4; q++)
+	{
+		const int yd = T->etc1_inten[best.inten * 4 + q];
+		const int cnt = T->cluster_fit_order[perm * 4 + q];
+		dr += cnt * (clampi(br + yd, 0, 255) - br);
+		dg += cnt * (clampi(bg + yd, 0, 255) - bg);
+		db += cnt * (clampi(bb + yd, 0, 255) - bb);
+	}
+	if (!dr && !dg && !db) return false;
+	const float k = 31 / 255.0f;
+	r1 = (uint32_t)clampi((int)((avg[0] - (float)dr / 8) * k + .5f), 0, 31);
+	g1 = (uint32_t)clampi((int)((avg[1] - (float)dg / 8) * k + .5f), 0, 31);
+	b1 = (uint32_t)clampi((int)((avg[2] - (float)db / 8) * k + .5f), 0, 31);
+	return true;
+}
+
+// encode_etc1s_blocks (cl:984): optimise one 4x4 block, return the 8 block bytes.
+BU_HD inline uint64_t etc1s_encode_block(const bu_tables* T, bool perceptual, uint32_t total_perms, const uint32_t* px)
+{
+	uint32_t mn[3] = { 255, 255, 255 }, mx[3] = { 0, 0, 0 };
+	uint64_t sum[3] = { 0, 0, 0 };
+	for (int i = 0; i < 16; i++)
+		for (uint32_t c = 0; c < 3; c++)
+		{
+			const uint32_t v = px_c(px[i], c);
+			mn[c] = minu(mn[c], v); mx[c] = maxu(mx[c], v); sum[c] += v;
+		}
+	float avg[3];
+	for (int c = 0; c < 3; c++) avg[c] = (float)sum[c] / (float)(uint64_t)16;
+	const uint32_t spread = (uint32_t)maxi(maxi((int)mx[0] - (int)mn[0], (int)mx[1] - (int)mn[1]), (int)mx[2] - (int)mn[2]);
+	const float k = 31 / 255.0f;
+	const uint32_t r0 = (uint32_t)clampi((int)(avg[0] * k + .5f), 0, 31), g0 = (uint32_t)clampi((int)(avg[1] * k + .5f), 0, 31), b0 = (uint32_t)clampi((int)(avg[2] * k + .5f), 0, 31);
+
+	etc1s_solution best;
+	best.err = UINT64_MAX; best.r5 = best.g5 = best.b5 = best.inten = 0; best.lsb_plane = best.msb_plane = 0; best.valid = 0;
+	etc1s_evaluate_block(T, perceptual, px, spread, r0, g0, b0, best);
+	if (best.err != 0)
+		for (uint32_t perm = 0; perm < total_perms; perm++)
+		{
+			uint32_t r1, g1, b1;
+			if (!etc1s_cluster_fit_step(T, best, avg, perm, r1, g1, b1)) continue;
+			etc1s_evaluate_block(T, perceptual, px, spread, r1, g1, b1, best);
+			if (best.err == 0) break;
+		}
+	return etc1s_pack(best.r5, best.g5, best.b5, best.inten, best.lsb_plane, best.msb_plane);
+}
+
+// determine_selectors (cl:1227): selectors for a given (rgb5, inten); ties prefer the lowest selector index.
+BU_HD inline uint64_t etc1s_determine_selectors(const bu_tables* T, bool perceptual, const uint32_t* px, uint32_t color5_inten)
+{
+	const uint32_t r5 = px_c(color5_inten, 0), g5 = px_c(color5_inten, 1), b5 = px_c(color5_inten, 2), inten = px_c(color5_inten, 3);
+	uint32_t colors[4];
+	etc1s_block_colors(T, r5, g5, b5, inten, colors);
+	uint32_t lsb = 0, msb = 0;
+	for (int i = 0; i < 16; i++)
+	{
+		uint32_t be = etc_color_distance(perceptual, px[i], colors[0]), s = 0;
+		for (uint32_t k = 1; k < 4; k++) { const uint32_t e = etc_color_distance(perceptual, px[i], colors[k]); if (e < be) { be = e; s = k; } }
+		const uint32_t raw = T->selector_index_to_etc1[s];
+		const uint32_t bit = (uint32_t)((i & 3) * 4 + (i >> 2));
+		lsb |= (raw & 1) << bit; msb |= (raw >> 1) << bit;
+	}
+	// pack_color5(c_unscaled, scaled=false) clamps each component to 31 (etc.cpp:368)
+	return etc1s_pack(minu(r5, 31), minu(g5, 31), minu(b5, 31), inten & 7, lsb, msb);
+}
+
+// Sum over the 16 texels of the best-of-4 error for one (rgb5, inten) (inner loop of refine_endpoint_clusterization, cl:1103-1126).
+BU_FI uint64_t etc1s_block_error(const bu_tables* T, bool perceptual, const uint32_t* px, uint32_t r5, uint32_t g5, uint32_t b5, uint32_t inten)
+{
+	uint32_t colors[4];
+	etc1s_block_colors(T, r5, g5, b5, inten, colors);
+	uint64_t total = 0;
+	for (int i = 0; i < 16; i++)
+	{
+		uint32_t be = etc_color_distance(perceptual, px[i], colors[0]);
+		be = minu(be, etc_color_distance(perceptual, px[i], colors[1]));
+		be = minu(be, etc_color_distance(perceptual, px[i], colors[2]));
+		be = minu(be, etc_color_distance(perceptual, px[i], colors[3]));
+		total += be;
+	}
+	return total;
+}
+
+} // namespace bu

@@ -116,10 +116,10 @@ BU_HD inline void finish_block(const bu_tables* T, const level_opts& o, int leve
 	ycc src_y[16], dec_y[16];
 	for (int i = 0; i < 16; i++) { src_y[i] = to_ycc(px[i]); dec_y[i] = to_ycc(dec[i]); }
 	etc1_hint hint;
-	hint.err = UINT64_MAX; hint.flip = 0; hint.diff = 0; hint.inten0 = 0; hint.inten1 = 0; hint.bias = 0;
+	hint.err = UINT64_MAX; hint.order = 0; hint.flip = 0; hint.diff = 0; hint.inten0 = 0; hint.inten1 = 0; hint.bias = 0;
 	for (uint32_t flip = so.first_flip; flip < so.last_flip; flip++)
 		for (uint32_t individ = so.first_individ; individ < so.last_individ; individ++)
-			etc1_hint_group(T, so, flip, individ, src_y, dec_y, dec, hint);
+			etc1_hint_trials(T, so, flip, individ, 0, 1, src_y, dec_y, dec, hint);
 
 	pack_block(T, best, ep, w, hint, eac_table, eac_mul, h0, h1, out16);
 }

@@ -51,4 +51,9 @@ struct bu_tables
 	uint16_t solid_cfg_ofs[256];
 	uint16_t solid_cfg[2048];
 	uint16_t etc1_inverse[64 * 256];
+
+	// ETC1S optimiser: selector-count permutations tried by the cluster fit (etc.cpp:267) and the intensity-table pruning
+	// table indexed by [inten_table][max component spread] (etc.cpp:1091).
+	uint8_t  cluster_fit_order[165 * 4];
+	uint8_t  eval_dist[8 * 256];
 };

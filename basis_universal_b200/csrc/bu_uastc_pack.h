@@ -396,10 +396,11 @@ BU_FI ycc to_ycc(uint32_t p)
 	v.cr = (r << 8) - v.y;
 	return v;
 }
+BU_FI uint64_t sq_u64(int d) { const uint32_t a = (uint32_t)(d < 0 ? -d : d); return (uint64_t)a * (uint64_t)a; } // one IMAD.WIDE.U32
 BU_FI uint64_t ycc_diff(const ycc& a, const ycc& b)
 {
-	const int64_t dy = a.y - b.y, dcb = a.cb - b.cb, dcr = a.cr - b.cr;
-	return (uint64_t)(dy * dy * 4 + dcr * dcr + dcb * dcb);
+	// uastc_enc.cpp:2645 color_diff: 4*dy^2 + dcr^2 + dcb^2 in 64 bits (|d| < 2^18, so each square needs up to 35 bits)
+	return sq_u64(a.y - b.y) * 4 + sq_u64(a.cr - b.cr) + sq_u64(a.cb - b.cb);
 }
 
 BU_FI int gray_distance2(uint32_t p, int r, int g, int b)
@@ -477,6 +478,7 @@ BU_HD inline void etc1_apply_bias(const int* in, uint32_t bias, int limit, uint3
 struct etc1_hint
 {
 	uint64_t err;      // UINT64_MAX = no trial accepted
+	uint32_t order;    // position of the accepted trial in the reference's (flip, individ, bias_iter) loop nest: the tie-breaker
 	uint8_t flip, diff, inten0, inten1, bias;
 };
 
@@ -518,8 +520,9 @@ BU_HD inline etc1_search_opts etc1_search_setup(const bu_tables* T, uint32_t mod
 	return o;
 }
 
-// One (flip, individ) trial group: all bias iterations, best kept with first-strictly-less.
-BU_NI inline void etc1_hint_group(const bu_tables* T, const etc1_search_opts& o, uint32_t flip, uint32_t individ,
+// Trials bias_iter = first, first + stride, ... of one (flip, individ) combination; best kept with first-strictly-less.
+// Splitting a combination's bias iterations over threads and reducing by (err, order) reproduces the sequential result.
+BU_NI inline void etc1_hint_trials(const bu_tables* T, const etc1_search_opts& o, uint32_t flip, uint32_t individ, uint32_t first, uint32_t stride,
 	const ycc* src_y, const ycc* dec_y, const uint32_t* dec, etc1_hint& best)
 {
 	const uint8_t sorted_bias[32] = { 13, 0, 22, 29, 27, 12, 26, 9, 30, 31, 8, 10, 25, 2, 23, 5, 15, 7, 3, 11, 6, 17, 28, 18, 1, 19, 20, 21, 24, 4, 14, 16 };
@@ -547,7 +550,7 @@ BU_NI inline void etc1_hint_group(const bu_tables* T, const etc1_search_opts& o,
 		for (int c = 0; c < 3; c++) unbiased[s][c] = (int)(uint8_t)((sum[c] * (uint32_t)mul + 1020) / (8 * 255));
 	}
 
-	for (uint32_t bias_iter = 0; bias_iter < o.last_bias; bias_iter++)
+	for (uint32_t bias_iter = first; bias_iter < o.last_bias; bias_iter += stride)
 	{
 		const uint32_t bias = o.sorted_bias_table ? sorted_bias[bias_iter] : bias_iter;
 
@@ -577,44 +580,72 @@ BU_NI inline void etc1_hint_group(const bu_tables* T, const etc1_search_opts& o,
 			}
 		}
 
+		// An ETC1 table colour is base + m on every channel, so unless a channel clamps, its luma is y_base + 256 m and its
+		// chroma equals the base's: the four candidates for a texel differ in the luma term only and
+		//     color_diff = 4 (dy - 256 m)^2 + dcr^2 + dcb^2
+		// is the same integer expression the reference evaluates, factored. Clamping (base + m outside 0..255) falls back
+		// to the general form. Both the table scan and the final selector choice use this.
 		uint32_t inten[2] = { 0, 0 };
+		uint64_t err = 0;
 		for (int s = 0; s < 2; s++)
 		{
-			int range = 0;
+			int range = 0, bmin = 255, bmax = 0;
 			for (int c = 0; c < 3; c++)
 			{
 				range = maxi(range, iabsi(mx[s][c] - base[s][c]));
 				range = maxi(range, iabsi(base[s][c] - mn[s][c]));
+				bmin = mini(bmin, base[s][c]); bmax = maxi(bmax, base[s][c]);
 			}
 			const uint32_t limit = o.all_inten_tables ? 8u : ((range > 51) ? 8u : (range >= 7 ? 4u : 2u));
+			const ycc base_y = to_ycc(px_make((uint32_t)base[s][0], (uint32_t)base[s][1], (uint32_t)base[s][2], 255));
+
+			// per texel: luma delta to the base and the (table independent) chroma term
+			int dy[8];
+			uint64_t chroma[8];
+			for (int j = 0; j < 8; j++)
+			{
+				const int x = flip ? (j & 3) : (s * 2 + (j >> 2)), y = flip ? (s * 2 + (j >> 2)) : (j & 3);
+				const ycc& q = dec_y[x + y * 4];
+				dy[j] = base_y.y - q.y;
+				chroma[j] = sq_u64(base_y.cr - q.cr) + sq_u64(base_y.cb - q.cb);
+			}
 
 			uint64_t best_sub = UINT64_MAX;
 			for (uint32_t t = 0; t < limit; t++)
 			{
-				ycc tab[4];
-				for (int k = 0; k < 4; k++)
-				{
-					const int m = T->etc1_inten[t * 4 + k];
-					tab[k] = to_ycc(px_make(clamp255i(base[s][0] + m), clamp255i(base[s][1] + m), clamp255i(base[s][2] + m), 255));
-				}
+				const int m0 = T->etc1_inten[t * 4], m3 = T->etc1_inten[t * 4 + 3]; // most negative / most positive modifier
 				uint64_t total = 0;
-				for (int j = 0; j < 8; j++)
+				if (bmin + m0 >= 0 && bmax + m3 <= 255)
 				{
-					const int x = flip ? (j & 3) : (s * 2 + (j >> 2)), y = flip ? (s * 2 + (j >> 2)) : (j & 3);
-					const ycc& q = dec_y[x + y * 4];
-					total += minu64(minu64(ycc_diff(tab[0], q), ycc_diff(tab[1], q)), minu64(ycc_diff(tab[2], q), ycc_diff(tab[3], q)));
+					for (int j = 0; j < 8; j++)
+					{
+						uint64_t e = sq_u64(dy[j] + 256 * m0);
+						for (int k = 1; k < 4; k++) e = minu64(e, sq_u64(dy[j] + 256 * (int)T->etc1_inten[t * 4 + k]));
+						total += e * 4 + chroma[j];
+					}
+				}
+				else
+				{
+					ycc tab[4];
+					for (int k = 0; k < 4; k++)
+					{
+						const int m = T->etc1_inten[t * 4 + k];
+						tab[k] = to_ycc(px_make(clamp255i(base[s][0] + m), clamp255i(base[s][1] + m), clamp255i(base[s][2] + m), 255));
+					}
+					for (int j = 0; j < 8; j++)
+					{
+						const int x = flip ? (j & 3) : (s * 2 + (j >> 2)), y = flip ? (s * 2 + (j >> 2)) : (j & 3);
+						const ycc& q = dec_y[x + y * 4];
+						total += minu64(minu64(ycc_diff(tab[0], q), ycc_diff(tab[1], q)), minu64(ycc_diff(tab[2], q), ycc_diff(tab[3], q)));
+					}
 				}
 				if (total < best_sub) { best_sub = total; inten[s] = t; }
 				// Reference quirk (uastc_enc.cpp:2933): in the non-flipped layout the early-out sits outside the row loop, so the
 				// first table that fails to improve ends the whole table scan; in the flipped layout it only ends that table's rows.
 				else if (!flip) break;
 			}
-		}
 
-		// Error of this trial against the ORIGINAL block, selectors chosen against the decoded UASTC block.
-		uint64_t err = 0;
-		for (int s = 0; s < 2; s++)
-		{
+			// Error of this trial against the ORIGINAL block, selectors chosen against the decoded UASTC block (lowest index on ties).
 			ycc tab[4];
 			for (int k = 0; k < 4; k++)
 			{
@@ -635,6 +666,7 @@ BU_NI inline void etc1_hint_group(const bu_tables* T, const etc1_search_opts& o,
 		if (err < best.err)
 		{
 			best.err = err;
+			best.order = (flip * 2 + individ) * 32 + bias_iter;
 			best.flip = (uint8_t)flip; best.diff = (uint8_t)(individ ? 0 : 1);
 			best.inten0 = (uint8_t)inten[0]; best.inten1 = (uint8_t)inten[1]; best.bias = (uint8_t)bias;
 		}

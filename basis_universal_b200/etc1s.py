@@ -1,0 +1,95 @@
+"""Host-side mirror of the reference's ETC1S GPU seam (encoder/basisu_opencl.h:46-141): one method per `opencl_*` entry
+point, same argument meaning, same failure behaviour (a False/exception tells the caller to use its own CPU path).
+
+Packed argument structs as numpy dtypes (opencl.h:49-135):"""
+import ctypes
+import numpy as np
+from ._lib import lib, B200Error
+
+pixel_cluster_dtype = np.dtype([("total_pixels", "<u8"), ("first_pixel_index", "<u8")])                                                           # cl_pixel_cluster
+block_info_dtype = np.dtype([("first_cluster_ofs", "<u2"), ("num_clusters", "<u2"), ("cur_cluster_index", "<u2"), ("cur_cluster_etc_inten", "u1")])  # cl_block_info_struct
+endpoint_cluster_dtype = np.dtype([("r", "u1"), ("g", "u1"), ("b", "u1"), ("a", "u1"), ("etc_inten", "u1"), ("cluster_index", "<u2")])               # cl_endpoint_cluster_struct
+fosc_block_dtype = np.dtype([("r", "u1"), ("g", "u1"), ("b", "u1"), ("inten", "u1"), ("first_selector", "<u4"), ("num_selectors", "<u4")])          # fosc_block_struct
+
+OPENCL_ENCODE_ETC1S_MAX_PERMS = 165  # opencl.h:44
+
+
+def _p(a):
+    return ctypes.c_void_p(a.ctypes.data)
+
+
+class Etc1sContext:
+    """opencl_context equivalent: one device, one stream, the slice's source blocks resident in HBM."""
+
+    def __init__(self, device=0):
+        self._lib = lib()
+        self._ctx = self._lib.b200_create_context(int(device))
+        if not self._ctx:
+            raise B200Error("b200_create_context failed: " + self._lib.b200_last_error(None).decode())
+        self.total_blocks = 0
+
+    def close(self):
+        if getattr(self, "_ctx", None):
+            self._lib.b200_destroy_context(self._ctx)
+            self._ctx = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, ok, what):
+        if not ok:
+            raise B200Error(f"{what} failed: {self._lib.b200_last_error(self._ctx).decode()}")
+
+    @property
+    def last_kernel_ms(self):
+        return float(self._lib.b200_last_kernel_ms(self._ctx))
+
+    def set_pixel_blocks(self, blocks):
+        """opencl_set_pixel_blocks(ctx, total_blocks, pPixel_blocks)"""
+        blocks = np.ascontiguousarray(blocks, np.uint8)
+        assert blocks.ndim == 2 and blocks.shape[1] == 64
+        self._check(self._lib.b200_etc1s_set_pixel_blocks(self._ctx, blocks.shape[0], _p(blocks)), "b200_etc1s_set_pixel_blocks")
+        self.total_blocks = blocks.shape[0]
+
+    def encode_etc1s_blocks(self, perceptual, total_perms):
+        """opencl_encode_etc1s_blocks(ctx, pOutput_blocks, perceptual, total_perms) -> (N, 8) uint8 etc_blocks"""
+        out = np.empty((self.total_blocks, 8), np.uint8)
+        self._check(self._lib.b200_etc1s_encode_blocks(self._ctx, _p(out), int(bool(perceptual)), int(total_perms)), "b200_etc1s_encode_blocks")
+        return out
+
+    def encode_etc1s_pixel_clusters(self, clusters, pixels, weights, perceptual, total_perms):
+        """opencl_encode_etc1s_pixel_clusters(...) -> (total_clusters, 8) uint8; only bytes 0..3 (colour, intensity, flags) are defined."""
+        clusters = np.ascontiguousarray(clusters); pixels = np.ascontiguousarray(pixels, np.uint8); weights = np.ascontiguousarray(weights, np.uint32)
+        n = clusters.shape[0]
+        out = np.zeros((n, 8), np.uint8)
+        self._check(self._lib.b200_etc1s_encode_pixel_clusters(self._ctx, _p(out), n, _p(clusters), ctypes.c_uint64(pixels.shape[0]), _p(pixels), _p(weights),
+                                                                int(bool(perceptual)), int(total_perms)), "b200_etc1s_encode_pixel_clusters")
+        return out
+
+    def refine_endpoint_clusterization(self, block_info, cluster_info, sorted_block_indices, perceptual):
+        """opencl_refine_endpoint_clusterization(...) -> (N,) uint32 best cluster index per block"""
+        block_info = np.ascontiguousarray(block_info); cluster_info = np.ascontiguousarray(cluster_info)
+        sorted_block_indices = np.ascontiguousarray(sorted_block_indices, np.uint32)
+        out = np.empty(self.total_blocks, np.uint32)
+        self._check(self._lib.b200_etc1s_refine_endpoint_clusterization(self._ctx, _p(block_info), cluster_info.shape[0], _p(cluster_info), _p(sorted_block_indices), _p(out),
+                                                                         int(bool(perceptual))), "b200_etc1s_refine_endpoint_clusterization")
+        return out
+
+    def find_optimal_selector_clusters_for_each_block(self, block_info, selectors, selector_cluster_indices, perceptual):
+        """opencl_find_optimal_selector_clusters_for_each_block(...) -> (N,) uint32 selector cluster index per block"""
+        block_info = np.ascontiguousarray(block_info); selectors = np.ascontiguousarray(selectors, np.uint32)
+        selector_cluster_indices = np.ascontiguousarray(selector_cluster_indices, np.uint32)
+        out = np.empty(self.total_blocks, np.uint32)
+        self._check(self._lib.b200_etc1s_find_optimal_selector_clusters_for_each_block(self._ctx, _p(block_info), selectors.shape[0], _p(selectors), _p(selector_cluster_indices),
+                                                                                        _p(out), int(bool(perceptual))), "b200_etc1s_find_optimal_selector_clusters_for_each_block")
+        return out
+
+    def determine_selectors(self, color5_and_inten, perceptual):
+        """opencl_determine_selectors(ctx, pInput_etc_color5_and_inten, pOutput_blocks, perceptual) -> (N, 8) uint8 etc_blocks"""
+        c = np.ascontiguousarray(color5_and_inten, np.uint8)
+        out = np.empty((self.total_blocks, 8), np.uint8)
+        self._check(self._lib.b200_etc1s_determine_selectors(self._ctx, _p(c), _p(out), int(bool(perceptual))), "b200_etc1s_determine_selectors")
+        return out

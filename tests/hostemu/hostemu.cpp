@@ -86,3 +86,53 @@ EMU_API uint64_t emu_color_cell_compression(const uint8_t* pPixels, uint32_t num
 
 EMU_API uint32_t emu_sizeof_candidate() { return (uint32_t)sizeof(candidate); }
 EMU_API uint32_t emu_sizeof_tables() { return (uint32_t)sizeof(bu_tables); }
+
+// ---- ETC1S stages (bu_etc1s.h) ----------------------------------------------------------------------------------------------
+#include "../../basis_universal_b200/csrc/bu_etc1s.h"
+#include "../../include/basisu_b200.h"
+
+EMU_API void emu_etc1s_encode_blocks(const uint8_t* pBlocks, uint32_t n, uint8_t* pOut, int perceptual, uint32_t total_perms)
+{
+	for (uint32_t i = 0; i < n; i++)
+	{
+		uint32_t px[16];
+		memcpy(px, pBlocks + (size_t)i * 64, 64);
+		const uint64_t v = etc1s_encode_block(&g_tables, perceptual != 0, total_perms, px);
+		memcpy(pOut + (size_t)i * 8, &v, 8);
+	}
+}
+
+EMU_API void emu_etc1s_determine_selectors(const uint8_t* pBlocks, uint32_t n, const uint32_t* pColor5_inten, uint8_t* pOut, int perceptual)
+{
+	for (uint32_t i = 0; i < n; i++)
+	{
+		uint32_t px[16];
+		memcpy(px, pBlocks + (size_t)i * 64, 64);
+		const uint64_t v = etc1s_determine_selectors(&g_tables, perceptual != 0, px, pColor5_inten[i]);
+		memcpy(pOut + (size_t)i * 8, &v, 8);
+	}
+}
+
+EMU_API void emu_etc1s_refine(const uint8_t* pBlocks, uint32_t n, const b200_block_info* info, const b200_endpoint_cluster* clusters, uint32_t* out, int perceptual)
+{
+	for (uint32_t bi = 0; bi < n; bi++)
+	{
+		uint32_t px[16];
+		memcpy(px, pBlocks + (size_t)bi * 64, 64);
+		const b200_block_info in = info[bi];
+		uint64_t best_err = UINT64_MAX;
+		uint32_t best_index = 0;
+		for (uint32_t k = 0; k < in.num_clusters; k++)
+		{
+			const b200_endpoint_cluster c = clusters[(uint32_t)in.first_cluster_ofs + k];
+			if (c.etc_inten > in.cur_cluster_etc_inten) continue;
+			const uint64_t e = etc1s_block_error(&g_tables, perceptual != 0, px, c.unscaled_r, c.unscaled_g, c.unscaled_b, c.etc_inten);
+			if (e < best_err || (c.cluster_index == in.cur_cluster_index && e == best_err))
+			{
+				best_err = e; best_index = c.cluster_index;
+				if (!best_err) break;
+			}
+		}
+		out[bi] = best_index;
+	}
+}

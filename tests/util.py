@@ -164,3 +164,102 @@ def uastc_fields(ref, block16):
     d["ep"] = out[11:29].tolist()
     d["w"] = out[29:61].tolist()
     return d
+
+
+OCL_SO = os.path.join(ROOT, "oracle", "_ref", "libocl_ref.so")
+
+
+class OclRef:
+    """The reference's own OpenCL C kernels (bin/ocl_kernels.cl) compiled for the host by oracle/Makefile (see oracle/ocl_host.cpp)."""
+
+    def __init__(self):
+        self.lib = ctypes.CDLL(OCL_SO)
+        self.threads = os.cpu_count() or 1
+
+    def encode_etc1s_blocks(self, blocks, perceptual, total_perms):
+        blocks = np.ascontiguousarray(blocks, np.uint8)
+        out = np.zeros((blocks.shape[0], 8), np.uint8)
+        self.lib.oclref_encode_etc1s_blocks(_ptr(blocks), ctypes.c_uint32(blocks.shape[0]), _ptr(out), int(perceptual), int(total_perms), ctypes.c_uint32(self.threads))
+        return out
+
+    def encode_pixel_clusters(self, clusters, pixels, weights, perceptual, total_perms):
+        clusters = np.ascontiguousarray(clusters, np.uint64)  # (n, 2): total_pixels, first_pixel_index
+        pixels = np.ascontiguousarray(pixels, np.uint8); weights = np.ascontiguousarray(weights, np.uint32)
+        out = np.zeros((clusters.shape[0], 8), np.uint8)
+        self.lib.oclref_encode_etc1s_pixel_clusters(_ptr(clusters), ctypes.c_uint32(clusters.shape[0]), _ptr(pixels), _ptr(weights), _ptr(out), int(perceptual), int(total_perms), ctypes.c_uint32(self.threads))
+        return out
+
+    def refine(self, blocks, block_info, cluster_info, sorted_idx, perceptual):
+        blocks = np.ascontiguousarray(blocks, np.uint8)
+        out = np.zeros(blocks.shape[0], np.uint32)
+        self.lib.oclref_refine_endpoint_clusterization(_ptr(blocks), ctypes.c_uint32(blocks.shape[0]), _ptr(block_info), _ptr(cluster_info), _ptr(sorted_idx), _ptr(out), int(perceptual), ctypes.c_uint32(self.threads))
+        return out
+
+    def fosc(self, blocks, block_info, selectors, cluster_indices, perceptual):
+        blocks = np.ascontiguousarray(blocks, np.uint8)
+        out = np.zeros(blocks.shape[0], np.uint32)
+        self.lib.oclref_find_optimal_selector_clusters_for_each_block(_ptr(blocks), ctypes.c_uint32(blocks.shape[0]), _ptr(block_info), _ptr(selectors), _ptr(cluster_indices), _ptr(out), int(perceptual), ctypes.c_uint32(self.threads))
+        return out
+
+    def determine_selectors(self, blocks, color5_inten, perceptual):
+        blocks = np.ascontiguousarray(blocks, np.uint8)
+        out = np.zeros((blocks.shape[0], 8), np.uint8)
+        self.lib.oclref_determine_selectors(_ptr(blocks), ctypes.c_uint32(blocks.shape[0]), _ptr(color5_inten), _ptr(out), int(perceptual), ctypes.c_uint32(self.threads))
+        return out
+
+
+BLOCK_INFO_DT = np.dtype([("first_cluster_ofs", "<u2"), ("num_clusters", "<u2"), ("cur_cluster_index", "<u2"), ("cur_cluster_etc_inten", "u1")])          # cl_block_info_struct, 7 B
+ENDPOINT_CLUSTER_DT = np.dtype([("r", "u1"), ("g", "u1"), ("b", "u1"), ("a", "u1"), ("etc_inten", "u1"), ("cluster_index", "<u2")])                       # cl_endpoint_cluster_struct, 7 B
+FOSC_BLOCK_DT = np.dtype([("r", "u1"), ("g", "u1"), ("b", "u1"), ("inten", "u1"), ("first_selector", "<u4"), ("num_selectors", "<u4")])                  # fosc_block_struct, 12 B
+
+
+def etc1s_stage_inputs(blocks, seed, parents=8, clusters_per_parent=(3, 40), selectors_per_parent=(5, 300)):
+    """Synthetic but structurally faithful inputs for the refine / fosc / determine_selectors stages."""
+    rng = np.random.default_rng(seed)
+    n = blocks.shape[0]
+    sizes = rng.integers(clusters_per_parent[0], clusters_per_parent[1], parents)
+    first = np.concatenate([[0], np.cumsum(sizes)[:-1]])
+    total = int(sizes.sum())
+    ci = np.zeros(total, ENDPOINT_CLUSTER_DT)
+    mean = blocks.reshape(n, 16, 4)[:, :, :3].mean(1)
+    pick = rng.integers(0, n, total)
+    base = np.clip(np.round(mean[pick] * 31 / 255 + rng.integers(-2, 3, (total, 3))), 0, 31).astype(np.uint8)
+    ci["r"], ci["g"], ci["b"], ci["a"] = base[:, 0], base[:, 1], base[:, 2], 255
+    ci["etc_inten"] = rng.integers(0, 8, total)
+    ci["cluster_index"] = rng.permutation(total).astype(np.uint16)
+    bi = np.zeros(n, BLOCK_INFO_DT)
+    par = rng.integers(0, parents, n)
+    bi["first_cluster_ofs"] = first[par]; bi["num_clusters"] = sizes[par]
+    own = first[par] + rng.integers(0, 1 << 30, n) % sizes[par]
+    bi["cur_cluster_index"] = ci["cluster_index"][own]; bi["cur_cluster_etc_inten"] = ci["etc_inten"][own]
+    sorted_idx = np.argsort(bi["cur_cluster_index"], kind="stable").astype(np.uint32)
+    ssz = rng.integers(selectors_per_parent[0], selectors_per_parent[1], parents)
+    sfirst = np.concatenate([[0], np.cumsum(ssz)[:-1]])
+    stotal = int(ssz.sum())
+    sels = rng.integers(0, 1 << 32, stotal, dtype=np.uint64).astype(np.uint32)
+    sels[rng.integers(0, stotal, stotal // 4)] = np.uint32(0xAAAAAAAA)
+    sel_cluster_idx = rng.permutation(stotal).astype(np.uint32)
+    fb = np.zeros(n, FOSC_BLOCK_DT)
+    c5 = np.clip(np.round(mean * 31 / 255), 0, 31).astype(np.uint8)
+    fb["r"], fb["g"], fb["b"] = c5[:, 0], c5[:, 1], c5[:, 2]
+    fb["inten"] = rng.integers(0, 8, n)
+    spar = rng.integers(0, parents, n)
+    fb["first_selector"] = sfirst[spar]; fb["num_selectors"] = ssz[spar]
+    color5_inten = np.stack([c5[:, 0], c5[:, 1], c5[:, 2], fb["inten"]], -1).astype(np.uint8)
+    return dict(block_info=bi, cluster_info=ci, sorted_idx=sorted_idx, fosc_blocks=fb, selectors=sels, sel_cluster_idx=sel_cluster_idx, color5_inten=np.ascontiguousarray(color5_inten))
+
+
+def pixel_cluster_inputs(seed, n_clusters=40):
+    rng = np.random.default_rng(seed)
+    sizes = np.concatenate([rng.integers(1, 40, n_clusters // 2), rng.integers(40, 3000, n_clusters - n_clusters // 2)])
+    first = np.concatenate([[0], np.cumsum(sizes)[:-1]])
+    total = int(sizes.sum())
+    px = np.zeros((total, 4), np.uint8)
+    for s, f in zip(sizes, first):
+        base = rng.integers(0, 256, 3)
+        spread = rng.integers(1, 80)
+        px[f:f + s, :3] = np.clip(base + rng.integers(-spread, spread + 1, (s, 3)), 0, 255)
+    px[:, 3] = 255
+    weights = rng.integers(1, 50, total).astype(np.uint32)
+    clusters = np.stack([sizes, first], -1).astype(np.uint64)
+    return clusters, px, weights
