@@ -30,6 +30,7 @@ def lib():
         L.b200_last_kernel_ms.argtypes = [vp]
         L.b200_last_launch_count.restype = u32
         L.b200_last_launch_count.argtypes = [vp]
+        L.b200_global_launch_count.restype = ctypes.c_uint64
         L.b200_last_stage_ms.restype = ctypes.c_float
         L.b200_last_stage_ms.argtypes = [vp, u32]
         L.b200_timer_start.restype = i32
@@ -64,5 +65,5 @@ EXPORTS = [
     "b200_etc1s_set_pixel_blocks", "b200_etc1s_encode_blocks", "b200_etc1s_encode_pixel_clusters",
     "b200_etc1s_refine_endpoint_clusterization", "b200_etc1s_find_optimal_selector_clusters_for_each_block",
     "b200_etc1s_determine_selectors", "b200_last_kernel_ms", "b200_last_launch_count", "b200_last_stage_ms",
-    "b200_timer_start", "b200_timer_stop_ms",
+    "b200_timer_start", "b200_timer_stop_ms", "b200_global_launch_count",
 ]

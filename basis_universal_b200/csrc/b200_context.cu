@@ -2,6 +2,7 @@
 #include "b200_internal.h"
 
 static char g_create_err[256] = "";
+unsigned long long g_b200_total_launches = 0;
 
 extern "C" int b200_device_count(void)
 {
@@ -71,3 +72,5 @@ extern "C" float b200_timer_stop_ms(b200_context* ctx)
 	if (cudaEventElapsedTime(&ms, ctx->ev_t0, ctx->ev_t1) != cudaSuccess) return -1.0f;
 	return ms;
 }
+
+extern "C" uint64_t b200_global_launch_count(void) { return g_b200_total_launches; }

@@ -265,7 +265,7 @@ extern "C" int b200_etc1s_encode_blocks(b200_context* ctx, void* pOutput_blocks,
 	if (total_perms > 165) { ctx->fail("b200_etc1s_encode_blocks: total_perms > 165"); return 0; }
 	const uint32_t n = ctx->etc_total_blocks;
 	if (!ctx->reserve(ctx->d_aux[0], ctx->aux_cap[0], (size_t)n * 8)) return 0;
-	ctx->launches = 1;
+	ctx->launches = 1; __atomic_add_fetch(&g_b200_total_launches, 1, __ATOMIC_RELAXED);
 	B200_CUDA_OK(ctx, cudaEventRecord(ctx->ev0, ctx->stream));
 	k_etc1s_encode_blocks<<<(n + 127) / 128, 128, 0, ctx->stream>>>(static_cast<const uint4*>(ctx->d_etc_blocks), n, static_cast<uint64_t*>(ctx->d_aux[0]), perceptual, total_perms);
 	return finish(ctx, pOutput_blocks, 0, (size_t)n * 8);
@@ -282,7 +282,7 @@ extern "C" int b200_etc1s_encode_pixel_clusters(b200_context* ctx, void* pOutput
 	if (!upload(ctx, 2, pPixels, (size_t)total_pixels * 4)) return 0;
 	if (!upload(ctx, 3, pPixel_weights, (size_t)total_pixels * 4)) return 0;
 	if (!ctx->reserve(ctx->d_aux[0], ctx->aux_cap[0], (size_t)total_clusters * 8)) return 0;
-	ctx->launches = 1;
+	ctx->launches = 1; __atomic_add_fetch(&g_b200_total_launches, 1, __ATOMIC_RELAXED);
 	B200_CUDA_OK(ctx, cudaEventRecord(ctx->ev0, ctx->stream));
 	const uint32_t warps_per_cta = 4;
 	k_etc1s_pixel_clusters<<<(total_clusters + warps_per_cta - 1) / warps_per_cta, warps_per_cta * 32, 0, ctx->stream>>>(
@@ -300,7 +300,7 @@ extern "C" int b200_etc1s_refine_endpoint_clusterization(b200_context* ctx, cons
 	if (!upload(ctx, 2, pCluster_info, (size_t)total_clusters * sizeof(b200_endpoint_cluster))) return 0;
 	if (!upload(ctx, 3, pSorted_block_indices, (size_t)n * 4)) return 0;
 	if (!ctx->reserve(ctx->d_aux[0], ctx->aux_cap[0], (size_t)n * 4)) return 0;
-	ctx->launches = 1;
+	ctx->launches = 1; __atomic_add_fetch(&g_b200_total_launches, 1, __ATOMIC_RELAXED);
 	B200_CUDA_OK(ctx, cudaEventRecord(ctx->ev0, ctx->stream));
 	k_etc1s_refine<<<(n + 127) / 128, 128, 0, ctx->stream>>>(static_cast<const uint4*>(ctx->d_etc_blocks), n, static_cast<const b200_block_info*>(ctx->d_aux[1]),
 		static_cast<const b200_endpoint_cluster*>(ctx->d_aux[2]), static_cast<const uint32_t*>(ctx->d_aux[3]), static_cast<uint32_t*>(ctx->d_aux[0]), perceptual);
@@ -316,7 +316,7 @@ extern "C" int b200_etc1s_find_optimal_selector_clusters_for_each_block(b200_con
 	if (!upload(ctx, 2, pInput_selectors, (size_t)total_input_selectors * 4)) return 0;
 	if (!upload(ctx, 3, pSelector_cluster_indices, (size_t)total_input_selectors * 4)) return 0;
 	if (!ctx->reserve(ctx->d_aux[0], ctx->aux_cap[0], (size_t)n * 4)) return 0;
-	ctx->launches = 1;
+	ctx->launches = 1; __atomic_add_fetch(&g_b200_total_launches, 1, __ATOMIC_RELAXED);
 	B200_CUDA_OK(ctx, cudaEventRecord(ctx->ev0, ctx->stream));
 	const uint32_t warps_per_cta = 4;
 	k_etc1s_fosc<<<(n + warps_per_cta - 1) / warps_per_cta, warps_per_cta * 32, 0, ctx->stream>>>(static_cast<const uint4*>(ctx->d_etc_blocks), n,
@@ -331,7 +331,7 @@ extern "C" int b200_etc1s_determine_selectors(b200_context* ctx, const void* pIn
 	const uint32_t n = ctx->etc_total_blocks;
 	if (!upload(ctx, 1, pInput_etc_color5_and_inten, (size_t)n * 4)) return 0;
 	if (!ctx->reserve(ctx->d_aux[0], ctx->aux_cap[0], (size_t)n * 8)) return 0;
-	ctx->launches = 1;
+	ctx->launches = 1; __atomic_add_fetch(&g_b200_total_launches, 1, __ATOMIC_RELAXED);
 	B200_CUDA_OK(ctx, cudaEventRecord(ctx->ev0, ctx->stream));
 	k_etc1s_determine_selectors<<<(n + 127) / 128, 128, 0, ctx->stream>>>(static_cast<const uint4*>(ctx->d_etc_blocks), n, static_cast<const uint32_t*>(ctx->d_aux[1]),
 		static_cast<uint64_t*>(ctx->d_aux[0]), perceptual);

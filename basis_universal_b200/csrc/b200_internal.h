@@ -6,6 +6,8 @@
 #include <string.h>
 #include "../../include/basisu_b200.h"
 
+extern unsigned long long g_b200_total_launches;
+
 struct b200_context
 {
 	int device;

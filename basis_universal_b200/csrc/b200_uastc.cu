@@ -139,14 +139,14 @@ static bool uastc_encode_chunk(b200_context* ctx, const uint4* dBlocks, uint32_t
 	cudaEvent_t* ev = ctx->chunk_events();
 	if (ev) cudaEventRecord(ev[0], ctx->stream);
 	k_classify_rank<<<gx, tpb, 0, ctx->stream>>>(dBlocks, n, meta, dOut, o);
-	ctx->launches++;
+	ctx->launches++; __atomic_add_fetch(&g_b200_total_launches, 1, __ATOMIC_RELAXED);
 	if (ev) cudaEventRecord(ev[1], ctx->stream);
 	// gridDim.y is limited to 65535; nslots <= 176.
 	k_candidates<<<dim3(gx, nslots), tpb, 0, ctx->stream>>>(dBlocks, n, meta, cands, static_cast<const slot_desc*>(ctx->d_slots), 0, o);
-	ctx->launches++;
+	ctx->launches++; __atomic_add_fetch(&g_b200_total_launches, 1, __ATOMIC_RELAXED);
 	if (ev) cudaEventRecord(ev[2], ctx->stream);
 	k_finish<<<gx, tpb, 0, ctx->stream>>>(dBlocks, n, meta, cands, nslots, dOut, o, level, flags);
-	ctx->launches++;
+	ctx->launches++; __atomic_add_fetch(&g_b200_total_launches, 1, __ATOMIC_RELAXED);
 	if (ev) cudaEventRecord(ev[3], ctx->stream);
 	B200_CUDA_OK(ctx, cudaGetLastError());
 	return true;

@@ -103,6 +103,10 @@ int b200_etc1s_determine_selectors(b200_context* ctx, const void* pInput_etc_col
 float b200_last_kernel_ms(const b200_context* ctx);
 uint32_t b200_last_launch_count(const b200_context* ctx);
 
+/* Kernel launches issued by this process through any context since load (lets a host that only sees the reference's API,
+ * e.g. the drop-in build of INTEGRATION.md section 1, confirm that the GPU path really ran). */
+uint64_t b200_global_launch_count(void);
+
 /* Per-stage device time of the last UASTC encode call, summed over its chunks (CUDA events around each kernel on the
  * context's stream): stage 0 = classify/rank, 1 = candidate generation + scoring, 2 = select/hints/pack. */
 float b200_last_stage_ms(const b200_context* ctx, uint32_t stage);

@@ -18,6 +18,7 @@
 #include "encoder/basisu_etc.h"
 #include "encoder/basisu_frontend.h"
 #include "encoder/basisu_gpu_texture.h"
+#include "encoder/basisu_opencl.h"
 #include "transcoder/basisu_transcoder.h"
 
 #include <atomic>
@@ -236,5 +237,31 @@ REF_API int ref_uastc_fields(const uint8_t* pBlock, uint8_t* out)
 		memcpy(out + 29, u.m_astc.m_weights, 32);
 	}
 	else { out[11] = u.m_solid_color.r; out[12] = u.m_solid_color.g; out[13] = u.m_solid_color.b; out[14] = u.m_solid_color.a; out[15]=(uint8_t)u.m_etc1_r; out[16]=(uint8_t)u.m_etc1_g; out[17]=(uint8_t)u.m_etc1_b; out[18]=(uint8_t)u.m_etc1_selector; }
+	return 1;
+}
+
+// ---- whole-file helpers for the end-to-end (drop-in) checks -----------------------------------------------------------------
+
+// Initialises the encoder with its GPU seam enabled (basisu_encoder_init(use_opencl=true), enc.cpp:194-211). Returns
+// opencl_is_available(): always 0 in the stock build (OpenCL compiled out), 1 in the drop-in build when a B200 is present.
+REF_API int ref_init_gpu_seam()
+{
+	if (!g_inited.exchange(true))
+		basisu_encoder_init(true, false);
+	return opencl_is_available() ? 1 : 0;
+}
+
+// Transcodes image 0 / level 0 of a .basis file to RGBA32 with the reference transcoder (transcoder/basisu_transcoder.h).
+REF_API int ref_transcode_basis_to_rgba(const void* pData, uint32_t size, uint8_t* pOut, uint32_t out_pixels)
+{
+	ref_init();
+	basist::basisu_transcoder dec;
+	if (!dec.validate_header(pData, size)) return 0;
+	if (!dec.start_transcoding(pData, size)) return 0;
+	basist::basisu_image_level_info li;
+	if (!dec.get_image_level_info(pData, size, li, 0, 0)) return 0;
+	if ((uint64_t)li.m_orig_width * li.m_orig_height > out_pixels) return 0;
+	if (!dec.transcode_image_level(pData, size, 0, 0, pOut, li.m_orig_width * li.m_orig_height, basist::transcoder_texture_format::cTFRGBA32, 0, li.m_orig_width, nullptr, li.m_orig_height))
+		return 0;
 	return 1;
 }

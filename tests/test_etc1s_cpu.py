@@ -58,3 +58,29 @@ def test_ocl_kernel_blocks_decode_like_reference_cpu(ocl, ref, blocks):
     cpu = np.zeros((blocks.shape[0], 8), np.uint8)
     ref.lib.ref_etc1s_encode_blocks(_ptr(blocks), ctypes.c_uint32(blocks.shape[0]), _ptr(cpu), 1, 1)
     assert abs(psnr(ocl.encode_etc1s_blocks(blocks, 1, 16)) - psnr(cpu)) < 0.2
+
+
+def test_plain_c_port_is_pinned_to_both_reference_builds(ocl, ref, blocks):
+    """oracle/etc1s_port.c (kind "port") agrees with the compiled reference CPU code and with the reference's OpenCL kernels."""
+    port_so = os.path.join(util.ROOT, "oracle", "_ref", "liboracle_port.so")
+    if not os.path.exists(port_so):
+        import subprocess
+        subprocess.check_call(["make", "-C", os.path.join(util.ROOT, "oracle"), "port"], stdout=subprocess.DEVNULL)
+    port = ctypes.CDLL(port_so)
+    port.port_color_distance.restype = ctypes.c_uint32
+    rng = np.random.default_rng(1)
+    for _ in range(2000):
+        a = rng.integers(0, 256, 4, dtype=np.uint8); b = rng.integers(0, 256, 4, dtype=np.uint8)
+        for p in (0, 1):
+            assert port.port_color_distance(p, _ptr(a), _ptr(b)) == ref.lib.ref_color_distance(p, _ptr(a), _ptr(b), 0)
+    inp = util.etc1s_stage_inputs(blocks, 23)
+    n = 400
+    for p in (0, 1):
+        want_cl = ocl.determine_selectors(blocks, inp["color5_inten"], p)
+        want_cpu = np.zeros((blocks.shape[0], 8), np.uint8)
+        ref.lib.ref_etc1s_determine_selectors(_ptr(blocks), ctypes.c_uint32(blocks.shape[0]), _ptr(inp["color5_inten"]), _ptr(want_cpu), p)
+        assert np.array_equal(want_cl, want_cpu)  # the reference's two implementations agree with each other
+        for i in range(n):
+            out = np.zeros(8, np.uint8)
+            port.port_determine_selectors(_ptr(blocks[i]), _ptr(inp["color5_inten"][i]), p, _ptr(out))
+            assert np.array_equal(out, want_cpu[i])
