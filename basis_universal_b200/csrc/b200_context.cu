@@ -22,6 +22,7 @@ extern "C" b200_context* b200_create_context(int device_index)
 	b200_context* ctx = new b200_context();
 	memset(ctx, 0, sizeof(*ctx));
 	ctx->device = device_index;
+	ctx->etc_flavour = B200_ETC1S_FLAVOUR_CPU_OPTIMIZER;
 	if ((e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking)) != cudaSuccess ||
 		(e = cudaEventCreate(&ctx->ev0)) != cudaSuccess || (e = cudaEventCreate(&ctx->ev1)) != cudaSuccess ||
 		(e = cudaEventCreate(&ctx->ev_t0)) != cudaSuccess || (e = cudaEventCreate(&ctx->ev_t1)) != cudaSuccess)

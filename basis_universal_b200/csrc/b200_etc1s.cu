@@ -28,13 +28,13 @@ __device__ __forceinline__ void load_block16(const uint4* __restrict__ blocks, u
 	}
 }
 
-__global__ void __launch_bounds__(128) k_etc1s_encode_blocks(const uint4* __restrict__ blocks, uint32_t n, uint64_t* __restrict__ out, int perceptual, uint32_t total_perms)
+__global__ void __launch_bounds__(128) k_etc1s_encode_blocks(const uint4* __restrict__ blocks, uint32_t n, uint64_t* __restrict__ out, int perceptual, uint32_t total_perms, int flavour)
 {
 	const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
 	if (i >= n) return;
 	uint32_t px[16];
 	load_block16(blocks, i, px);
-	out[i] = etc1s_encode_block(&d_tables, perceptual != 0, total_perms, px);
+	out[i] = etc1s_encode_block(&d_tables, perceptual != 0, total_perms, px, flavour);
 }
 
 __global__ void __launch_bounds__(128) k_etc1s_determine_selectors(const uint4* __restrict__ blocks, uint32_t n, const uint32_t* __restrict__ color5_inten, uint64_t* __restrict__ out, int perceptual)
@@ -63,14 +63,14 @@ __device__ __forceinline__ uint64_t warp_sum_u64(uint64_t v)
 // Weighted error of base colour (r5,g5,b5) against the cluster's texels for every non-pruned intensity table; returns the
 // best (first strictly smaller) table and its error. Uniform across the warp.
 __device__ void cluster_evaluate(const bu_tables* T, bool perceptual, const uint32_t* __restrict__ px, const uint32_t* __restrict__ wts, uint64_t n,
-	uint32_t lane, uint32_t spread, uint32_t r5, uint32_t g5, uint32_t b5, etc1s_solution& best)
+	uint32_t lane, uint32_t spread, uint32_t r5, uint32_t g5, uint32_t b5, etc1s_solution& best, bool prune)
 {
 	uint64_t trial_err = (uint64_t)INT64_MAX;
 	uint32_t trial_inten = 0;
 	bool valid = false;
 	for (uint32_t inten = 0; inten < 8; inten++)
 	{
-		if (!T->eval_dist[inten * 256 + spread]) continue;
+		if (prune && !T->eval_dist[inten * 256 + spread]) continue;
 		uint32_t colors[4];
 		etc1s_block_colors(T, r5, g5, b5, inten, colors);
 		uint64_t total = 0;
@@ -89,8 +89,20 @@ __device__ void cluster_evaluate(const bu_tables* T, bool perceptual, const uint
 	if (trial_err < best.err) { best.err = trial_err; best.r5 = r5; best.g5 = g5; best.b5 = b5; best.inten = trial_inten; best.valid = valid ? 1u : 0u; }
 }
 
+// The CPU optimiser's 1024-bit Bloom filter of tried base colours (etc.cpp:1072), one 32-bit word per lane.
+__device__ __forceinline__ bool warp_bloom_test_and_set(uint32_t& my_word, uint32_t lane, uint32_t r5, uint32_t g5, uint32_t b5)
+{
+	const uint32_t kh = hash_hsieh3(r5, g5, b5);
+	const uint32_t h0 = kh & 1023, h1 = (kh >> 10) & 1023;
+	const uint32_t w0 = __shfl_sync(0xffffffffu, my_word, h0 >> 5), w1 = __shfl_sync(0xffffffffu, my_word, h1 >> 5);
+	if ((w0 >> (h0 & 31)) & (w1 >> (h1 & 31)) & 1) return false;
+	if (lane == (h0 >> 5)) my_word |= 1u << (h0 & 31);
+	if (lane == (h1 >> 5)) my_word |= 1u << (h1 & 31);
+	return true;
+}
+
 __global__ void __launch_bounds__(128) k_etc1s_pixel_clusters(const b200_pixel_cluster* __restrict__ clusters, uint32_t total_clusters,
-	const uint32_t* __restrict__ pixels, const uint32_t* __restrict__ weights, uint64_t* __restrict__ out, int perceptual_i, uint32_t total_perms)
+	const uint32_t* __restrict__ pixels, const uint32_t* __restrict__ weights, uint64_t* __restrict__ out, int perceptual_i, uint32_t total_perms, int flavour)
 {
 	const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
 	if (warp >= total_clusters) return;
@@ -128,18 +140,23 @@ __global__ void __launch_bounds__(128) k_etc1s_pixel_clusters(const b200_pixel_c
 	float avg[3];
 	for (int c = 0; c < 3; c++) avg[c] = (float)sum[c] / (float)tw;
 	const uint32_t spread = (uint32_t)max(max((int)mx[0] - (int)mn[0], (int)mx[1] - (int)mn[1]), (int)mx[2] - (int)mn[2]);
-	const float k = 31 / 255.0f;
-	const uint32_t r0 = (uint32_t)clampi((int)(avg[0] * k + .5f), 0, 31), g0 = (uint32_t)clampi((int)(avg[1] * k + .5f), 0, 31), b0 = (uint32_t)clampi((int)(avg[2] * k + .5f), 0, 31);
+	if (total_perms <= 4) flavour = ETC1S_FLAVOUR_OCL;
+	const bool cpu = flavour == ETC1S_FLAVOUR_CPU;
+	const bool prune = !cpu || total_perms <= 16;
+	const uint32_t r0 = etc1s_round5(avg[0], flavour), g0 = etc1s_round5(avg[1], flavour), b0 = etc1s_round5(avg[2], flavour);
 
+	uint32_t bloom_word = 0;
+	if (cpu) warp_bloom_test_and_set(bloom_word, lane, r0, g0, b0);
 	etc1s_solution best;
 	best.err = UINT64_MAX; best.r5 = best.g5 = best.b5 = best.inten = 0; best.lsb_plane = best.msb_plane = 0; best.valid = 0;
-	cluster_evaluate(T, perceptual, px, wts, n, lane, spread, r0, g0, b0, best);
+	cluster_evaluate(T, perceptual, px, wts, n, lane, spread, r0, g0, b0, best, prune);
 	if (best.err != 0)
 		for (uint32_t perm = 0; perm < total_perms; perm++)
 		{
 			uint32_t r1, g1, b1;
-			if (!etc1s_cluster_fit_step(T, best, avg, perm, r1, g1, b1)) continue;
-			cluster_evaluate(T, perceptual, px, wts, n, lane, spread, r1, g1, b1, best);
+			if (!etc1s_cluster_fit_step(T, best, avg, perm, r1, g1, b1, flavour)) continue;
+			if (cpu && !warp_bloom_test_and_set(bloom_word, lane, r1, g1, b1)) continue;
+			cluster_evaluate(T, perceptual, px, wts, n, lane, spread, r1, g1, b1, best, prune);
 			if (best.err == 0) break;
 		}
 	if (lane == 0) out[warp] = etc1s_pack(best.r5, best.g5, best.b5, best.inten, 0, 0); // the kernel defines no selectors for clusters
@@ -247,6 +264,14 @@ static int finish(b200_context* ctx, void* host_out, int slot, size_t bytes)
 	return 1;
 }
 
+extern "C" int b200_etc1s_set_flavour(b200_context* ctx, int flavour)
+{
+	if (!ctx) return 0;
+	if (flavour != B200_ETC1S_FLAVOUR_OPENCL_KERNELS && flavour != B200_ETC1S_FLAVOUR_CPU_OPTIMIZER) { ctx->fail("b200_etc1s_set_flavour: unknown flavour"); return 0; }
+	ctx->etc_flavour = flavour;
+	return 1;
+}
+
 extern "C" int b200_etc1s_set_pixel_blocks(b200_context* ctx, uint32_t total_blocks, const void* pPixel_blocks)
 {
 	if (!ctx) return 0;
@@ -267,7 +292,7 @@ extern "C" int b200_etc1s_encode_blocks(b200_context* ctx, void* pOutput_blocks,
 	if (!ctx->reserve(ctx->d_aux[0], ctx->aux_cap[0], (size_t)n * 8)) return 0;
 	ctx->launches = 1; __atomic_add_fetch(&g_b200_total_launches, 1, __ATOMIC_RELAXED);
 	B200_CUDA_OK(ctx, cudaEventRecord(ctx->ev0, ctx->stream));
-	k_etc1s_encode_blocks<<<(n + 127) / 128, 128, 0, ctx->stream>>>(static_cast<const uint4*>(ctx->d_etc_blocks), n, static_cast<uint64_t*>(ctx->d_aux[0]), perceptual, total_perms);
+	k_etc1s_encode_blocks<<<(n + 127) / 128, 128, 0, ctx->stream>>>(static_cast<const uint4*>(ctx->d_etc_blocks), n, static_cast<uint64_t*>(ctx->d_aux[0]), perceptual, total_perms, ctx->etc_flavour);
 	return finish(ctx, pOutput_blocks, 0, (size_t)n * 8);
 }
 
@@ -287,7 +312,7 @@ extern "C" int b200_etc1s_encode_pixel_clusters(b200_context* ctx, void* pOutput
 	const uint32_t warps_per_cta = 4;
 	k_etc1s_pixel_clusters<<<(total_clusters + warps_per_cta - 1) / warps_per_cta, warps_per_cta * 32, 0, ctx->stream>>>(
 		static_cast<const b200_pixel_cluster*>(ctx->d_aux[1]), total_clusters, static_cast<const uint32_t*>(ctx->d_aux[2]),
-		static_cast<const uint32_t*>(ctx->d_aux[3]), static_cast<uint64_t*>(ctx->d_aux[0]), perceptual, total_perms);
+		static_cast<const uint32_t*>(ctx->d_aux[3]), static_cast<uint64_t*>(ctx->d_aux[0]), perceptual, total_perms, ctx->etc_flavour);
 	return finish(ctx, pOutput_blocks, 0, (size_t)total_clusters * 8);
 }
 

@@ -36,7 +36,7 @@ struct cell_fit
 
 // ---- evaluate one endpoint pair (bc7enc.cpp:822) -------------------------------------------------------------------
 
-BU_NI inline void cell_evaluate(const bu_tables* T, const cell_cfg& cfg, const uint32_t* px, uint32_t n, const uint8_t* lo, const uint8_t* hi, cell_fit& fit)
+BU_NI inline void cell_evaluate(const bu_tables* T, const cell_cfg& cfg, const uint32_t* px, uint32_t n, const uint8_t* lo, const uint8_t* hi, cell_fit& fit, const uint8_t* force_sel = nullptr)
 {
 	const uint8_t* su = T->sorted_unq + cfg.slot * 256;
 	const uint32_t N = 1u << cfg.wbits;
@@ -62,7 +62,17 @@ BU_NI inline void cell_evaluate(const bu_tables* T, const cell_cfg& cfg, const u
 
 	uint8_t st[16];
 	uint64_t total = 0;
-	if (cfg.has_alpha)
+	if (force_sel)
+	{
+		// caller-imposed selectors (bc7enc.cpp:885-898): only the error is computed
+		for (uint32_t i = 0; i < n; i++)
+		{
+			const uint32_t s = force_sel[i];
+			total += cfg.has_alpha ? dist_rgba(wc[s], px[i]) : dist_rgb(wc[s], px[i]);
+			st[i] = (uint8_t)s;
+		}
+	}
+	else if (cfg.has_alpha)
 	{
 		const float f = (float)N / ((float)(dc[0] * dc[0] + dc[1] * dc[1] + dc[2] * dc[2] + dc[3] * dc[3]) + .00000125f);
 		for (uint32_t i = 0; i < n; i++)
@@ -114,7 +124,7 @@ BU_FI bool cell_same_endpoints(const cell_fit& fit, const uint8_t* lo, const uin
 	return true;
 }
 
-BU_NI inline uint64_t cell_try_endpoints(const bu_tables* T, const cell_cfg& cfg, const uint32_t* px, uint32_t n, const float* xl_in, const float* xh_in, cell_fit& fit)
+BU_NI inline uint64_t cell_try_endpoints(const bu_tables* T, const cell_cfg& cfg, const uint32_t* px, uint32_t n, const float* xl_in, const float* xh_in, cell_fit& fit, const uint8_t* force_sel = nullptr)
 {
 	float xl[4], xh[4];
 	uint8_t lo0[4], hi0[4];
@@ -147,11 +157,11 @@ BU_NI inline uint64_t cell_try_endpoints(const bu_tables* T, const cell_cfg& cfg
 					if ((flags & 2) && (int)hi[c] < top) hi[c]++;
 				}
 			if (fit.err == UINT64_MAX || !cell_same_endpoints(fit, lo, hi))
-				cell_evaluate(T, cfg, px, n, lo, hi, fit);
+				cell_evaluate(T, cfg, px, n, lo, hi, fit, force_sel);
 		}
 	}
 	else if (fit.err == UINT64_MAX || !cell_same_endpoints(fit, lo0, hi0))
-		cell_evaluate(T, cfg, px, n, lo0, hi0, fit);
+		cell_evaluate(T, cfg, px, n, lo0, hi0, fit, force_sel);
 
 	return fit.err;
 }
@@ -204,12 +214,12 @@ BU_NI inline void cell_least_squares(const bu_tables* T, const cell_cfg& cfg, co
 }
 
 // LS refit + quantise + evaluate; returns false if a zero-error solution was reached (reference returns early then).
-BU_HD inline bool cell_refit(const bu_tables* T, const cell_cfg& cfg, const uint32_t* px, uint32_t n, const uint8_t* sel, cell_fit& fit)
+BU_HD inline bool cell_refit(const bu_tables* T, const cell_cfg& cfg, const uint32_t* px, uint32_t n, const uint8_t* sel, cell_fit& fit, const uint8_t* force_sel = nullptr)
 {
 	float xl[4], xh[4];
 	cell_least_squares(T, cfg, px, n, sel, xl, xh);
 	for (int c = 0; c < 4; c++) { xl[c] = xl[c] * (1.0f / 255.0f); xh[c] = xh[c] * (1.0f / 255.0f); }
-	return cell_try_endpoints(T, cfg, px, n, xl, xh, fit) != 0;
+	return cell_try_endpoints(T, cfg, px, n, xl, xh, fit, force_sel) != 0;
 }
 
 // ---- single-colour tables (bc7enc.cpp:628-820) ----------------------------------------------------------------------
@@ -264,7 +274,8 @@ BU_HD inline void cell_finish(const bu_tables* T, const cell_cfg& cfg, const cel
 	for (uint32_t i = 0; i < n; i++) out.sel[i] = fit.sel[i];
 }
 
-BU_NI inline void cell_compress(const bu_tables* T, const cell_cfg& cfg, const uint32_t* px, uint32_t n, cell_result& out)
+// force_sel != nullptr: the selectors are imposed (uastc_rdo endpoint refinement): no single-colour shortcuts, no selector perturbation.
+BU_NI inline void cell_compress(const bu_tables* T, const cell_cfg& cfg, const uint32_t* px, uint32_t n, cell_result& out, const uint8_t* force_sel = nullptr)
 {
 	cell_fit fit;
 	fit.err = UINT64_MAX;
@@ -272,7 +283,7 @@ BU_NI inline void cell_compress(const bu_tables* T, const cell_cfg& cfg, const u
 	for (int i = 0; i < 16; i++) fit.sel[i] = 0;
 
 	uint32_t one_sel = 0, one_alpha = 0;
-	const uint8_t* one_tab = cell_one_colour_table(T, cfg, one_sel, one_alpha);
+	const uint8_t* one_tab = force_sel ? nullptr : cell_one_colour_table(T, cfg, one_sel, one_alpha);
 
 	// All texels equal and a single-colour table exists for this configuration: done (bc7enc.cpp:1379-1411).
 	if (one_tab)
@@ -382,12 +393,12 @@ BU_NI inline void cell_compress(const bu_tables* T, const cell_cfg& cfg, const u
 		for (int c = 0; c < 4; c++) { const float tmp = minc[c]; minc[c] = maxc[c]; maxc[c] = tmp; }
 
 	// PCA solution, then least-squares passes (bc7enc.cpp:1546-1565). A zero-error solution ends the search.
-	bool go = cell_try_endpoints(T, cfg, px, n, minc, maxc, fit) != 0;
+	bool go = cell_try_endpoints(T, cfg, px, n, minc, maxc, fit, force_sel) != 0;
 
 	for (uint32_t pass = 0; go && pass < cfg.ls_passes; pass++)
-		go = cell_refit(T, cfg, px, n, fit.sel, fit);
+		go = cell_refit(T, cfg, px, n, fit.sel, fit, force_sel);
 
-	if (go && cfg.uber > 0)
+	if (go && cfg.uber > 0 && !force_sel)
 	{
 		// Selector perturbation (bc7enc.cpp:1567-1677): bump the extreme selectors inward, refit.
 		uint8_t base[16] = { 0 }, trial[16] = { 0 };

@@ -47,6 +47,49 @@ BU_FI uint64_t etc1s_pack(uint32_t r5, uint32_t g5, uint32_t b5, uint32_t inten,
 	return b0 | (b1 << 8) | (b2 << 16) | (b3 << 24) | (b4 << 32) | (b5_ << 40) | (b6 << 48) | (b7 << 56);
 }
 
+// Two arithmetic "flavours" of the block/cluster optimiser exist in the reference and the seam must be able to stand in for
+// either:
+//   ETC1S_FLAVOUR_OCL  what the OpenCL kernels compute (cl:772-982): intensity tables always pruned by g_eval_dist_tables,
+//                      base colours rounded with x * (31/255.0f).
+//   ETC1S_FLAVOUR_CPU  what the CPU etc1_optimizer computes for the same stage (etc.cpp:948-995, 1104-1278) at quality
+//                      Medium/Slow/Uber: pruning only at Medium (total_perms <= 16), rounding x * 31 / 255.0f, and the
+//                      2-probe Bloom filter over tried base colours (etc.cpp:1072-1089, hash_hsieh of the 3 colour bytes)
+//                      whose false positives skip evaluations. Bit-exact with the CPU frontend => ETC1S output (and PSNR)
+//                      identical to the reference CPU encoder's for these stages. Quality Fast (total_perms == 4) uses a
+//                      different sorted-luma evaluator on the CPU; it keeps the OCL flavour.
+enum { ETC1S_FLAVOUR_OCL = 0, ETC1S_FLAVOUR_CPU = 1 };
+
+// basist::hash_hsieh (transcoder/basisu_transcoder.cpp:355) specialised to the 3-byte key (r5, g5, b5).
+BU_FI uint32_t hash_hsieh3(uint32_t r5, uint32_t g5, uint32_t b5)
+{
+	uint32_t h = 3;
+	h += r5 | (g5 << 8);
+	h ^= h << 16;
+	h ^= b5 << 18;
+	h += h >> 11;
+	h ^= h << 3; h += h >> 5; h ^= h << 4; h += h >> 17; h ^= h << 25; h += h >> 6;
+	return h;
+}
+
+struct etc1s_bloom { uint32_t bits[32]; };
+BU_FI void bloom_clear(etc1s_bloom& b) { for (int i = 0; i < 32; i++) b.bits[i] = 0; }
+// false if (r5,g5,b5) was probably tried already (etc.cpp:1072 check_for_redundant_solution)
+BU_FI bool bloom_test_and_set(etc1s_bloom& b, uint32_t r5, uint32_t g5, uint32_t b5)
+{
+	const uint32_t kh = hash_hsieh3(r5, g5, b5);
+	const uint32_t h0 = kh & 1023, h1 = (kh >> 10) & 1023;
+	if ((b.bits[h0 >> 5] >> (h0 & 31)) & (b.bits[h1 >> 5] >> (h1 & 31)) & 1) return false;
+	b.bits[h0 >> 5] |= 1u << (h0 & 31);
+	b.bits[h1 >> 5] |= 1u << (h1 & 31);
+	return true;
+}
+
+BU_FI uint32_t etc1s_round5(float v, int flavour)
+{
+	const int i = (flavour == ETC1S_FLAVOUR_CPU) ? (int)(v * 31.0f / 255.0f + .5f) : (int)(v * (31 / 255.0f) + .5f);
+	return (uint32_t)clampi(i, 0, 31);
+}
+
 struct etc1s_solution
 {
 	uint64_t err;
@@ -56,14 +99,14 @@ struct etc1s_solution
 };
 
 // One candidate base colour against all (non-pruned) intensity tables, 16-texel block (cl:772). Updates `best` if strictly better.
-BU_HD inline void etc1s_evaluate_block(const bu_tables* T, bool perceptual, const uint32_t* px, uint32_t spread, uint32_t r5, uint32_t g5, uint32_t b5, etc1s_solution& best)
+BU_HD inline void etc1s_evaluate_block(const bu_tables* T, bool perceptual, const uint32_t* px, uint32_t spread, uint32_t r5, uint32_t g5, uint32_t b5, etc1s_solution& best, bool prune = true)
 {
 	uint64_t trial_err = (uint64_t)INT64_MAX;
 	uint32_t trial_inten = 0, trial_lsb = 0, trial_msb = 0;
 	bool valid = false;
 	for (uint32_t inten = 0; inten < 8; inten++)
 	{
-		if (!T->eval_dist[inten * 256 + spread]) continue;
+		if (prune && !T->eval_dist[inten * 256 + spread]) continue;
 		uint32_t colors[4];
 		etc1s_block_colors(T, r5, g5, b5, inten, colors);
 		uint64_t total = 0;
@@ -90,7 +133,7 @@ BU_HD inline void etc1s_evaluate_block(const bu_tables* T, bool perceptual, cons
 
 // Next base colour proposed by the cluster fit for selector-count permutation `perm` (cl:944-973). Returns false if the
 // permutation leaves the colour unchanged (all clamped deltas zero).
-BU_FI bool etc1s_cluster_fit_step(const bu_tables* T, const etc1s_solution& best, const float* avg, uint32_t perm, uint32_t& r1, uint32_t& g1, uint32_t& b1)
+BU_FI bool etc1s_cluster_fit_step(const bu_tables* T, const etc1s_solution& best, const float* avg, uint32_t perm, uint32_t& r1, uint32_t& g1, uint32_t& b1, int flavour = ETC1S_FLAVOUR_OCL)
 {
 	const int br = (int)((best.r5 << 3) | (best.r5 >> 2)), bg = (int)((best.g5 << 3) | (best.g5 >> 2)), bb = (int)((best.b5 << 3) | (best.b5 >> 2));
 	int dr = 0, dg = 0, db = 0;
@@ -103,16 +146,16 @@ BU_FI bool etc1s_cluster_fit_step(const bu_tables* T, const etc1s_solution& best
 		db += cnt * (clampi(bb + yd, 0, 255) - bb);
 	}
 	if (!dr && !dg && !db) return false;
-	const float k = 31 / 255.0f;
-	r1 = (uint32_t)clampi((int)((avg[0] - (float)dr / 8) * k + .5f), 0, 31);
-	g1 = (uint32_t)clampi((int)((avg[1] - (float)dg / 8) * k + .5f), 0, 31);
-	b1 = (uint32_t)clampi((int)((avg[2] - (float)db / 8) * k + .5f), 0, 31);
+	r1 = etc1s_round5(avg[0] - (float)dr / 8, flavour);
+	g1 = etc1s_round5(avg[1] - (float)dg / 8, flavour);
+	b1 = etc1s_round5(avg[2] - (float)db / 8, flavour);
 	return true;
 }
 
-// encode_etc1s_blocks (cl:984): optimise one 4x4 block, return the 8 block bytes.
-BU_HD inline uint64_t etc1s_encode_block(const bu_tables* T, bool perceptual, uint32_t total_perms, const uint32_t* px)
+// encode_etc1s_blocks (cl:984) / init_etc1_images CPU path (frontend.cpp:775-815): optimise one 4x4 block, return the 8 block bytes.
+BU_HD inline uint64_t etc1s_encode_block(const bu_tables* T, bool perceptual, uint32_t total_perms, const uint32_t* px, int flavour = ETC1S_FLAVOUR_OCL)
 {
+	if (total_perms <= 4) flavour = ETC1S_FLAVOUR_OCL; // CPU quality Fast is a different evaluator (see the flavour note)
 	uint32_t mn[3] = { 255, 255, 255 }, mx[3] = { 0, 0, 0 };
 	uint64_t sum[3] = { 0, 0, 0 };
 	for (int i = 0; i < 16; i++)
@@ -122,20 +165,24 @@ BU_HD inline uint64_t etc1s_encode_block(const bu_tables* T, bool perceptual, ui
 			mn[c] = minu(mn[c], v); mx[c] = maxu(mx[c], v); sum[c] += v;
 		}
 	float avg[3];
-	for (int c = 0; c < 3; c++) avg[c] = (float)sum[c] / (float)(uint64_t)16;
+	for (int c = 0; c < 3; c++) avg[c] = (float)sum[c] / (float)(uint64_t)16; // 16-texel sums are exact in float either way
 	const uint32_t spread = (uint32_t)maxi(maxi((int)mx[0] - (int)mn[0], (int)mx[1] - (int)mn[1]), (int)mx[2] - (int)mn[2]);
-	const float k = 31 / 255.0f;
-	const uint32_t r0 = (uint32_t)clampi((int)(avg[0] * k + .5f), 0, 31), g0 = (uint32_t)clampi((int)(avg[1] * k + .5f), 0, 31), b0 = (uint32_t)clampi((int)(avg[2] * k + .5f), 0, 31);
+	const uint32_t r0 = etc1s_round5(avg[0], flavour), g0 = etc1s_round5(avg[1], flavour), b0 = etc1s_round5(avg[2], flavour);
+	const bool cpu = flavour == ETC1S_FLAVOUR_CPU;
+	const bool prune = !cpu || total_perms <= 16;
 
+	etc1s_bloom bloom;
+	if (cpu) { bloom_clear(bloom); bloom_test_and_set(bloom, r0, g0, b0); }
 	etc1s_solution best;
 	best.err = UINT64_MAX; best.r5 = best.g5 = best.b5 = best.inten = 0; best.lsb_plane = best.msb_plane = 0; best.valid = 0;
-	etc1s_evaluate_block(T, perceptual, px, spread, r0, g0, b0, best);
+	etc1s_evaluate_block(T, perceptual, px, spread, r0, g0, b0, best, prune);
 	if (best.err != 0)
 		for (uint32_t perm = 0; perm < total_perms; perm++)
 		{
 			uint32_t r1, g1, b1;
-			if (!etc1s_cluster_fit_step(T, best, avg, perm, r1, g1, b1)) continue;
-			etc1s_evaluate_block(T, perceptual, px, spread, r1, g1, b1, best);
+			if (!etc1s_cluster_fit_step(T, best, avg, perm, r1, g1, b1, flavour)) continue;
+			if (cpu && !bloom_test_and_set(bloom, r1, g1, b1)) continue;
+			etc1s_evaluate_block(T, perceptual, px, spread, r1, g1, b1, best, prune);
 			if (best.err == 0) break;
 		}
 	return etc1s_pack(best.r5, best.g5, best.b5, best.inten, best.lsb_plane, best.msb_plane);

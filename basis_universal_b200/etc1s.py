@@ -12,6 +12,7 @@ endpoint_cluster_dtype = np.dtype([("r", "u1"), ("g", "u1"), ("b", "u1"), ("a", 
 fosc_block_dtype = np.dtype([("r", "u1"), ("g", "u1"), ("b", "u1"), ("inten", "u1"), ("first_selector", "<u4"), ("num_selectors", "<u4")])          # fosc_block_struct
 
 OPENCL_ENCODE_ETC1S_MAX_PERMS = 165  # opencl.h:44
+FLAVOUR_OPENCL_KERNELS, FLAVOUR_CPU_OPTIMIZER = 0, 1
 
 
 def _p(a):
@@ -46,6 +47,10 @@ class Etc1sContext:
     @property
     def last_kernel_ms(self):
         return float(self._lib.b200_last_kernel_ms(self._ctx))
+
+    def set_flavour(self, flavour):
+        """FLAVOUR_CPU_OPTIMIZER (default) or FLAVOUR_OPENCL_KERNELS: which of the reference's two optimiser implementations to reproduce."""
+        self._check(self._lib.b200_etc1s_set_flavour(self._ctx, int(flavour)), "b200_etc1s_set_flavour")
 
     def set_pixel_blocks(self, blocks):
         """opencl_set_pixel_blocks(ctx, total_blocks, pPixel_blocks)"""

@@ -21,6 +21,18 @@ cPackUASTCETC1DisableFlipAndIndividual = 256
 cPackUASTCFavorSimplerModes = 512
 
 
+class uastc_rdo_params(ctypes.Structure):
+    """basisu::uastc_rdo_params (encoder/basisu_uastc_enc.h:82-128) with the reference's defaults (clear(), :89-100)."""
+    _fields_ = [("lz_dict_size", ctypes.c_uint32), ("lambda_", ctypes.c_float), ("max_allowed_rms_increase_ratio", ctypes.c_float),
+                ("skip_block_rms_thresh", ctypes.c_float), ("endpoint_refinement", ctypes.c_uint32), ("max_smooth_block_std_dev", ctypes.c_float),
+                ("smooth_block_max_error_scale", ctypes.c_float), ("lz_literal_cost", ctypes.c_uint32)]
+
+    def __init__(self, lambda_=0.5, lz_dict_size=4096, max_allowed_rms_increase_ratio=10.0, skip_block_rms_thresh=8.0, endpoint_refinement=True,
+                 max_smooth_block_std_dev=18.0, smooth_block_max_error_scale=10.0, lz_literal_cost=100):
+        super().__init__(lz_dict_size, lambda_, max_allowed_rms_increase_ratio, skip_block_rms_thresh, int(bool(endpoint_refinement)),
+                         max_smooth_block_std_dev, smooth_block_max_error_scale, lz_literal_cost)
+
+
 def extract_blocks(image):
     """(H, W, 4) uint8 -> (num_blocks, 64) uint8 in raster block order; edge texels are clamped like
     image::extract_block_clamped (encoder/basisu_enc.h:3168)."""
@@ -94,6 +106,18 @@ class Encoder:
         ok = self._lib.b200_uastc_encode_blocks(self._ctx, blocks.ctypes.data, n, out.ctypes.data, int(flags))
         self._check(ok, "b200_uastc_encode_blocks")
         return out
+
+    def uastc_rdo(self, uastc_blocks, source_blocks, params=None, flags=cPackUASTCLevelDefault, total_jobs=4):
+        """basisu::uastc_rdo (uastc_enc.h:139): in-place RDO post-pass. `total_jobs` is the reference's chain split
+        (comp.cpp:2078 passes min(4, pool threads)); the output depends on it. Returns the modified (N, 16) array."""
+        blocks = np.ascontiguousarray(uastc_blocks, np.uint8).copy()
+        src = np.ascontiguousarray(source_blocks, np.uint8)
+        if blocks.shape[0] != src.shape[0] or blocks.shape[1] != 16 or src.shape[1] != 64:
+            raise ValueError("uastc_blocks must be (N,16) and source_blocks (N,64)")
+        p = params if params is not None else uastc_rdo_params()
+        ok = self._lib.b200_uastc_rdo(self._ctx, blocks.shape[0], blocks.ctypes.data, src.ctypes.data, ctypes.byref(p), int(flags), int(total_jobs))
+        self._check(ok, "b200_uastc_rdo")
+        return blocks
 
     def encode_uastc_device(self, d_blocks_ptr, num_blocks, d_out_ptr, flags=cPackUASTCLevelDefault):
         """Device-resident form: raw device pointers (e.g. torch tensor .data_ptr()) to (N,64) and (N,16) uint8 buffers."""

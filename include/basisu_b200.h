@@ -80,6 +80,16 @@ typedef struct b200_fosc_block { uint8_t etc_r, etc_g, etc_b, etc_a; uint32_t fi
 typedef struct b200_fosc_selector { uint32_t packed_selectors; } b200_fosc_selector; /* fosc_selector_struct, opencl.h:98 */
 #pragma pack(pop)
 
+/* The reference has two implementations of the block/cluster optimiser behind this seam: its OpenCL kernels
+ * (bin/ocl_kernels.cl:772-982, always prune intensity tables) and the CPU etc1_optimizer the frontend falls back to
+ * (encoder/basisu_etc.cpp:948-995, 1104-1278). b200_etc1s_encode_blocks / _pixel_clusters can reproduce either, bit for bit:
+ *   CPU_OPTIMIZER (default): output identical to the reference CPU encoder for these stages (total_perms 16/64/165), hence
+ *                            identical ETC1S PSNR at the same -q; total_perms 4 (CPU quality "Fast") uses the kernel flavour.
+ *   OPENCL_KERNELS:          output identical to the reference's OpenCL path.
+ * The three integer stages (refine, selector search, determine_selectors) are the same in both. */
+enum { B200_ETC1S_FLAVOUR_OPENCL_KERNELS = 0, B200_ETC1S_FLAVOUR_CPU_OPTIMIZER = 1 };
+int b200_etc1s_set_flavour(b200_context* ctx, int flavour);
+
 /* opencl_set_pixel_blocks (opencl.h:46): uploads the slice's source blocks once; later calls read them from HBM. */
 int b200_etc1s_set_pixel_blocks(b200_context* ctx, uint32_t total_blocks, const void* pPixel_blocks);
 /* opencl_encode_etc1s_blocks (opencl.h:47): per-block ETC1S optimisation, total_perms in {4,16,64,165}. */

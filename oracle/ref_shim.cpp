@@ -265,3 +265,26 @@ REF_API int ref_transcode_basis_to_rgba(const void* pData, uint32_t size, uint8_
 		return 0;
 	return 1;
 }
+
+// The CPU path of basisu_frontend::generate_endpoint_codebook for one endpoint cluster (frontend.cpp:1523-1549):
+// etc1_optimizer over `n` texels with the quality the comp_level maps to. out4 = {r5, g5, b5, inten}.
+REF_API uint64_t ref_etc1s_encode_cluster(const uint8_t* pPixels, uint32_t n, uint32_t perceptual, uint32_t comp_level, uint8_t* out4)
+{
+	ref_init();
+	etc1_optimizer optimizer;
+	etc1_optimizer::params p;
+	p.m_num_src_pixels = n;
+	p.m_pSrc_pixels = reinterpret_cast<const color_rgba*>(pPixels);
+	p.m_use_color4 = false;
+	p.m_perceptual = perceptual != 0;
+	if (comp_level <= 1) p.m_quality = cETCQualityMedium;
+	else if (comp_level == BASISU_MAX_ETC1S_COMPRESSION_LEVEL) p.m_quality = cETCQualityUber;
+	etc1_optimizer::results r;
+	std::vector<uint8_t> sel(n);
+	r.m_n = n;
+	r.m_pSelectors = sel.data();
+	optimizer.init(p, r);
+	optimizer.compute();
+	out4[0] = r.m_block_color_unscaled.r; out4[1] = r.m_block_color_unscaled.g; out4[2] = r.m_block_color_unscaled.b; out4[3] = (uint8_t)r.m_block_inten_table;
+	return r.m_error;
+}

@@ -91,6 +91,17 @@ EMU_API uint32_t emu_sizeof_tables() { return (uint32_t)sizeof(bu_tables); }
 #include "../../basis_universal_b200/csrc/bu_etc1s.h"
 #include "../../include/basisu_b200.h"
 
+EMU_API void emu_etc1s_encode_blocks_flavour(const uint8_t* pBlocks, uint32_t n, uint8_t* pOut, int perceptual, uint32_t total_perms, int flavour)
+{
+	for (uint32_t i = 0; i < n; i++)
+	{
+		uint32_t px[16];
+		memcpy(px, pBlocks + (size_t)i * 64, 64);
+		const uint64_t v = etc1s_encode_block(&g_tables, perceptual != 0, total_perms, px, flavour);
+		memcpy(pOut + (size_t)i * 8, &v, 8);
+	}
+}
+
 EMU_API void emu_etc1s_encode_blocks(const uint8_t* pBlocks, uint32_t n, uint8_t* pOut, int perceptual, uint32_t total_perms)
 {
 	for (uint32_t i = 0; i < n; i++)
@@ -135,4 +146,95 @@ EMU_API void emu_etc1s_refine(const uint8_t* pBlocks, uint32_t n, const b200_blo
 		}
 		out[bi] = best_index;
 	}
+}
+
+// ---- UASTC RDO (bu_rdo.h): sequential host rendition of the chain the CUDA kernel runs cooperatively -------------------------
+#include "../../basis_universal_b200/csrc/bu_rdo.h"
+#include <map>
+
+static block_bits load_bits(const uint8_t* p) { block_bits b; memcpy(&b.lo, p, 8); memcpy(&b.hi, p + 8, 8); return b; }
+static void store_bits(uint8_t* p, const block_bits& b) { memcpy(p, &b.lo, 8); memcpy(p + 8, &b.hi, 8); }
+
+static bool rdo_chain(uint32_t first, uint32_t last, uint8_t* blocks, const uint8_t* pixels, const rdo_params& p, std::vector<uint8_t>& modified)
+{
+	const bu_tables* T = &g_tables;
+	const int window = (int)std::max<uint32_t>(1u, p.lz_dict_size / 16);
+	std::map<std::pair<uint32_t, uint64_t>, uint32_t> history;
+	for (uint32_t bi = first; bi < last; bi++)
+	{
+		rdo_step st;
+		st.bits = load_bits(blocks + (size_t)bi * 16);
+		if (!unpack_block_bits(T, st.bits, st.cur)) return false;
+		if (st.cur.mode == 8) continue;
+		uint32_t px[16];
+		memcpy(px, pixels + (size_t)bi * 64, 64);
+		st.smooth_scale = rdo_smooth_scale(p, px);
+		const uint64_t cur_err = rdo_block_error(T, st.cur, px);
+		st.cur_ms_err = (float)cur_err * (1.0f / 64.0f);
+		st.cur_rms_err = sqrtf(st.cur_ms_err);
+		mode_selector_field(st.cur.mode, st.first_sel_bit, st.total_sel_bits);
+		const uint32_t n0 = std::min(64u, st.total_sel_bits);
+		st.cur_sel_bits = bits_read(st.bits, st.first_sel_bit, n0);
+		const auto cur_key = std::make_pair(st.first_sel_bit, st.cur_sel_bits);
+		if (st.cur_rms_err >= p.skip_block_rms_thresh) { history[cur_key] = bi; continue; }
+
+		int cur_bits;
+		auto it = history.find(cur_key);
+		if (it == history.end()) cur_bits = (int)((st.total_sel_bits * p.lz_literal_cost) / 100);
+		else cur_bits = (int)match_cost_estimate((bi - it->second) * 16);
+
+		float best_t = st.cur_ms_err * st.smooth_scale + (float)cur_bits * p.lambda;
+		block_bits best_bits = st.bits;
+		int best_index = (int)bi;
+		const int first_check = std::max<int>((int)first, (int)bi - window);
+		for (int pi = (int)bi - 1; pi >= first_check; --pi)
+		{
+			const block_bits prev = load_bits(blocks + (size_t)pi * 16);
+			int match = pi;
+			auto r = history.find(std::make_pair(st.first_sel_bit, bits_read(prev, st.first_sel_bit, n0)));
+			if (r != history.end()) match = (int)r->second;
+			float t; block_bits tb;
+			if (!rdo_trial(T, p, st, px, prev, pi, match, (int)bi, t, tb)) continue;
+			if (t < best_t) { best_t = t; best_index = pi; best_bits = tb; }
+		}
+
+		if (best_index != (int)bi)
+		{
+			candidate bc;
+			if (!unpack_block_bits(T, best_bits, bc)) return false;
+			if (p.endpoint_refinement && st.cur.mode == 0) rdo_refine_mode0(T, bc, px);
+			best_bits = pack_without_hints(T, bc);
+			store_bits(blocks + (size_t)bi * 16, best_bits);
+			modified[bi] = 1;
+		}
+		history[std::make_pair(st.first_sel_bit, bits_read(best_bits, st.first_sel_bit, n0))] = bi;
+	}
+	return true;
+}
+
+EMU_API int emu_uastc_rdo(uint32_t n, uint8_t* blocks, const uint8_t* pixels, const b200_uastc_rdo_params* bp, uint32_t flags, uint32_t total_jobs)
+{
+	rdo_params p;
+	p.lz_dict_size = bp->lz_dict_size; p.lambda = bp->lambda; p.max_allowed_rms_increase_ratio = bp->max_allowed_rms_increase_ratio;
+	p.skip_block_rms_thresh = bp->skip_block_rms_thresh; p.endpoint_refinement = bp->endpoint_refinement;
+	p.max_smooth_block_std_dev = bp->max_smooth_block_std_dev; p.smooth_block_max_error_scale = bp->smooth_block_max_error_scale; p.lz_literal_cost = bp->lz_literal_cost;
+	std::vector<uint8_t> modified(n, 0);
+	const uint32_t per_job = total_jobs ? n / total_jobs : 0;
+	bool ok = true;
+	if (total_jobs <= 1 || per_job <= 8) ok = rdo_chain(0, n, blocks, pixels, p, modified);
+	else for (uint32_t f = 0; f < n && ok; f += per_job) ok = rdo_chain(f, std::min(n, f + per_job), blocks, pixels, p, modified);
+	if (!ok) return 0;
+	// deferred hint pass (uastc_recompute_hints, uastc_enc.cpp:3647)
+	const int lvl = (int)(flags & 0xF);
+	const level_opts o = make_level_opts(lvl);
+	for (uint32_t i = 0; i < n; i++)
+	{
+		if (!modified[i]) continue;
+		candidate c;
+		if (!unpack_block_bits(&g_tables, load_bits(blocks + (size_t)i * 16), c)) return 0;
+		uint32_t px[16];
+		memcpy(px, pixels + (size_t)i * 64, 64);
+		finish_block(&g_tables, o, lvl, flags, px, c, blocks + (size_t)i * 16);
+	}
+	return 1;
 }

@@ -84,3 +84,14 @@ def test_plain_c_port_is_pinned_to_both_reference_builds(ocl, ref, blocks):
             out = np.zeros(8, np.uint8)
             port.port_determine_selectors(_ptr(blocks[i]), _ptr(inp["color5_inten"][i]), p, _ptr(out))
             assert np.array_equal(out, want_cpu[i])
+
+
+@pytest.mark.parametrize("perceptual", [0, 1])
+@pytest.mark.parametrize("comp_level,perms", [(1, 16), (2, 64), (6, 165)])
+def test_cpu_flavour_matches_reference_cpu_optimizer(ref, emu, blocks, perceptual, comp_level, perms):
+    """ETC1S_FLAVOUR_CPU (the library default) is bit-exact with the reference CPU etc1_optimizer (incl. its Bloom filter)."""
+    want = np.zeros((blocks.shape[0], 8), np.uint8)
+    ref.lib.ref_etc1s_encode_blocks(_ptr(blocks), ctypes.c_uint32(blocks.shape[0]), _ptr(want), perceptual, comp_level)
+    got = np.zeros_like(want)
+    emu.lib.emu_etc1s_encode_blocks_flavour(_ptr(blocks), blocks.shape[0], _ptr(got), perceptual, perms, 1)
+    assert np.array_equal(got, want)

@@ -26,9 +26,46 @@ def blocks():
 @pytest.fixture(scope="module")
 def ctx(blocks):
     c = etc1s.Etc1sContext(0)
+    c.set_flavour(etc1s.FLAVOUR_OPENCL_KERNELS)  # the oracle in this module is the reference's OpenCL kernel source
     c.set_pixel_blocks(blocks)
     yield c
     c.close()
+
+
+@pytest.fixture(scope="module")
+def ctx_cpu(blocks):
+    c = etc1s.Etc1sContext(0)                    # default flavour: the reference's CPU etc1_optimizer
+    c.set_pixel_blocks(blocks)
+    yield c
+    c.close()
+
+
+@pytest.mark.parametrize("perceptual", [0, 1])
+@pytest.mark.parametrize("comp_level,perms", [(1, 16), (2, 64), (6, 165)])
+def test_encode_blocks_cpu_flavour_matches_reference_cpu_optimizer(ctx_cpu, ref, blocks, perceptual, comp_level, perms):
+    """Default flavour: bit-exact with basisu_frontend::init_etc1_images' CPU path (etc1_optimizer, frontend.cpp:775-815)."""
+    import ctypes
+    want = np.zeros((blocks.shape[0], 8), np.uint8)
+    ref.lib.ref_etc1s_encode_blocks(util._ptr(blocks), ctypes.c_uint32(blocks.shape[0]), util._ptr(want), perceptual, comp_level)
+    assert np.array_equal(ctx_cpu.encode_etc1s_blocks(perceptual, perms), want)
+
+
+@pytest.mark.parametrize("perceptual", [0, 1])
+@pytest.mark.parametrize("comp_level,perms", [(1, 16), (2, 64)])
+def test_pixel_clusters_cpu_flavour_matches_reference_cpu_optimizer(ctx_cpu, ref, perceptual, comp_level, perms):
+    """Weighted unique-colour clusters vs the CPU path of generate_endpoint_codebook (frontend.cpp:1523-1549) fed the same
+    texels with repetition (what the CPU path sees)."""
+    import ctypes
+    clusters, px, weights = util.pixel_cluster_inputs(13, 40)
+    weights = np.minimum(weights, 6).astype(np.uint32)
+    got = ctx_cpu.encode_etc1s_pixel_clusters(clusters, px, weights, perceptual, perms)
+    for k, (n, first) in enumerate(clusters):
+        n, first = int(n), int(first)
+        rep = np.ascontiguousarray(np.repeat(px[first:first + n], weights[first:first + n], axis=0))
+        out4 = np.zeros(4, np.uint8)
+        ref.lib.ref_etc1s_encode_cluster(util._ptr(rep), ctypes.c_uint32(rep.shape[0]), perceptual, comp_level, util._ptr(out4))
+        want = np.array([out4[0] << 3, out4[1] << 3, out4[2] << 3, (int(out4[3]) << 5) | (int(out4[3]) << 2) | 3], np.uint8)
+        assert np.array_equal(got[k, :4], want), k
 
 
 @pytest.mark.parametrize("perceptual", [0, 1])

@@ -263,3 +263,30 @@ def pixel_cluster_inputs(seed, n_clusters=40):
     weights = rng.integers(1, 50, total).astype(np.uint32)
     clusters = np.stack([sizes, first], -1).astype(np.uint64)
     return clusters, px, weights
+
+
+class RdoParams(ctypes.Structure):
+    """b200_uastc_rdo_params / basisu::uastc_rdo_params with the reference defaults."""
+    _fields_ = [("lz_dict_size", ctypes.c_uint32), ("lam", ctypes.c_float), ("ratio", ctypes.c_float), ("skip", ctypes.c_float), ("refine", ctypes.c_uint32),
+                ("sd", ctypes.c_float), ("scale", ctypes.c_float), ("lit", ctypes.c_uint32)]
+
+
+def ref_rdo(ref, uastc, src, lam, flags, jobs):
+    out = np.ascontiguousarray(uastc).copy()
+    ok = ref.lib.ref_uastc_rdo(len(out), _ptr(out), _ptr(np.ascontiguousarray(src)), lam, 4096, 10.0, 8.0, 18.0, 10.0, flags, jobs, max(jobs, 4))
+    assert ok
+    return out
+
+
+def emu_rdo(emu, uastc, src, lam, flags, jobs):
+    out = np.ascontiguousarray(uastc).copy()
+    p = RdoParams(4096, lam, 10.0, 8.0, 1, 18.0, 10.0, 100)
+    ok = emu.lib.emu_uastc_rdo(len(out), _ptr(out), _ptr(np.ascontiguousarray(src)), ctypes.byref(p), flags, jobs)
+    assert ok
+    return out
+
+
+def rdo_test_image():
+    """A crop of a natural image (RDO modifies ~half of its blocks) tiled with part of the synthetic image (alpha modes)."""
+    g = np.load(os.path.join(GOLDEN, "kodim03_uastc_l0.npz"))
+    return np.ascontiguousarray(np.concatenate([g["image"][:128, :256], synth(256, 77)[:64]], 0))
