@@ -61,7 +61,7 @@ BU_NI inline void cell_evaluate(const bu_tables* T, const cell_cfg& cfg, const u
 	}
 
 	uint8_t st[16];
-	uint64_t total = 0;
+	uint32_t total = 0; // <= 16 * 4 * 255^2, fits 32 bits
 	if (force_sel)
 	{
 		// caller-imposed selectors (bc7enc.cpp:885-898): only the error is computed
@@ -72,35 +72,26 @@ BU_NI inline void cell_evaluate(const bu_tables* T, const cell_cfg& cfg, const u
 			st[i] = (uint8_t)s;
 		}
 	}
-	else if (cfg.has_alpha)
-	{
-		const float f = (float)N / ((float)(dc[0] * dc[0] + dc[1] * dc[1] + dc[2] * dc[2] + dc[3] * dc[3]) + .00000125f);
-		for (uint32_t i = 0; i < n; i++)
-		{
-			const uint32_t p = px[i];
-			const int dot = ((int)px_c(p, 0) - lc[0]) * dc[0] + ((int)px_c(p, 1) - lc[1]) * dc[1] + ((int)px_c(p, 2) - lc[2]) * dc[2] + ((int)px_c(p, 3) - lc[3]) * dc[3];
-			int s = (int)((float)dot * f + .5f);
-			s = clampi(s, 1, (int)N - 1);
-			const uint32_t e0 = dist_rgba(wc[s - 1], p), e1 = dist_rgba(wc[s], p);
-			uint32_t e = e1;
-			if (e0 == e1) { if (s == 1) s = 0; }            // prefer the non-interpolated endpoint
-			else if (e1 > e0) { e = e0; --s; }
-			total += e;
-			st[i] = (uint8_t)s;
-		}
-	}
 	else
 	{
-		const float f = (float)N / ((float)(dc[0] * dc[0] + dc[1] * dc[1] + dc[2] * dc[2]) + .00000125f);
+		// Projection of each texel on the endpoint axis picks two neighbouring selectors to compare (bc7enc.cpp:906-972).
+		// dot = sum_c (p_c - l_c) d_c = sum_c p_c d_c - K, with K constant per endpoint pair: exact integer arithmetic either way.
+		const bool a4 = cfg.has_alpha != 0;
+		const int d3 = a4 ? dc[3] : 0;
+		const float f = a4 ? (float)N / ((float)(dc[0] * dc[0] + dc[1] * dc[1] + dc[2] * dc[2] + dc[3] * dc[3]) + .00000125f)
+		                   : (float)N / ((float)(dc[0] * dc[0] + dc[1] * dc[1] + dc[2] * dc[2]) + .00000125f);
+		const uint32_t dc01 = pack_s16x2(dc[0], dc[1]), dc23 = pack_s16x2(dc[2], d3);
+		const int K = lc[0] * dc[0] + lc[1] * dc[1] + lc[2] * dc[2] + (a4 ? lc[3] * dc[3] : 0);
 		for (uint32_t i = 0; i < n; i++)
 		{
 			const uint32_t p = px[i];
-			const int dot = ((int)px_c(p, 0) - lc[0]) * dc[0] + ((int)px_c(p, 1) - lc[1]) * dc[1] + ((int)px_c(p, 2) - lc[2]) * dc[2];
+			const int dot = dot_s16x4_u8x4(dc01, dc23, p) - K;
 			int s = (int)((float)dot * f + .5f);
 			s = clampi(s, 1, (int)N - 1);
-			const uint32_t e0 = dist_rgb(wc[s - 1], p), e1 = dist_rgb(wc[s], p);
+			const uint32_t e0 = a4 ? dist_rgba(wc[s - 1], p) : dist_rgb(wc[s - 1], p);
+			const uint32_t e1 = a4 ? dist_rgba(wc[s], p) : dist_rgb(wc[s], p);
 			uint32_t e = e1;
-			if (e0 == e1) { if (s == 1) s = 0; }
+			if (e0 == e1) { if (s == 1) s = 0; }   // prefer the non-interpolated endpoint
 			else if (e0 < e1) { e = e0; --s; }
 			total += e;
 			st[i] = (uint8_t)s;

@@ -61,11 +61,34 @@ BU_FI uint32_t astc_lerp(uint32_t l, uint32_t h, uint32_t w)
 }
 
 BU_FI uint32_t sq_diff(int a, int b) { int d = a - b; return (uint32_t)(d * d); }
+
+// Squared distances between packed RGBA8 texels. On the device these are two instructions: per-byte |a-b| (VABSDIFF4) and
+// a 4-way dot product of the differences with themselves (IDP4A); on the host the same integers are computed per channel.
+#if defined(__CUDA_ARCH__)
+BU_FI uint32_t dist_rgba(uint32_t p, uint32_t q) { const uint32_t d = __vabsdiffu4(p, q); return __dp4a(d, d, 0u); }
+BU_FI uint32_t dist_rgb(uint32_t p, uint32_t q) { const uint32_t d = __vabsdiffu4(p, q) & 0x00FFFFFFu; return __dp4a(d, d, 0u); }
+BU_FI uint32_t dist_la(uint32_t p, uint32_t q) { const uint32_t d = __vabsdiffu4(p, q) & 0xFF0000FFu; return __dp4a(d, d, 0u); }
+// sum_c s16(dc[c]) * u8(p[c]) with dc packed as two s16 pairs: one DP2A each for the low and high byte pairs of p.
+BU_FI int dot_s16x4_u8x4(uint32_t dc01, uint32_t dc23, uint32_t p)
+{
+	int r;
+	asm("dp2a.lo.s32.u32 %0, %1, %2, %3;" : "=r"(r) : "r"(dc01), "r"(p), "r"(0));
+	asm("dp2a.hi.s32.u32 %0, %1, %2, %3;" : "=r"(r) : "r"(dc23), "r"(p), "r"(r));
+	return r;
+}
+#else
 BU_FI uint32_t dist_rgb(uint32_t p, uint32_t q)
 {
 	return sq_diff((int)px_c(p, 0), (int)px_c(q, 0)) + sq_diff((int)px_c(p, 1), (int)px_c(q, 1)) + sq_diff((int)px_c(p, 2), (int)px_c(q, 2));
 }
 BU_FI uint32_t dist_rgba(uint32_t p, uint32_t q) { return dist_rgb(p, q) + sq_diff((int)px_c(p, 3), (int)px_c(q, 3)); }
 BU_FI uint32_t dist_la(uint32_t p, uint32_t q) { return sq_diff((int)px_c(p, 0), (int)px_c(q, 0)) + sq_diff((int)px_c(p, 3), (int)px_c(q, 3)); }
+BU_FI int dot_s16x4_u8x4(uint32_t dc01, uint32_t dc23, uint32_t p)
+{
+	return (int)(int16_t)(dc01 & 0xFFFF) * (int)px_c(p, 0) + (int)(int16_t)(dc01 >> 16) * (int)px_c(p, 1) +
+		(int)(int16_t)(dc23 & 0xFFFF) * (int)px_c(p, 2) + (int)(int16_t)(dc23 >> 16) * (int)px_c(p, 3);
+}
+#endif
+BU_FI uint32_t pack_s16x2(int a, int b) { return ((uint32_t)a & 0xFFFFu) | ((uint32_t)b << 16); }
 
 } // namespace bu

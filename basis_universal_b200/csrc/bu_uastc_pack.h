@@ -520,6 +520,102 @@ BU_HD inline etc1_search_opts etc1_search_setup(const bu_tables* T, uint32_t mod
 	return o;
 }
 
+// Intensity-table scan and error contribution of one subset for a given scaled base colour (uastc_enc.cpp:2859-2995).
+// An ETC1 table colour is base + m on every channel, so unless a channel clamps, its luma is y_base + 256 m and its chroma equals
+// the base's: the four candidates for a texel differ in the luma term only and
+//     color_diff = 4 (dy + 256 m)^2 + dcr^2 + dcb^2
+// is the same integer expression the reference evaluates, factored. A clamping table (base + m outside 0..255) takes the general form.
+BU_NI inline void etc1_subset_search(const bu_tables* T, const etc1_search_opts& o, uint32_t flip, uint32_t s, const int* base, const int* mn, const int* mx,
+	const ycc* src_y, const ycc* dec_y, uint32_t& inten_out, uint64_t& err_out)
+{
+	int range = 0, bmin = 255, bmax = 0;
+	for (int c = 0; c < 3; c++)
+	{
+		range = maxi(range, iabsi(mx[c] - base[c]));
+		range = maxi(range, iabsi(base[c] - mn[c]));
+		bmin = mini(bmin, base[c]); bmax = maxi(bmax, base[c]);
+	}
+	const uint32_t limit = o.all_inten_tables ? 8u : ((range > 51) ? 8u : (range >= 7 ? 4u : 2u));
+	const ycc base_y = to_ycc(px_make((uint32_t)base[0], (uint32_t)base[1], (uint32_t)base[2], 255));
+
+	int dy[8];
+	uint64_t chroma[8];
+	for (int j = 0; j < 8; j++)
+	{
+		const int x = flip ? (j & 3) : (int)(s * 2 + (j >> 2)), y = flip ? (int)(s * 2 + (j >> 2)) : (j & 3);
+		const ycc& q = dec_y[x + y * 4];
+		dy[j] = base_y.y - q.y;
+		chroma[j] = sq_u64(base_y.cr - q.cr) + sq_u64(base_y.cb - q.cb);
+	}
+
+	uint32_t inten = 0;
+	uint64_t best_sub = UINT64_MAX;
+	for (uint32_t t = 0; t < limit; t++)
+	{
+		const int m0 = T->etc1_inten[t * 4], m3 = T->etc1_inten[t * 4 + 3]; // most negative / most positive modifier
+		uint64_t total = 0;
+		if (bmin + m0 >= 0 && bmax + m3 <= 255)
+		{
+			const int m1 = T->etc1_inten[t * 4 + 1], m2 = T->etc1_inten[t * 4 + 2];
+			for (int j = 0; j < 8; j++)
+			{
+				const uint64_t e = minu64(minu64(sq_u64(dy[j] + 256 * m0), sq_u64(dy[j] + 256 * m1)), minu64(sq_u64(dy[j] + 256 * m2), sq_u64(dy[j] + 256 * m3)));
+				total += e * 4 + chroma[j];
+			}
+		}
+		else
+		{
+			ycc tab[4];
+			for (int k = 0; k < 4; k++)
+			{
+				const int m = T->etc1_inten[t * 4 + k];
+				tab[k] = to_ycc(px_make(clamp255i(base[0] + m), clamp255i(base[1] + m), clamp255i(base[2] + m), 255));
+			}
+			for (int j = 0; j < 8; j++)
+			{
+				const int x = flip ? (j & 3) : (int)(s * 2 + (j >> 2)), y = flip ? (int)(s * 2 + (j >> 2)) : (j & 3);
+				const ycc& q = dec_y[x + y * 4];
+				total += minu64(minu64(ycc_diff(tab[0], q), ycc_diff(tab[1], q)), minu64(ycc_diff(tab[2], q), ycc_diff(tab[3], q)));
+			}
+		}
+		if (total < best_sub) { best_sub = total; inten = t; }
+		// Reference quirk (uastc_enc.cpp:2933): in the non-flipped layout the early-out sits outside the row loop, so the
+		// first table that fails to improve ends the whole table scan; in the flipped layout it only ends that table's rows.
+		else if (!flip) break;
+	}
+
+	// Error of the chosen table against the ORIGINAL block, selectors chosen against the decoded UASTC block (lowest index on ties).
+	ycc tab[4];
+	bool clamped = false;
+	for (int k = 0; k < 4; k++)
+	{
+		const int m = T->etc1_inten[inten * 4 + k];
+		if (bmin + m < 0 || bmax + m > 255) clamped = true;
+		tab[k] = to_ycc(px_make(clamp255i(base[0] + m), clamp255i(base[1] + m), clamp255i(base[2] + m), 255));
+	}
+	uint64_t err = 0;
+	for (int j = 0; j < 8; j++)
+	{
+		const int x = flip ? (j & 3) : (int)(s * 2 + (j >> 2)), y = flip ? (int)(s * 2 + (j >> 2)) : (j & 3);
+		const int i = x + y * 4;
+		uint32_t bi = 0;
+		if (!clamped)
+		{
+			// chroma terms are equal for the four candidates: the arg-min is decided by the luma term alone
+			uint64_t be = sq_u64(dy[j] + 256 * (int)T->etc1_inten[inten * 4]);
+			for (uint32_t k = 1; k < 4; k++) { const uint64_t e = sq_u64(dy[j] + 256 * (int)T->etc1_inten[inten * 4 + k]); if (e < be) { be = e; bi = k; } }
+		}
+		else
+		{
+			uint64_t be = ycc_diff(tab[0], dec_y[i]);
+			for (uint32_t k = 1; k < 4; k++) { const uint64_t e = ycc_diff(tab[k], dec_y[i]); if (e < be) { be = e; bi = k; } }
+		}
+		err += ycc_diff(src_y[i], tab[bi]);
+	}
+	inten_out = inten;
+	err_out = err;
+}
+
 // Trials bias_iter = first, first + stride, ... of one (flip, individ) combination; best kept with first-strictly-less.
 // Splitting a combination's bias iterations over threads and reducing by (err, order) reproduces the sequential result.
 BU_NI inline void etc1_hint_trials(const bu_tables* T, const etc1_search_opts& o, uint32_t flip, uint32_t individ, uint32_t first, uint32_t stride,
@@ -527,6 +623,9 @@ BU_NI inline void etc1_hint_trials(const bu_tables* T, const etc1_search_opts& o
 {
 	const uint8_t sorted_bias[32] = { 13, 0, 22, 29, 27, 12, 26, 9, 30, 31, 8, 10, 25, 2, 23, 5, 15, 7, 3, 11, 6, 17, 28, 18, 1, 19, 20, 21, 24, 4, 14, 16 };
 	const int mul = individ ? 15 : 31;
+	uint32_t memo_key[2][32], memo_n[2] = { 0, 0 };
+	uint8_t memo_inten[2][32];
+	uint64_t memo_err[2][32];
 
 	// texel index of subset s, slot j
 	// flip: subset = row pair, else column pair (g_etc1_pixel_coords, etc.cpp:314)
@@ -580,87 +679,25 @@ BU_NI inline void etc1_hint_trials(const bu_tables* T, const etc1_search_opts& o
 			}
 		}
 
-		// An ETC1 table colour is base + m on every channel, so unless a channel clamps, its luma is y_base + 256 m and its
-		// chroma equals the base's: the four candidates for a texel differ in the luma term only and
-		//     color_diff = 4 (dy - 256 m)^2 + dcr^2 + dcb^2
-		// is the same integer expression the reference evaluates, factored. Clamping (base + m outside 0..255) falls back
-		// to the general form. Both the table scan and the final selector choice use this.
+		// Both the chosen intensity table and the error contribution of a subset are pure functions of its base colour (for
+		// fixed flip / texels), and the bias trials revisit the same base colours many times (20 sorted biases produce only
+		// 13 / 10 distinct per-subset deltas), so each distinct base colour is searched once per call and remembered.
 		uint32_t inten[2] = { 0, 0 };
 		uint64_t err = 0;
 		for (int s = 0; s < 2; s++)
 		{
-			int range = 0, bmin = 255, bmax = 0;
-			for (int c = 0; c < 3; c++)
+			const uint32_t key = (uint32_t)base[s][0] | ((uint32_t)base[s][1] << 8) | ((uint32_t)base[s][2] << 16);
+			int hit = -1;
+			for (uint32_t k = 0; k < memo_n[s]; k++) if (memo_key[s][k] == key) { hit = (int)k; break; }
+			if (hit < 0)
 			{
-				range = maxi(range, iabsi(mx[s][c] - base[s][c]));
-				range = maxi(range, iabsi(base[s][c] - mn[s][c]));
-				bmin = mini(bmin, base[s][c]); bmax = maxi(bmax, base[s][c]);
+				uint32_t t; uint64_t e;
+				etc1_subset_search(T, o, flip, (uint32_t)s, base[s], mn[s], mx[s], src_y, dec_y, t, e);
+				hit = (int)memo_n[s]++;
+				memo_key[s][hit] = key; memo_inten[s][hit] = (uint8_t)t; memo_err[s][hit] = e;
 			}
-			const uint32_t limit = o.all_inten_tables ? 8u : ((range > 51) ? 8u : (range >= 7 ? 4u : 2u));
-			const ycc base_y = to_ycc(px_make((uint32_t)base[s][0], (uint32_t)base[s][1], (uint32_t)base[s][2], 255));
-
-			// per texel: luma delta to the base and the (table independent) chroma term
-			int dy[8];
-			uint64_t chroma[8];
-			for (int j = 0; j < 8; j++)
-			{
-				const int x = flip ? (j & 3) : (s * 2 + (j >> 2)), y = flip ? (s * 2 + (j >> 2)) : (j & 3);
-				const ycc& q = dec_y[x + y * 4];
-				dy[j] = base_y.y - q.y;
-				chroma[j] = sq_u64(base_y.cr - q.cr) + sq_u64(base_y.cb - q.cb);
-			}
-
-			uint64_t best_sub = UINT64_MAX;
-			for (uint32_t t = 0; t < limit; t++)
-			{
-				const int m0 = T->etc1_inten[t * 4], m3 = T->etc1_inten[t * 4 + 3]; // most negative / most positive modifier
-				uint64_t total = 0;
-				if (bmin + m0 >= 0 && bmax + m3 <= 255)
-				{
-					for (int j = 0; j < 8; j++)
-					{
-						uint64_t e = sq_u64(dy[j] + 256 * m0);
-						for (int k = 1; k < 4; k++) e = minu64(e, sq_u64(dy[j] + 256 * (int)T->etc1_inten[t * 4 + k]));
-						total += e * 4 + chroma[j];
-					}
-				}
-				else
-				{
-					ycc tab[4];
-					for (int k = 0; k < 4; k++)
-					{
-						const int m = T->etc1_inten[t * 4 + k];
-						tab[k] = to_ycc(px_make(clamp255i(base[s][0] + m), clamp255i(base[s][1] + m), clamp255i(base[s][2] + m), 255));
-					}
-					for (int j = 0; j < 8; j++)
-					{
-						const int x = flip ? (j & 3) : (s * 2 + (j >> 2)), y = flip ? (s * 2 + (j >> 2)) : (j & 3);
-						const ycc& q = dec_y[x + y * 4];
-						total += minu64(minu64(ycc_diff(tab[0], q), ycc_diff(tab[1], q)), minu64(ycc_diff(tab[2], q), ycc_diff(tab[3], q)));
-					}
-				}
-				if (total < best_sub) { best_sub = total; inten[s] = t; }
-				// Reference quirk (uastc_enc.cpp:2933): in the non-flipped layout the early-out sits outside the row loop, so the
-				// first table that fails to improve ends the whole table scan; in the flipped layout it only ends that table's rows.
-				else if (!flip) break;
-			}
-
-			// Error of this trial against the ORIGINAL block, selectors chosen against the decoded UASTC block (lowest index on ties).
-			ycc tab[4];
-			for (int k = 0; k < 4; k++)
-			{
-				const int m = T->etc1_inten[inten[s] * 4 + k];
-				tab[k] = to_ycc(px_make(clamp255i(base[s][0] + m), clamp255i(base[s][1] + m), clamp255i(base[s][2] + m), 255));
-			}
-			for (int j = 0; j < 8; j++)
-			{
-				const int x = flip ? (j & 3) : (s * 2 + (j >> 2)), y = flip ? (s * 2 + (j >> 2)) : (j & 3);
-				const int i = x + y * 4;
-				uint32_t bi = 0;
-				uint64_t be = ycc_diff(tab[0], dec_y[i]);
-				for (uint32_t k = 1; k < 4; k++) { const uint64_t e = ycc_diff(tab[k], dec_y[i]); if (e < be) { be = e; bi = k; } }
-				err += ycc_diff(src_y[i], tab[bi]);
-			}
+			inten[s] = memo_inten[s][hit];
+			err += memo_err[s][hit];
 		}
 
 		if (err < best.err)
