@@ -43,6 +43,10 @@ def lib():
             f.argtypes = [vp, vp, u32, vp, u32]
         L.b200_uastc_rdo.restype = i32
         L.b200_uastc_rdo.argtypes = [vp, u32, vp, vp, vp, u32, u32]
+        L.b200_etc1s_endpoint_histogram.restype = i32
+        L.b200_etc1s_endpoint_histogram.argtypes = [vp, vp, u32, vp]
+        L.b200_etc1s_endpoint_histogram_device.restype = i32
+        L.b200_etc1s_endpoint_histogram_device.argtypes = [vp, vp, u32, vp]
         L.b200_etc1s_set_flavour.restype = i32
         L.b200_etc1s_set_flavour.argtypes = [vp, i32]
         L.b200_etc1s_set_pixel_blocks.restype = i32
@@ -64,7 +68,7 @@ def lib():
 EXPORTS = [
     "b200_device_count", "b200_create_context", "b200_destroy_context", "b200_last_error",
     "b200_uastc_encode_blocks", "b200_uastc_encode_blocks_device", "b200_uastc_rdo",
-    "b200_etc1s_set_flavour", "b200_etc1s_set_pixel_blocks", "b200_etc1s_encode_blocks", "b200_etc1s_encode_pixel_clusters",
+    "b200_etc1s_set_flavour", "b200_etc1s_set_pixel_blocks", "b200_etc1s_endpoint_histogram", "b200_etc1s_endpoint_histogram_device", "b200_etc1s_encode_blocks", "b200_etc1s_encode_pixel_clusters",
     "b200_etc1s_refine_endpoint_clusterization", "b200_etc1s_find_optimal_selector_clusters_for_each_block",
     "b200_etc1s_determine_selectors", "b200_last_kernel_ms", "b200_last_launch_count", "b200_last_stage_ms",
     "b200_timer_start", "b200_timer_stop_ms", "b200_global_launch_count",

@@ -238,6 +238,21 @@ __global__ void __launch_bounds__(128) k_etc1s_fosc(const uint4* __restrict__ bl
 	}
 }
 
+// ---- endpoint training-set histogram (multi-GPU exchange point) ------------------------------------------------------------------
+// A block's endpoint training vector is a function of its 18-bit (r5, g5, b5, inten) key only (init_endpoint_training_vectors,
+// frontend.cpp:843-857: low/high block colours / 255, inserted twice with weight 1), and generate_hierarchical_codebook_threaded
+// starts by merging identical vectors into (vector, weight) pairs in lexicographic order (encoder/basisu_enc.h:2228-2260).
+// A dense u32[2^18] count per key is therefore a complete, order-free description of a shard's training set: ranks SUM
+// all-reduce it (1 MiB over NVLink) and every rank holds the global weighted unique set.
+__global__ void __launch_bounds__(256) k_etc1s_endpoint_histogram(const uint2* __restrict__ etc_blocks, uint32_t n, uint32_t* __restrict__ hist)
+{
+	const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= n) return;
+	const uint32_t w = __ldg(&etc_blocks[i]).x; // bytes 0..3: R5<<3, G5<<3, B5<<3, inten0<<5 | inten1<<2 | diff | flip
+	const uint32_t key = (((w >> 3) & 31) << 13) | (((w >> 11) & 31) << 8) | (((w >> 19) & 31) << 3) | ((w >> 29) & 7);
+	atomicAdd(hist + key, 2u); // two subblocks per block, weight 1 each
+}
+
 // ---- C ABI ------------------------------------------------------------------------------------------------------------------
 
 #define ETC_CHECK_BLOCKS(ctx, name) do { if (!(ctx)) return 0; if (!(ctx)->activate()) return 0; \
@@ -361,4 +376,34 @@ extern "C" int b200_etc1s_determine_selectors(b200_context* ctx, const void* pIn
 	k_etc1s_determine_selectors<<<(n + 127) / 128, 128, 0, ctx->stream>>>(static_cast<const uint4*>(ctx->d_etc_blocks), n, static_cast<const uint32_t*>(ctx->d_aux[1]),
 		static_cast<uint64_t*>(ctx->d_aux[0]), perceptual);
 	return finish(ctx, pOutput_blocks, 0, (size_t)n * 8);
+}
+
+extern "C" int b200_etc1s_endpoint_histogram_device(b200_context* ctx, const void* dEtc_blocks, uint32_t num_blocks, uint32_t* dHist)
+{
+	if (!ctx) return 0;
+	if (!ctx->activate()) return 0;
+	if (!num_blocks) return 1;
+	ctx->launches = 1; __atomic_add_fetch(&g_b200_total_launches, 1, __ATOMIC_RELAXED);
+	B200_CUDA_OK(ctx, cudaEventRecord(ctx->ev0, ctx->stream));
+	k_etc1s_endpoint_histogram<<<(num_blocks + 255) / 256, 256, 0, ctx->stream>>>(static_cast<const uint2*>(dEtc_blocks), num_blocks, dHist);
+	B200_CUDA_OK(ctx, cudaGetLastError());
+	B200_CUDA_OK(ctx, cudaEventRecord(ctx->ev1, ctx->stream));
+	B200_CUDA_OK(ctx, cudaStreamSynchronize(ctx->stream));
+	B200_CUDA_OK(ctx, cudaEventElapsedTime(&ctx->last_ms, ctx->ev0, ctx->ev1));
+	return 1;
+}
+
+extern "C" int b200_etc1s_endpoint_histogram(b200_context* ctx, const void* pEtc_blocks, uint32_t num_blocks, uint32_t* pHist)
+{
+	if (!ctx) return 0;
+	if (!ctx->activate()) return 0;
+	if (!pHist) { ctx->fail("b200_etc1s_endpoint_histogram: null histogram"); return 0; }
+	const size_t hist_bytes = sizeof(uint32_t) << 18;
+	if (!upload(ctx, 1, pEtc_blocks, (size_t)num_blocks * 8)) return 0;
+	if (!ctx->reserve(ctx->d_aux[0], ctx->aux_cap[0], hist_bytes)) return 0;
+	B200_CUDA_OK(ctx, cudaMemsetAsync(ctx->d_aux[0], 0, hist_bytes, ctx->stream));
+	B200_CUDA_OK(ctx, cudaStreamSynchronize(ctx->stream));
+	if (!b200_etc1s_endpoint_histogram_device(ctx, ctx->d_aux[1], num_blocks, static_cast<uint32_t*>(ctx->d_aux[0]))) return 0;
+	B200_CUDA_OK(ctx, cudaMemcpy(pHist, ctx->d_aux[0], hist_bytes, cudaMemcpyDeviceToHost));
+	return 1;
 }

@@ -15,6 +15,17 @@ using namespace bu;
 
 #include "b200_tables.cuh"
 
+// Occupancy knobs (tools/build_variant.sh -D...): minimum resident CTAs per SM the register allocator must allow.
+#ifndef BU_CAND_MINB
+#define BU_CAND_MINB 4
+#endif
+#ifndef BU_FIN_MINB
+#define BU_FIN_MINB 1
+#endif
+#ifndef BU_CLS_MINB
+#define BU_CLS_MINB 1
+#endif
+
 struct block_meta { block_class k; block_ranks ranks; }; // 16 B
 
 __device__ __forceinline__ void load_block(const uint4* __restrict__ blocks, uint32_t i, uint32_t* px)
@@ -28,7 +39,7 @@ __device__ __forceinline__ void load_block(const uint4* __restrict__ blocks, uin
 	}
 }
 
-__global__ void __launch_bounds__(128) k_classify_rank(const uint4* __restrict__ blocks, uint32_t n, block_meta* __restrict__ meta, uint4* __restrict__ out, level_opts o)
+__global__ void __launch_bounds__(128, BU_CLS_MINB) k_classify_rank(const uint4* __restrict__ blocks, uint32_t n, block_meta* __restrict__ meta, uint4* __restrict__ out, level_opts o)
 {
 	const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
 	if (i >= n) return;
@@ -54,7 +65,7 @@ __global__ void __launch_bounds__(128) k_classify_rank(const uint4* __restrict__
 }
 
 // gridDim.y = slot index; candidates are stored slot-major so a warp writes 32 consecutive 64 B records.
-__global__ void __launch_bounds__(128) k_candidates(const uint4* __restrict__ blocks, uint32_t n, const block_meta* __restrict__ meta,
+__global__ void __launch_bounds__(128, BU_CAND_MINB) k_candidates(const uint4* __restrict__ blocks, uint32_t n, const block_meta* __restrict__ meta,
 	candidate* __restrict__ cands, const slot_desc* __restrict__ slots, uint32_t first_slot, level_opts o)
 {
 	const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -79,7 +90,7 @@ __global__ void __launch_bounds__(128) k_candidates(const uint4* __restrict__ bl
 
 // One thread per block. (A cooperative 8-lanes-per-block variant was measured in round 1: 33.5 ms vs 23.8 ms for this
 // one -- the stage is issue-bound, not latency-bound, so spreading a block over lanes only adds redundant instructions.)
-__global__ void __launch_bounds__(128) k_finish(const uint4* __restrict__ blocks, uint32_t n, const block_meta* __restrict__ meta,
+__global__ void __launch_bounds__(128, BU_FIN_MINB) k_finish(const uint4* __restrict__ blocks, uint32_t n, const block_meta* __restrict__ meta,
 	const candidate* __restrict__ cands, uint32_t nslots, uint4* __restrict__ out, level_opts o, int level, uint32_t flags)
 {
 	const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;

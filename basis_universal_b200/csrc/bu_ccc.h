@@ -49,26 +49,32 @@ BU_NI inline void cell_evaluate(const bu_tables* T, const cell_cfg& cfg, const u
 		dc[c] = (int)su[hi[c]] - lc[c];
 	}
 
+	// Interpolated colours, channels (0,2) and (1,3) on 16-bit lanes. RGB cells keep byte 3 of the inner entries zero
+	// (the RGB metric never reads it).
 	uint32_t wc[32];
 	wc[0] = px_make(lc[0], lc[1], lc[2], lc[3]);
 	wc[N - 1] = px_make(lc[0] + dc[0], lc[1] + dc[1], lc[2] + dc[2], lc[3] + dc[3]);
-	for (uint32_t i = 1; i + 1 < N; i++)
 	{
-		const uint32_t w = wt[i];
-		uint32_t v = astc_lerp(lc[0], lc[0] + dc[0], w) | (astc_lerp(lc[1], lc[1] + dc[1], w) << 8) | (astc_lerp(lc[2], lc[2] + dc[2], w) << 16);
-		if (cfg.has_alpha) v |= astc_lerp(lc[3], lc[3] + dc[3], w) << 24;
-		wc[i] = v;
+		const uint32_t l02 = (uint32_t)lc[0] | ((uint32_t)lc[2] << 16), h02 = (uint32_t)(lc[0] + dc[0]) | ((uint32_t)(lc[2] + dc[2]) << 16);
+		const uint32_t l13 = cfg.has_alpha ? ((uint32_t)lc[1] | ((uint32_t)lc[3] << 16)) : (uint32_t)lc[1];
+		const uint32_t h13 = cfg.has_alpha ? ((uint32_t)(lc[1] + dc[1]) | ((uint32_t)(lc[3] + dc[3]) << 16)) : (uint32_t)(lc[1] + dc[1]);
+		for (uint32_t i = 1; i + 1 < N; i++)
+		{
+			const uint32_t w = wt[i];
+			wc[i] = astc_lerp_x2(l02, h02, w) | (astc_lerp_x2(l13, h13, w) << 8);
+		}
 	}
 
 	uint8_t st[16];
 	uint32_t total = 0; // <= 16 * 4 * 255^2, fits 32 bits
+	const uint32_t cmask = cfg.has_alpha ? 0xFFFFFFFFu : 0x00FFFFFFu;
 	if (force_sel)
 	{
 		// caller-imposed selectors (bc7enc.cpp:885-898): only the error is computed
 		for (uint32_t i = 0; i < n; i++)
 		{
 			const uint32_t s = force_sel[i];
-			total += cfg.has_alpha ? dist_rgba(wc[s], px[i]) : dist_rgb(wc[s], px[i]);
+			total += dist_masked(wc[s], px[i], cmask);
 			st[i] = (uint8_t)s;
 		}
 	}
@@ -82,14 +88,16 @@ BU_NI inline void cell_evaluate(const bu_tables* T, const cell_cfg& cfg, const u
 		                   : (float)N / ((float)(dc[0] * dc[0] + dc[1] * dc[1] + dc[2] * dc[2]) + .00000125f);
 		const uint32_t dc01 = pack_s16x2(dc[0], dc[1]), dc23 = pack_s16x2(dc[2], d3);
 		const int K = lc[0] * dc[0] + lc[1] * dc[1] + lc[2] * dc[2] + (a4 ? lc[3] * dc[3] : 0);
+#if defined(BU_EVAL_UNROLL1)
+#pragma unroll 1
+#endif
 		for (uint32_t i = 0; i < n; i++)
 		{
 			const uint32_t p = px[i];
 			const int dot = dot_s16x4_u8x4(dc01, dc23, p) - K;
 			int s = (int)((float)dot * f + .5f);
 			s = clampi(s, 1, (int)N - 1);
-			const uint32_t e0 = a4 ? dist_rgba(wc[s - 1], p) : dist_rgb(wc[s - 1], p);
-			const uint32_t e1 = a4 ? dist_rgba(wc[s], p) : dist_rgb(wc[s], p);
+			const uint32_t e0 = dist_masked(wc[s - 1], p, cmask), e1 = dist_masked(wc[s], p, cmask);
 			uint32_t e = e1;
 			if (e0 == e1) { if (s == 1) s = 0; }   // prefer the non-interpolated endpoint
 			else if (e0 < e1) { e = e0; --s; }
@@ -457,7 +465,12 @@ BU_NI inline void cell_compress(const bu_tables* T, const cell_cfg& cfg, const u
 // Integer only. The reference's early-out on best_err_so_far only truncates sums that already exceed the running best, so
 // returning the full sum leaves every comparison made by the partition rankers unchanged.
 
-BU_NI inline uint64_t cell_estimate(const bu_tables* T, uint32_t wbits, uint32_t comps, const uint32_t* px, uint32_t n)
+#if defined(BU_RANK_INLINE)
+BU_FI uint64_t cell_estimate(
+#else
+BU_NI inline uint64_t cell_estimate(
+#endif
+const bu_tables* T, uint32_t wbits, uint32_t comps, const uint32_t* px, uint32_t n)
 {
 	const uint32_t N = 1u << wbits;
 	const uint8_t* wt = T->weights + wbits * 32;
@@ -474,8 +487,13 @@ BU_NI inline uint64_t cell_estimate(const bu_tables* T, uint32_t wbits, uint32_t
 	uint32_t wc[32];
 	wc[0] = px_make(lo[0], lo[1], lo[2], lo[3]);
 	wc[N - 1] = px_make(hi[0], hi[1], hi[2], hi[3]);
-	for (uint32_t i = 1; i + 1 < N; i++)
-		wc[i] = px_make(astc_lerp(lo[0], hi[0], wt[i]), astc_lerp(lo[1], hi[1], wt[i]), astc_lerp(lo[2], hi[2], wt[i]), (comps == 4) ? astc_lerp(lo[3], hi[3], wt[i]) : 255u);
+	{
+		const uint32_t l02 = lo[0] | (lo[2] << 16), h02 = hi[0] | (hi[2] << 16);
+		const uint32_t l13 = (comps == 4) ? (lo[1] | (lo[3] << 16)) : lo[1], h13 = (comps == 4) ? (hi[1] | (hi[3] << 16)) : hi[1];
+		const uint32_t opaque = (comps == 4) ? 0u : 0xFF000000u;
+		for (uint32_t i = 1; i + 1 < N; i++)
+			wc[i] = astc_lerp_x2(l02, h02, wt[i]) | (astc_lerp_x2(l13, h13, wt[i]) << 8) | opaque;
+	}
 
 	const int a[4] = { (int)hi[0] - (int)lo[0], (int)hi[1] - (int)lo[1], (int)hi[2] - (int)lo[2], (int)hi[3] - (int)lo[3] };
 	int thresh[31];

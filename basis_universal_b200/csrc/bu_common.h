@@ -60,6 +60,14 @@ BU_FI uint32_t astc_lerp(uint32_t l, uint32_t h, uint32_t w)
 	return ((l * (64 - w) + h * w + 32) >> 6) >> 8;
 }
 
+// Two interpolations at once on 16-bit lanes (l, h <= 255 per lane). With t = l (64 - w) + h w <= 16320 the scalar form is
+// (257 t + 32) >> 14 = (t + ((t + 32) >> 8)) >> 6 (nested floor division), and every intermediate fits its 16-bit lane.
+BU_FI uint32_t astc_lerp_x2(uint32_t l2, uint32_t h2, uint32_t w)
+{
+	const uint32_t t = l2 * (64 - w) + h2 * w;
+	return ((t + (((t + 0x00200020u) >> 8) & 0x00FF00FFu)) >> 6) & 0x00FF00FFu;
+}
+
 BU_FI uint32_t sq_diff(int a, int b) { int d = a - b; return (uint32_t)(d * d); }
 
 // Squared distances between packed RGBA8 texels. On the device these are two instructions: per-byte |a-b| (VABSDIFF4) and
@@ -68,6 +76,8 @@ BU_FI uint32_t sq_diff(int a, int b) { int d = a - b; return (uint32_t)(d * d); 
 BU_FI uint32_t dist_rgba(uint32_t p, uint32_t q) { const uint32_t d = __vabsdiffu4(p, q); return __dp4a(d, d, 0u); }
 BU_FI uint32_t dist_rgb(uint32_t p, uint32_t q) { const uint32_t d = __vabsdiffu4(p, q) & 0x00FFFFFFu; return __dp4a(d, d, 0u); }
 BU_FI uint32_t dist_la(uint32_t p, uint32_t q) { const uint32_t d = __vabsdiffu4(p, q) & 0xFF0000FFu; return __dp4a(d, d, 0u); }
+// byte mask selects the channels that count (0x00FFFFFF rgb, 0xFFFFFFFF rgba)
+BU_FI uint32_t dist_masked(uint32_t p, uint32_t q, uint32_t mask) { const uint32_t d = __vabsdiffu4(p, q) & mask; return __dp4a(d, d, 0u); }
 // sum_c s16(dc[c]) * u8(p[c]) with dc packed as two s16 pairs: one DP2A each for the low and high byte pairs of p.
 BU_FI int dot_s16x4_u8x4(uint32_t dc01, uint32_t dc23, uint32_t p)
 {
@@ -83,6 +93,7 @@ BU_FI uint32_t dist_rgb(uint32_t p, uint32_t q)
 }
 BU_FI uint32_t dist_rgba(uint32_t p, uint32_t q) { return dist_rgb(p, q) + sq_diff((int)px_c(p, 3), (int)px_c(q, 3)); }
 BU_FI uint32_t dist_la(uint32_t p, uint32_t q) { return sq_diff((int)px_c(p, 0), (int)px_c(q, 0)) + sq_diff((int)px_c(p, 3), (int)px_c(q, 3)); }
+BU_FI uint32_t dist_masked(uint32_t p, uint32_t q, uint32_t mask) { return (mask >> 24) ? dist_rgba(p, q) : dist_rgb(p, q); }
 BU_FI int dot_s16x4_u8x4(uint32_t dc01, uint32_t dc23, uint32_t p)
 {
 	return (int)(int16_t)(dc01 & 0xFFFF) * (int)px_c(p, 0) + (int)(int16_t)(dc01 >> 16) * (int)px_c(p, 1) +

@@ -525,9 +525,10 @@ BU_HD inline etc1_search_opts etc1_search_setup(const bu_tables* T, uint32_t mod
 // the base's: the four candidates for a texel differ in the luma term only and
 //     color_diff = 4 (dy + 256 m)^2 + dcr^2 + dcb^2
 // is the same integer expression the reference evaluates, factored. A clamping table (base + m outside 0..255) takes the general form.
-BU_NI inline void etc1_subset_search(const bu_tables* T, const etc1_search_opts& o, uint32_t flip, uint32_t s, const int* base, const int* mn, const int* mx,
+BU_NI inline void etc1_subset_search(const bu_tables* T, const etc1_search_opts& o, uint32_t flip, uint32_t s, uint32_t base_key, const int* mn, const int* mx,
 	const ycc* src_y, const ycc* dec_y, uint32_t& inten_out, uint64_t& err_out)
 {
+	const int base[3] = { (int)(base_key & 255), (int)((base_key >> 8) & 255), (int)((base_key >> 16) & 255) };
 	int range = 0, bmin = 255, bmax = 0;
 	for (int c = 0; c < 3; c++)
 	{
@@ -538,30 +539,31 @@ BU_NI inline void etc1_subset_search(const bu_tables* T, const etc1_search_opts&
 	const uint32_t limit = o.all_inten_tables ? 8u : ((range > 51) ? 8u : (range >= 7 ? 4u : 2u));
 	const ycc base_y = to_ycc(px_make((uint32_t)base[0], (uint32_t)base[1], (uint32_t)base[2], 255));
 
-	int dy[8];
-	uint64_t chroma[8];
+	// The four modifiers of a table are (-a, -b, b, a), so min_k (dy + 256 m_k)^2 = (min(||dy| - 256 a|, ||dy| - 256 b|))^2.
+	int ady[8];
+	uint64_t chroma_sum = 0;
 	for (int j = 0; j < 8; j++)
 	{
 		const int x = flip ? (j & 3) : (int)(s * 2 + (j >> 2)), y = flip ? (int)(s * 2 + (j >> 2)) : (j & 3);
 		const ycc& q = dec_y[x + y * 4];
-		dy[j] = base_y.y - q.y;
-		chroma[j] = sq_u64(base_y.cr - q.cr) + sq_u64(base_y.cb - q.cb);
+		ady[j] = iabsi(base_y.y - q.y);
+		chroma_sum += sq_u64(base_y.cr - q.cr) + sq_u64(base_y.cb - q.cb);
 	}
 
 	uint32_t inten = 0;
 	uint64_t best_sub = UINT64_MAX;
 	for (uint32_t t = 0; t < limit; t++)
 	{
-		const int m0 = T->etc1_inten[t * 4], m3 = T->etc1_inten[t * 4 + 3]; // most negative / most positive modifier
+		const int mb = 256 * (int)T->etc1_inten[t * 4 + 2], ma = 256 * (int)T->etc1_inten[t * 4 + 3]; // small / large positive modifier
 		uint64_t total = 0;
-		if (bmin + m0 >= 0 && bmax + m3 <= 255)
+		if (bmin * 256 >= ma && bmax * 256 + ma <= 255 * 256)
 		{
-			const int m1 = T->etc1_inten[t * 4 + 1], m2 = T->etc1_inten[t * 4 + 2];
 			for (int j = 0; j < 8; j++)
 			{
-				const uint64_t e = minu64(minu64(sq_u64(dy[j] + 256 * m0), sq_u64(dy[j] + 256 * m1)), minu64(sq_u64(dy[j] + 256 * m2), sq_u64(dy[j] + 256 * m3)));
-				total += e * 4 + chroma[j];
+				const uint32_t d = (uint32_t)mini(iabsi(ady[j] - ma), iabsi(ady[j] - mb));
+				total += (uint64_t)d * d;
 			}
+			total = total * 4 + chroma_sum;
 		}
 		else
 		{
@@ -601,9 +603,10 @@ BU_NI inline void etc1_subset_search(const bu_tables* T, const etc1_search_opts&
 		uint32_t bi = 0;
 		if (!clamped)
 		{
-			// chroma terms are equal for the four candidates: the arg-min is decided by the luma term alone
-			uint64_t be = sq_u64(dy[j] + 256 * (int)T->etc1_inten[inten * 4]);
-			for (uint32_t k = 1; k < 4; k++) { const uint64_t e = sq_u64(dy[j] + 256 * (int)T->etc1_inten[inten * 4 + k]); if (e < be) { be = e; bi = k; } }
+			// chroma terms are equal for the four candidates: the arg-min is decided by |luma difference| alone
+			const int dy = base_y.y - dec_y[i].y;
+			int be = iabsi(dy + 256 * (int)T->etc1_inten[inten * 4]);
+			for (uint32_t k = 1; k < 4; k++) { const int e = iabsi(dy + 256 * (int)T->etc1_inten[inten * 4 + k]); if (e < be) { be = e; bi = k; } }
 		}
 		else
 		{
@@ -618,17 +621,19 @@ BU_NI inline void etc1_subset_search(const bu_tables* T, const etc1_search_opts&
 
 // Trials bias_iter = first, first + stride, ... of one (flip, individ) combination; best kept with first-strictly-less.
 // Splitting a combination's bias iterations over threads and reducing by (err, order) reproduces the sequential result.
+//
+// Both the chosen intensity table and the error contribution of a subset are pure functions of its scaled base colour (for
+// fixed flip / texels), and the bias trials revisit the same base colours many times (the 20 sorted biases of level 2 give
+// only 13 / 10 distinct per-subset deltas). The work is therefore phased: (1) enumerate the trials' base colours and
+// deduplicate them per subset, (2) search each distinct base colour once -- a loop every lane of a warp walks together,
+// which a look-aside cache inside the trial loop would not give -- (3) combine per trial in the reference's order.
 BU_NI inline void etc1_hint_trials(const bu_tables* T, const etc1_search_opts& o, uint32_t flip, uint32_t individ, uint32_t first, uint32_t stride,
 	const ycc* src_y, const ycc* dec_y, const uint32_t* dec, etc1_hint& best)
 {
 	const uint8_t sorted_bias[32] = { 13, 0, 22, 29, 27, 12, 26, 9, 30, 31, 8, 10, 25, 2, 23, 5, 15, 7, 3, 11, 6, 17, 28, 18, 1, 19, 20, 21, 24, 4, 14, 16 };
 	const int mul = individ ? 15 : 31;
-	uint32_t memo_key[2][32], memo_n[2] = { 0, 0 };
-	uint8_t memo_inten[2][32];
-	uint64_t memo_err[2][32];
 
-	// texel index of subset s, slot j
-	// flip: subset = row pair, else column pair (g_etc1_pixel_coords, etc.cpp:314)
+	// subset = row pair when flipped, else column pair (g_etc1_pixel_coords, etc.cpp:314)
 	int unbiased[2][3];
 	int mn[2][3], mx[2][3];
 	for (int s = 0; s < 2; s++)
@@ -649,7 +654,11 @@ BU_NI inline void etc1_hint_trials(const bu_tables* T, const etc1_search_opts& o
 		for (int c = 0; c < 3; c++) unbiased[s][c] = (int)(uint8_t)((sum[c] * (uint32_t)mul + 1020) / (8 * 255));
 	}
 
-	for (uint32_t bias_iter = first; bias_iter < o.last_bias; bias_iter += stride)
+	// (1) base colours of every trial, deduplicated per subset
+	uint32_t keys[2][32], n_keys[2] = { 0, 0 };
+	uint8_t trial_key[2][32];
+	uint32_t n_trials = 0;
+	for (uint32_t bias_iter = first; bias_iter < o.last_bias; bias_iter += stride, n_trials++)
 	{
 		const uint32_t bias = o.sorted_bias_table ? sorted_bias[bias_iter] : bias_iter;
 
@@ -661,11 +670,11 @@ BU_NI inline void etc1_hint_trials(const bu_tables* T, const etc1_search_opts& o
 		}
 
 		// Stored base colours -> scaled 8-bit base per subset (etc.h set_block_color4 / set_block_color5_clamp, get_block_color).
-		int base[2][3];
+		uint32_t key[2] = { 0, 0 };
 		if (individ)
 		{
 			for (int s = 0; s < 2; s++)
-				for (int c = 0; c < 3; c++) { const int v = mini(col[s][c], 15); base[s][c] = (v << 4) | v; }
+				for (int c = 0; c < 3; c++) { const int v = mini(col[s][c], 15); key[s] |= (uint32_t)((v << 4) | v) << (8 * c); }
 		}
 		else
 		{
@@ -674,38 +683,43 @@ BU_NI inline void etc1_hint_trials(const bu_tables* T, const etc1_search_opts& o
 				const int b0 = mini(col[0][c], 31);
 				const int d = clampi(col[1][c] - col[0][c], -4, 3);
 				const int b1 = clampi(b0 + d, 0, 31);
-				base[0][c] = (b0 << 3) | (b0 >> 2);
-				base[1][c] = (b1 << 3) | (b1 >> 2);
+				key[0] |= (uint32_t)((b0 << 3) | (b0 >> 2)) << (8 * c);
+				key[1] |= (uint32_t)((b1 << 3) | (b1 >> 2)) << (8 * c);
 			}
 		}
-
-		// Both the chosen intensity table and the error contribution of a subset are pure functions of its base colour (for
-		// fixed flip / texels), and the bias trials revisit the same base colours many times (20 sorted biases produce only
-		// 13 / 10 distinct per-subset deltas), so each distinct base colour is searched once per call and remembered.
-		uint32_t inten[2] = { 0, 0 };
-		uint64_t err = 0;
 		for (int s = 0; s < 2; s++)
 		{
-			const uint32_t key = (uint32_t)base[s][0] | ((uint32_t)base[s][1] << 8) | ((uint32_t)base[s][2] << 16);
-			int hit = -1;
-			for (uint32_t k = 0; k < memo_n[s]; k++) if (memo_key[s][k] == key) { hit = (int)k; break; }
-			if (hit < 0)
-			{
-				uint32_t t; uint64_t e;
-				etc1_subset_search(T, o, flip, (uint32_t)s, base[s], mn[s], mx[s], src_y, dec_y, t, e);
-				hit = (int)memo_n[s]++;
-				memo_key[s][hit] = key; memo_inten[s][hit] = (uint8_t)t; memo_err[s][hit] = e;
-			}
-			inten[s] = memo_inten[s][hit];
-			err += memo_err[s][hit];
+			uint32_t k = 0;
+			while (k < n_keys[s] && keys[s][k] != key[s]) k++;
+			if (k == n_keys[s]) keys[s][n_keys[s]++] = key[s];
+			trial_key[s][n_trials] = (uint8_t)k;
+		}
+	}
+
+	// (2) one search per distinct base colour
+	uint8_t key_inten[2][32];
+	uint64_t key_err[2][32];
+	for (int s = 0; s < 2; s++)
+		for (uint32_t k = 0; k < n_keys[s]; k++)
+		{
+			uint32_t t; uint64_t e;
+			etc1_subset_search(T, o, flip, (uint32_t)s, keys[s][k], mn[s], mx[s], src_y, dec_y, t, e);
+			key_inten[s][k] = (uint8_t)t; key_err[s][k] = e;
 		}
 
+	// (3) trials in the reference's order, first strictly smaller error wins
+	uint32_t bias_iter = first;
+	for (uint32_t i = 0; i < n_trials; i++, bias_iter += stride)
+	{
+		const uint32_t k0 = trial_key[0][i], k1 = trial_key[1][i];
+		const uint64_t err = key_err[0][k0] + key_err[1][k1];
 		if (err < best.err)
 		{
 			best.err = err;
 			best.order = (flip * 2 + individ) * 32 + bias_iter;
 			best.flip = (uint8_t)flip; best.diff = (uint8_t)(individ ? 0 : 1);
-			best.inten0 = (uint8_t)inten[0]; best.inten1 = (uint8_t)inten[1]; best.bias = (uint8_t)bias;
+			best.inten0 = key_inten[0][k0]; best.inten1 = key_inten[1][k1];
+			best.bias = (uint8_t)(o.sorted_bias_table ? sorted_bias[bias_iter] : bias_iter);
 		}
 	}
 }

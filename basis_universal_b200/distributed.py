@@ -1,0 +1,32 @@
+"""Multi-GPU plumbing for the ETC1S path: per-block stages shard by block rows with no collective; the
+codebook stage needs one exchange -- a SUM all-reduce of the 2^18-bin endpoint-key histogram -- after which every rank holds
+the same global training set and can run the (deterministic) clusterer replicated. UASTC needs no collective at all."""
+import numpy as np
+
+from . import etc1s, sharding
+
+
+def allreduce_endpoint_histogram(local_hist, group=None):
+    """local_hist: torch tensor (2**18,) of int32/int64 counts on this rank's device (cuda for NCCL, cpu for gloo).
+    In-place SUM all-reduce; a no-op when torch.distributed is not initialised (single process)."""
+    import torch.distributed as dist
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+        dist.all_reduce(local_hist, op=dist.ReduceOp.SUM, group=group)
+    return local_hist
+
+
+def global_endpoint_training_set(ctx, blocks_x, blocks_y, all_blocks, perceptual, total_perms, rank, world_size, group=None):
+    """Rank-local ETC1S block optimisation of this rank's block rows on the GPU, histogram of its endpoint keys on the GPU,
+    NCCL all-reduce, then the global (keys, vec6F, weights) -- identical on every rank."""
+    import torch
+    first, last = sharding.block_range(blocks_x, blocks_y, rank, world_size)
+    local = np.ascontiguousarray(all_blocks[first:last])
+    ctx.set_pixel_blocks(local)
+    etc_blocks = ctx.encode_etc1s_blocks(perceptual, total_perms)
+    d_blocks = torch.from_numpy(etc_blocks).cuda()
+    d_hist = torch.zeros(1 << 18, dtype=torch.int32, device="cuda")
+    torch.cuda.synchronize()
+    ctx.endpoint_histogram_device(d_blocks.data_ptr(), etc_blocks.shape[0], d_hist.data_ptr())
+    allreduce_endpoint_histogram(d_hist, group)
+    hist = d_hist.cpu().numpy().astype(np.uint32)
+    return etc_blocks, etc1s.training_vectors_from_histogram(hist)

@@ -98,3 +98,37 @@ class Etc1sContext:
         out = np.empty((self.total_blocks, 8), np.uint8)
         self._check(self._lib.b200_etc1s_determine_selectors(self._ctx, _p(c), _p(out), int(bool(perceptual))), "b200_etc1s_determine_selectors")
         return out
+
+
+    def endpoint_histogram(self, etc_blocks):
+        """(N, 8) uint8 ETC1S blocks (host) -> (2**18,) uint32 counts per endpoint training key (two per block)."""
+        b = np.ascontiguousarray(etc_blocks, np.uint8)
+        hist = np.empty(1 << 18, np.uint32)
+        self._check(self._lib.b200_etc1s_endpoint_histogram(self._ctx, _p(b), b.shape[0], _p(hist)), "b200_etc1s_endpoint_histogram")
+        return hist
+
+    def endpoint_histogram_device(self, d_etc_blocks_ptr, num_blocks, d_hist_ptr):
+        """Device form: accumulates into a caller-zeroed device buffer of 2**18 uint32 (ready for an NCCL all-reduce)."""
+        ok = self._lib.b200_etc1s_endpoint_histogram_device(self._ctx, ctypes.c_void_p(d_etc_blocks_ptr), int(num_blocks), ctypes.c_void_p(d_hist_ptr))
+        self._check(ok, "b200_etc1s_endpoint_histogram_device")
+
+
+def endpoint_keys(etc_blocks):
+    """Host restatement of the key extraction (test oracle for the histogram kernel): bytes 0..3 of an ETC1S etc_block."""
+    b = np.asarray(etc_blocks, np.uint8).astype(np.uint32)
+    return ((b[:, 0] >> 3) << 13) | ((b[:, 1] >> 3) << 8) | ((b[:, 2] >> 3) << 3) | (b[:, 3] >> 5)
+
+
+_INTEN_LOW_HIGH = np.array([[-8, 8], [-17, 17], [-29, 29], [-42, 42], [-60, 60], [-80, 80], [-106, 106], [-183, 183]], np.int32)  # g_etc1_inten_tables[t][0], [t][3]
+
+
+def training_vectors_from_histogram(hist):
+    """Global weighted unique endpoint training set from the (all-reduced) key histogram, as the reference builds it
+    (frontend.cpp:843-857): vec6F = (low rgb, high rgb) * (1/255), weight = count. Returned in ascending key order."""
+    keys = np.nonzero(hist)[0].astype(np.uint32)
+    r5, g5, b5, inten = (keys >> 13) & 31, (keys >> 8) & 31, (keys >> 3) & 31, keys & 7
+    base = np.stack([(r5 << 3) | (r5 >> 2), (g5 << 3) | (g5 >> 2), (b5 << 3) | (b5 >> 2)], -1).astype(np.int32)
+    low = np.clip(base + _INTEN_LOW_HIGH[inten, 0:1], 0, 255)
+    high = np.clip(base + _INTEN_LOW_HIGH[inten, 1:2], 0, 255)
+    vecs = np.concatenate([low, high], -1).astype(np.float32) * np.float32(1.0 / 255.0)
+    return keys, vecs, hist[keys].astype(np.uint64)

@@ -106,6 +106,18 @@ int b200_etc1s_find_optimal_selector_clusters_for_each_block(b200_context* ctx, 
 /* opencl_determine_selectors (opencl.h:137). */
 int b200_etc1s_determine_selectors(b200_context* ctx, const void* pInput_etc_color5_and_inten, void* pOutput_blocks, int perceptual);
 
+/* ---- ETC1S multi-GPU exchange point -------------------------------------------------------------------------------------- */
+
+/* Histogram of the 18-bit endpoint training keys (r5<<13 | g5<<8 | b5<<3 | inten) of `num_blocks` ETC1S blocks, each block
+ * counted twice (its two subblocks): a complete description of the shard's endpoint training set
+ * (basisu_frontend::init_endpoint_training_vectors, encoder/basisu_frontend.cpp:825-867, followed by the duplicate-merging
+ * std::map at the top of generate_hierarchical_codebook_threaded, encoder/basisu_enc.h:2228-2260). Ranks that each own a
+ * block-row range SUM all-reduce these 2^18 u32 counters (NCCL) to obtain the global weighted unique training set.
+ * Host form: pHist receives 2^18 counters. Device form ACCUMULATES into dHist (caller zeroes it), so the buffer can be
+ * handed straight to an all-reduce. */
+int b200_etc1s_endpoint_histogram(b200_context* ctx, const void* pEtc_blocks, uint32_t num_blocks, uint32_t* pHist);
+int b200_etc1s_endpoint_histogram_device(b200_context* ctx, const void* dEtc_blocks, uint32_t num_blocks, uint32_t* dHist);
+
 /* ---- instrumentation ------------------------------------------------------------------------------------------------- */
 
 /* Device time in milliseconds of the kernels of the last successful encode call on this context (CUDA events on the

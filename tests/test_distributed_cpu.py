@@ -50,3 +50,37 @@ def test_two_rank_block_row_sharding_gloo():
         assert p.exitcode == 0
     ok, units, tmax = q.get()
     assert ok and units == nbx * nby * 16 and tmax == 1.5
+
+
+def _hist_worker(rank, world, port, q):
+    """gloo all-reduce of per-rank endpoint-key histograms == histogram of the whole image (the ETC1S exchange step)."""
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from basis_universal_b200 import distributed, etc1s
+    rng = np.random.default_rng(5)           # same stream on every rank: the "image" of ETC1S blocks
+    nbx, nby = 24, 19
+    blocks = rng.integers(0, 256, (nbx * nby, 8), dtype=np.uint8)
+    first, last = sharding.block_range(nbx, nby, rank, world)
+    local = torch.from_numpy(np.bincount(etc1s.endpoint_keys(blocks[first:last]), minlength=1 << 18).astype(np.int32) * 2)
+    distributed.allreduce_endpoint_histogram(local)
+    whole = np.bincount(etc1s.endpoint_keys(blocks), minlength=1 << 18) * 2
+    keys, vecs, weights = etc1s.training_vectors_from_histogram(local.numpy().astype(np.uint32))
+    ok = bool(np.array_equal(local.numpy(), whole)) and int(weights.sum()) == 2 * nbx * nby and vecs.shape == (len(keys), 6)
+    if rank == 0:
+        q.put(ok)
+    dist.destroy_process_group()
+
+
+def test_two_rank_endpoint_histogram_allreduce_gloo():
+    world = 2
+    ctx = mp.get_context("spawn")
+    q = ctx.SimpleQueue()
+    port = _free_port()
+    procs = [ctx.Process(target=_hist_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(180)
+        assert p.exitcode == 0
+    assert q.get()
