@@ -4,7 +4,8 @@ import ctypes
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libbasisu_b200.so")
+# BASISU_B200_LIB selects another build of the same library (tools/build_variant.sh); there is still no CPU fallback.
+LIB_PATH = os.environ.get("BASISU_B200_LIB") or os.path.join(HERE, "libbasisu_b200.so")
 
 _lib = None
 

@@ -39,7 +39,7 @@ extern "C" void b200_destroy_context(b200_context* ctx)
 	if (!ctx) return;
 	cudaSetDevice(ctx->device);
 	cudaStreamSynchronize(ctx->stream);
-	void* bufs[] = { ctx->d_in, ctx->d_out, ctx->d_meta, ctx->d_cands, ctx->d_slots, ctx->d_etc_blocks };
+	void* bufs[] = { ctx->d_in, ctx->d_out, ctx->d_meta, ctx->d_cands, ctx->d_slots, ctx->d_lists, ctx->d_etc_blocks };
 	for (void* p : bufs) if (p) cudaFree(p);
 	for (void* p : ctx->d_aux) if (p) cudaFree(p);
 	cudaEventDestroy(ctx->ev0);

@@ -17,7 +17,7 @@ using namespace bu;
 
 // Occupancy knobs (tools/build_variant.sh -D...): minimum resident CTAs per SM the register allocator must allow.
 #ifndef BU_CAND_MINB
-#define BU_CAND_MINB 4
+#define BU_CAND_MINB 10
 #endif
 #ifndef BU_FIN_MINB
 #define BU_FIN_MINB 1
@@ -39,59 +39,86 @@ __device__ __forceinline__ void load_block(const uint4* __restrict__ blocks, uin
 	}
 }
 
-__global__ void __launch_bounds__(128, BU_CLS_MINB) k_classify_rank(const uint4* __restrict__ blocks, uint32_t n, block_meta* __restrict__ meta, uint4* __restrict__ out, level_opts o)
+// Work lists: one compacted list of block indices per slot class (LA / RGB / alpha slots), so that every warp of
+// k_candidates is fully populated with blocks that actually run its slot. Layout: counts[4] then lists[3][n].
+struct work_lists { uint32_t* counts; uint32_t* list[3]; };
+
+__device__ __forceinline__ void list_append(uint32_t* count, uint32_t* list, bool pred, uint32_t value)
 {
-	const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-	if (i >= n) return;
-	uint32_t px[16];
-	load_block(blocks, i, px);
-	block_meta m;
-	m.k = classify_block(px, o.la_only_transparent != 0);
-	if (m.k.solid)
-	{
-		uint8_t b[16];
-		pack_solid_block(&d_tables, px[0], b);
-		uint4 v;
-		v.x = b[0] | (b[1] << 8) | (b[2] << 16) | ((uint32_t)b[3] << 24);
-		v.y = b[4] | (b[5] << 8) | (b[6] << 16) | ((uint32_t)b[7] << 24);
-		v.z = b[8] | (b[9] << 8) | (b[10] << 16) | ((uint32_t)b[11] << 24);
-		v.w = b[12] | (b[13] << 8) | (b[14] << 16) | ((uint32_t)b[15] << 24);
-		out[i] = v;
-		for (int j = 0; j < 12; j++) m.ranks.r[j] = 0;
-	}
-	else
-		rank_block(&d_tables, o, m.k, px, m.ranks);
-	meta[i] = m;
+	// warp-aggregated: one atomic per warp; a warp's blocks stay contiguous and in order
+	const uint32_t mask = __ballot_sync(0xFFFFFFFFu, pred);
+	if (!mask) return;
+	const uint32_t lane = threadIdx.x & 31u, leader = (uint32_t)__ffs((int)mask) - 1u;
+	uint32_t base = 0;
+	if (lane == leader) base = atomicAdd(count, (uint32_t)__popc(mask));
+	base = __shfl_sync(0xFFFFFFFFu, base, (int)leader);
+	if (pred) list[base + (uint32_t)__popc(mask & ((1u << lane) - 1u))] = value;
 }
 
-// gridDim.y = slot index; candidates are stored slot-major so a warp writes 32 consecutive 64 B records.
-__global__ void __launch_bounds__(128, BU_CAND_MINB) k_candidates(const uint4* __restrict__ blocks, uint32_t n, const block_meta* __restrict__ meta,
-	candidate* __restrict__ cands, const slot_desc* __restrict__ slots, uint32_t first_slot, level_opts o)
+__global__ void __launch_bounds__(128, BU_CLS_MINB) k_classify_rank(const uint4* __restrict__ blocks, uint32_t n, block_meta* __restrict__ meta, uint4* __restrict__ out,
+	work_lists wl, level_opts o)
 {
 	const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-	if (i >= n) return;
+	const bool in_range = i < n;
+	bool active = false;
+	block_meta m;
+	m.k.has_alpha = 0; m.k.is_la = 0; m.k.solid = 0;
+	if (in_range)
+	{
+		uint32_t px[16];
+		load_block(blocks, i, px);
+		m.k = classify_block(px, o.la_only_transparent != 0);
+		if (m.k.solid)
+		{
+			uint8_t b[16];
+			pack_solid_block(&d_tables, px[0], b);
+			uint4 v;
+			v.x = b[0] | (b[1] << 8) | (b[2] << 16) | ((uint32_t)b[3] << 24);
+			v.y = b[4] | (b[5] << 8) | (b[6] << 16) | ((uint32_t)b[7] << 24);
+			v.z = b[8] | (b[9] << 8) | (b[10] << 16) | ((uint32_t)b[11] << 24);
+			v.w = b[12] | (b[13] << 8) | (b[14] << 16) | ((uint32_t)b[15] << 24);
+			out[i] = v;
+			for (int j = 0; j < 12; j++) m.ranks.r[j] = 0;
+		}
+		else
+		{
+			rank_block(&d_tables, o, m.k, px, m.ranks);
+			active = true;
+		}
+		meta[i] = m;
+	}
+	slot_desc probe; probe.mode = 0; probe.variant = 0; probe.pad = 0;
+	for (uint32_t c = 0; c < 3; c++)
+	{
+		probe.klass = (uint8_t)c;
+		list_append(wl.counts + c, wl.list[c], active && slot_active(probe, m.k, o), i);
+	}
+}
+
+// gridDim.y = slot index within the launch's slot class; candidates are stored slot-major (cands[slot][block], 64 B records).
+__global__ void __launch_bounds__(128, BU_CAND_MINB) k_candidates(const uint4* __restrict__ blocks, uint32_t n, const block_meta* __restrict__ meta,
+	candidate* __restrict__ cands, const slot_desc* __restrict__ slots, uint32_t first_slot, const uint32_t* __restrict__ list, const uint32_t* __restrict__ count, level_opts o)
+{
+	const uint32_t li = blockIdx.x * blockDim.x + threadIdx.x;
+	if (li >= __ldg(count)) return;
+	const uint32_t i = __ldg(list + li);
 	const uint32_t si = first_slot + blockIdx.y;
 	const slot_desc s = slots[si];
 	const block_meta m = meta[i];
-	candidate* dst = cands + (size_t)si * n + i;
-	if (m.k.solid || !slot_active(s, m.k, o))
-	{
-		reinterpret_cast<uint32_t*>(dst)[0] = 0; // valid = 0
-		return;
-	}
 	uint32_t px[16];
 	load_block(blocks, i, px);
 	candidate c;
 	run_slot(&d_tables, o, s, m.k, m.ranks, px, c);
 	const uint4* src = reinterpret_cast<const uint4*>(&c);
-	uint4* d4 = reinterpret_cast<uint4*>(dst);
+	uint4* d4 = reinterpret_cast<uint4*>(cands + (size_t)si * n + i);
 	d4[0] = src[0]; d4[1] = src[1]; d4[2] = src[2]; d4[3] = src[3];
 }
 
 // One thread per block. (A cooperative 8-lanes-per-block variant was measured in round 1: 33.5 ms vs 23.8 ms for this
 // one -- the stage is issue-bound, not latency-bound, so spreading a block over lanes only adds redundant instructions.)
+// A slot's record exists iff the slot is active for the block's class (same predicate that built the work lists).
 __global__ void __launch_bounds__(128, BU_FIN_MINB) k_finish(const uint4* __restrict__ blocks, uint32_t n, const block_meta* __restrict__ meta,
-	const candidate* __restrict__ cands, uint32_t nslots, uint4* __restrict__ out, level_opts o, int level, uint32_t flags)
+	const candidate* __restrict__ cands, const slot_desc* __restrict__ slots, uint32_t nslots, uint4* __restrict__ out, level_opts o, int level, uint32_t flags)
 {
 	const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
 	if (i >= n) return;
@@ -103,10 +130,10 @@ __global__ void __launch_bounds__(128, BU_FIN_MINB) k_finish(const uint4* __rest
 	uint32_t cnt = 0;
 	for (uint32_t s = 0; s < nslots; s++)
 	{
+		const slot_desc sd = slots[s];
+		if (!slot_active(sd, m.k, o)) continue;
 		const candidate* c = cands + (size_t)s * n + i;
-		const uint32_t head = reinterpret_cast<const uint32_t*>(c)[0];
-		if (!(head >> 24)) continue; // valid byte
-		ue[cnt] = c->uastc_err; be[cnt] = c->bc7_err; modes[cnt] = (uint8_t)(head & 0xFF); idx[cnt] = (uint8_t)s;
+		ue[cnt] = c->uastc_err; be[cnt] = c->bc7_err; modes[cnt] = sd.mode; idx[cnt] = (uint8_t)s;
 		cnt++;
 	}
 	const int best = select_candidate(cnt, ue, be, modes, flags);
@@ -143,20 +170,41 @@ static bool uastc_encode_chunk(b200_context* ctx, const uint4* dBlocks, uint32_t
 	if (!ctx->reserve(ctx->d_slots, ctx->slots_cap, sizeof(slot_desc) * MAX_SLOTS)) return false;
 	B200_CUDA_OK(ctx, cudaMemcpyAsync(ctx->d_slots, slots, sizeof(slot_desc) * nslots, cudaMemcpyHostToDevice, ctx->stream));
 
+	// Slots are listed class by class (build_slots: LA, then RGB, then alpha), so each class is one contiguous slot range.
+	uint32_t class_first[3] = { 0, 0, 0 }, class_count[3] = { 0, 0, 0 };
+	for (uint32_t s = 0; s < nslots; s++)
+	{
+		const uint32_t k = slots[s].klass;
+		if (!class_count[k]) class_first[k] = s;
+		class_count[k]++;
+	}
+
+	if (!ctx->reserve(ctx->d_lists, ctx->lists_cap, sizeof(uint32_t) * (4 + 3 * (size_t)n))) return false;
+	work_lists wl;
+	wl.counts = static_cast<uint32_t*>(ctx->d_lists);
+	for (int k = 0; k < 3; k++) wl.list[k] = wl.counts + 4 + (size_t)k * n;
+	B200_CUDA_OK(ctx, cudaMemsetAsync(wl.counts, 0, sizeof(uint32_t) * 4, ctx->stream));
+
 	const uint32_t tpb = 128, gx = (n + tpb - 1) / tpb;
 	block_meta* meta = static_cast<block_meta*>(ctx->d_meta);
 	candidate* cands = static_cast<candidate*>(ctx->d_cands);
+	const slot_desc* d_slots = static_cast<const slot_desc*>(ctx->d_slots);
 
 	cudaEvent_t* ev = ctx->chunk_events();
 	if (ev) cudaEventRecord(ev[0], ctx->stream);
-	k_classify_rank<<<gx, tpb, 0, ctx->stream>>>(dBlocks, n, meta, dOut, o);
+	k_classify_rank<<<gx, tpb, 0, ctx->stream>>>(dBlocks, n, meta, dOut, wl, o);
 	ctx->launches++; __atomic_add_fetch(&g_b200_total_launches, 1, __ATOMIC_RELAXED);
 	if (ev) cudaEventRecord(ev[1], ctx->stream);
-	// gridDim.y is limited to 65535; nslots <= 176.
-	k_candidates<<<dim3(gx, nslots), tpb, 0, ctx->stream>>>(dBlocks, n, meta, cands, static_cast<const slot_desc*>(ctx->d_slots), 0, o);
-	ctx->launches++; __atomic_add_fetch(&g_b200_total_launches, 1, __ATOMIC_RELAXED);
+	// One launch per slot class over that class's work list. The list length is only known on the device: the grid covers
+	// the worst case (every block in the class) and surplus CTAs retire on their first instruction.
+	for (int k = 0; k < 3; k++)
+	{
+		if (!class_count[k]) continue;
+		k_candidates<<<dim3(gx, class_count[k]), tpb, 0, ctx->stream>>>(dBlocks, n, meta, cands, d_slots, class_first[k], wl.list[k], wl.counts + k, o);
+		ctx->launches++; __atomic_add_fetch(&g_b200_total_launches, 1, __ATOMIC_RELAXED);
+	}
 	if (ev) cudaEventRecord(ev[2], ctx->stream);
-	k_finish<<<gx, tpb, 0, ctx->stream>>>(dBlocks, n, meta, cands, nslots, dOut, o, level, flags);
+	k_finish<<<gx, tpb, 0, ctx->stream>>>(dBlocks, n, meta, cands, d_slots, nslots, dOut, o, level, flags);
 	ctx->launches++; __atomic_add_fetch(&g_b200_total_launches, 1, __ATOMIC_RELAXED);
 	if (ev) cudaEventRecord(ev[3], ctx->stream);
 	B200_CUDA_OK(ctx, cudaGetLastError());

@@ -58,6 +58,7 @@ BU_NI inline void cell_evaluate(const bu_tables* T, const cell_cfg& cfg, const u
 		const uint32_t l02 = (uint32_t)lc[0] | ((uint32_t)lc[2] << 16), h02 = (uint32_t)(lc[0] + dc[0]) | ((uint32_t)(lc[2] + dc[2]) << 16);
 		const uint32_t l13 = cfg.has_alpha ? ((uint32_t)lc[1] | ((uint32_t)lc[3] << 16)) : (uint32_t)lc[1];
 		const uint32_t h13 = cfg.has_alpha ? ((uint32_t)(lc[1] + dc[1]) | ((uint32_t)(lc[3] + dc[3]) << 16)) : (uint32_t)(lc[1] + dc[1]);
+		BU_ROLL
 		for (uint32_t i = 1; i + 1 < N; i++)
 		{
 			const uint32_t w = wt[i];
@@ -71,6 +72,7 @@ BU_NI inline void cell_evaluate(const bu_tables* T, const cell_cfg& cfg, const u
 	if (force_sel)
 	{
 		// caller-imposed selectors (bc7enc.cpp:885-898): only the error is computed
+		BU_ROLL
 		for (uint32_t i = 0; i < n; i++)
 		{
 			const uint32_t s = force_sel[i];
@@ -88,9 +90,7 @@ BU_NI inline void cell_evaluate(const bu_tables* T, const cell_cfg& cfg, const u
 		                   : (float)N / ((float)(dc[0] * dc[0] + dc[1] * dc[1] + dc[2] * dc[2]) + .00000125f);
 		const uint32_t dc01 = pack_s16x2(dc[0], dc[1]), dc23 = pack_s16x2(dc[2], d3);
 		const int K = lc[0] * dc[0] + lc[1] * dc[1] + lc[2] * dc[2] + (a4 ? lc[3] * dc[3] : 0);
-#if defined(BU_EVAL_UNROLL1)
-#pragma unroll 1
-#endif
+		BU_ROLL
 		for (uint32_t i = 0; i < n; i++)
 		{
 			const uint32_t p = px[i];
@@ -110,6 +110,7 @@ BU_NI inline void cell_evaluate(const bu_tables* T, const cell_cfg& cfg, const u
 	{
 		fit.err = total;
 		for (int c = 0; c < 4; c++) { fit.lo[c] = lo[c]; fit.hi[c] = hi[c]; }
+		BU_ROLL
 		for (uint32_t i = 0; i < n; i++) fit.sel[i] = st[i];
 	}
 }
@@ -174,6 +175,7 @@ BU_NI inline void cell_least_squares(const bu_tables* T, const cell_cfg& cfg, co
 	double z00 = 0.0, z10 = 0.0, z11 = 0.0;
 	double q00[4] = { 0, 0, 0, 0 }, t[4] = { 0, 0, 0, 0 };
 
+	BU_ROLL
 	for (uint32_t i = 0; i < n; i++)
 	{
 		const float* w4 = wx + sel[i] * 4;
@@ -207,13 +209,14 @@ BU_NI inline void cell_least_squares(const bu_tables* T, const cell_cfg& cfg, co
 		if (xl[c] < 0.0f || xh[c] > 255.0f)
 		{
 			uint32_t lo_v = 0xFFFFFFFFu, hi_v = 0;
+			BU_ROLL
 			for (uint32_t i = 0; i < n; i++) { lo_v = minu(lo_v, px_c(px[i], c)); hi_v = maxu(hi_v, px_c(px[i], c)); }
 			if (lo_v == hi_v) { xl[c] = (float)lo_v; xh[c] = (float)hi_v; }
 		}
 }
 
 // LS refit + quantise + evaluate; returns false if a zero-error solution was reached (reference returns early then).
-BU_HD inline bool cell_refit(const bu_tables* T, const cell_cfg& cfg, const uint32_t* px, uint32_t n, const uint8_t* sel, cell_fit& fit, const uint8_t* force_sel = nullptr)
+BU_NI inline bool cell_refit(const bu_tables* T, const cell_cfg& cfg, const uint32_t* px, uint32_t n, const uint8_t* sel, cell_fit& fit, const uint8_t* force_sel = nullptr)
 {
 	float xl[4], xh[4];
 	cell_least_squares(T, cfg, px, n, sel, xl, xh);
@@ -250,9 +253,10 @@ BU_NI inline uint64_t cell_one_colour(const bu_tables* T, const cell_cfg& cfg, c
 	// Reference quirks kept: RGB-only range-8/range-7 cells compare with alpha 255, range 13/11 interpolate the alpha slot (unused by the RGB metric).
 	if (cfg.has_alpha) p |= astc_lerp(su[lo[3]], su[hi[3]], w) << 24;
 
-	uint64_t total = 0;
-	if (cfg.has_alpha) for (uint32_t i = 0; i < n; i++) total += dist_rgba(p, px[i]);
-	else for (uint32_t i = 0; i < n; i++) total += dist_rgb(p, px[i]);
+	uint32_t total = 0; // <= 16 * 4 * 255^2
+	const uint32_t cmask = cfg.has_alpha ? 0xFFFFFFFFu : 0x00FFFFFFu;
+	BU_ROLL
+	for (uint32_t i = 0; i < n; i++) total += dist_masked(p, px[i], cmask);
 	return total;
 }
 
@@ -270,38 +274,19 @@ BU_HD inline void cell_finish(const bu_tables* T, const cell_cfg& cfg, const cel
 	const uint8_t* si = T->sorted_idx + cfg.slot * 256;
 	out.err = fit.err;
 	for (int c = 0; c < 4; c++) { out.astc_lo[c] = si[fit.lo[c]]; out.astc_hi[c] = si[fit.hi[c]]; }
+	BU_ROLL
 	for (uint32_t i = 0; i < n; i++) out.sel[i] = fit.sel[i];
 }
 
-// force_sel != nullptr: the selectors are imposed (uastc_rdo endpoint refinement): no single-colour shortcuts, no selector perturbation.
-BU_NI inline void cell_compress(const bu_tables* T, const cell_cfg& cfg, const uint32_t* px, uint32_t n, cell_result& out, const uint8_t* force_sel = nullptr)
+// The general path of cell_compress: PCA start, least-squares passes, selector perturbation, mean-colour fallback.
+// Kept as its own function with a single exit: the caller's solid-colour shortcut is a data-dependent (divergent) branch, and
+// every thread of a warp leaves through the same return.
+BU_NI inline void cell_compress_general(const bu_tables* T, const cell_cfg& cfg, const uint32_t* px, uint32_t n, cell_fit& fit,
+	const uint8_t* one_tab, uint32_t one_sel, uint32_t one_alpha, const uint8_t* force_sel)
 {
-	cell_fit fit;
-	fit.err = UINT64_MAX;
-	for (int c = 0; c < 4; c++) { fit.lo[c] = 0; fit.hi[c] = 0; }
-	for (int i = 0; i < 16; i++) fit.sel[i] = 0;
-
-	uint32_t one_sel = 0, one_alpha = 0;
-	const uint8_t* one_tab = force_sel ? nullptr : cell_one_colour_table(T, cfg, one_sel, one_alpha);
-
-	// All texels equal and a single-colour table exists for this configuration: done (bc7enc.cpp:1379-1411).
-	if (one_tab)
-	{
-		const uint32_t mask = cfg.has_alpha ? 0xFFFFFFFFu : 0x00FFFFFFu;
-		bool solid = true;
-		for (uint32_t i = 1; i < n; i++) if ((px[i] ^ px[0]) & mask) { solid = false; break; }
-		if (solid)
-		{
-			const uint32_t c4[4] = { px_c(px[0], 0), px_c(px[0], 1), px_c(px[0], 2), px_c(px[0], 3) };
-			fit.err = cell_one_colour(T, cfg, one_tab, one_sel, one_alpha, px, n, c4, fit.lo, fit.hi);
-			for (uint32_t i = 0; i < n; i++) fit.sel[i] = (uint8_t)one_sel;
-			cell_finish(T, cfg, fit, n, out);
-			return;
-		}
-	}
-
 	// Mean and principal axis (bc7enc.cpp:1413-1498).
 	float mean[4] = { 0, 0, 0, 0 };
+	BU_ROLL
 	for (uint32_t i = 0; i < n; i++)
 		for (int c = 0; c < 4; c++) mean[c] = mean[c] + (float)px_c(px[i], c);
 
@@ -316,6 +301,7 @@ BU_NI inline void cell_compress(const bu_tables* T, const cell_cfg& cfg, const u
 	if (cfg.has_alpha)
 	{
 		axis[0] = axis[1] = axis[2] = axis[3] = 0.0f;
+		BU_ROLL
 		for (uint32_t i = 0; i < n; i++)
 		{
 			float d[4];
@@ -336,6 +322,7 @@ BU_NI inline void cell_compress(const bu_tables* T, const cell_cfg& cfg, const u
 	else
 	{
 		float cov[6] = { 0, 0, 0, 0, 0, 0 };
+		BU_ROLL
 		for (uint32_t i = 0; i < n; i++)
 		{
 			const float r = (float)px_c(px[i], 0) - mean_s[0], g = (float)px_c(px[i], 1) - mean_s[1], b = (float)px_c(px[i], 2) - mean_s[2];
@@ -370,6 +357,7 @@ BU_NI inline void cell_compress(const bu_tables* T, const cell_cfg& cfg, const u
 	}
 
 	float l = 1e+9f, h = -1e+9f;
+	BU_ROLL
 	for (uint32_t i = 0; i < n; i++)
 	{
 		float q[4];
@@ -403,18 +391,22 @@ BU_NI inline void cell_compress(const bu_tables* T, const cell_cfg& cfg, const u
 		uint8_t base[16] = { 0 }, trial[16] = { 0 };
 		uint32_t min_sel = 256, max_sel = 0;
 		const uint32_t top = (1u << cfg.wbits) - 1;
+		BU_ROLL
 		for (uint32_t i = 0; i < n; i++) { base[i] = fit.sel[i]; min_sel = minu(min_sel, base[i]); max_sel = maxu(max_sel, base[i]); }
 
+		BU_ROLL
 		for (uint32_t i = 0; i < n; i++) { uint32_t s = base[i]; if (s == min_sel && s < top) s++; trial[i] = (uint8_t)s; }
 		go = cell_refit(T, cfg, px, n, trial, fit);
 
 		if (go)
 		{
+			BU_ROLL
 			for (uint32_t i = 0; i < n; i++) { uint32_t s = base[i]; if (s == max_sel && s > 0) s--; trial[i] = (uint8_t)s; }
 			go = cell_refit(T, cfg, px, n, trial, fit);
 		}
 		if (go)
 		{
+			BU_ROLL
 			for (uint32_t i = 0; i < n; i++)
 			{
 				uint32_t s = base[i];
@@ -435,6 +427,7 @@ BU_NI inline void cell_compress(const bu_tables* T, const cell_cfg& cfg, const u
 				for (int hy = max_selector - 1; go && hy <= max_selector + Q; hy++)
 				{
 					if (ly == 0 && hy == max_selector) continue;
+					BU_ROLL
 					for (uint32_t i = 0; i < n; i++)
 						trial[i] = f2u8_x86(clampf_(floorf((float)max_selector * ((float)base[i] - (float)ly) / ((float)hy - (float)ly) + .5f), 0.0f, (float)max_selector));
 					go = cell_refit(T, cfg, px, n, trial, fit);
@@ -454,9 +447,44 @@ BU_NI inline void cell_compress(const bu_tables* T, const cell_cfg& cfg, const u
 		{
 			fit.err = avg_err;
 			for (int c = 0; c < 4; c++) { fit.lo[c] = lo[c]; fit.hi[c] = hi[c]; }
+			BU_ROLL
 			for (uint32_t i = 0; i < n; i++) fit.sel[i] = (uint8_t)one_sel;
 		}
 	}
+
+}
+
+// force_sel != nullptr: the selectors are imposed (uastc_rdo endpoint refinement): no single-colour shortcuts, no selector perturbation.
+BU_NI inline void cell_compress(const bu_tables* T, const cell_cfg& cfg, const uint32_t* px, uint32_t n, cell_result& out, const uint8_t* force_sel = nullptr)
+{
+	cell_fit fit;
+	fit.err = UINT64_MAX;
+	for (int c = 0; c < 4; c++) { fit.lo[c] = 0; fit.hi[c] = 0; }
+	BU_ROLL
+	for (int i = 0; i < 16; i++) fit.sel[i] = 0;
+
+	uint32_t one_sel = 0, one_alpha = 0;
+	const uint8_t* one_tab = force_sel ? nullptr : cell_one_colour_table(T, cfg, one_sel, one_alpha);
+
+	// All texels equal and a single-colour table exists for this configuration: done (bc7enc.cpp:1379-1411).
+	bool solid = false;
+	if (one_tab)
+	{
+		const uint32_t mask = cfg.has_alpha ? 0xFFFFFFFFu : 0x00FFFFFFu;
+		uint32_t differing = 0;
+		BU_ROLL
+		for (uint32_t i = 1; i < n; i++) differing |= (px[i] ^ px[0]) & mask;
+		solid = differing == 0;
+	}
+	if (solid)
+	{
+		const uint32_t c4[4] = { px_c(px[0], 0), px_c(px[0], 1), px_c(px[0], 2), px_c(px[0], 3) };
+		fit.err = cell_one_colour(T, cfg, one_tab, one_sel, one_alpha, px, n, c4, fit.lo, fit.hi);
+		BU_ROLL
+		for (uint32_t i = 0; i < n; i++) fit.sel[i] = (uint8_t)one_sel;
+	}
+	else
+		cell_compress_general(T, cfg, px, n, fit, one_tab, one_sel, one_alpha, force_sel);
 
 	cell_finish(T, cfg, fit, n, out);
 }
@@ -472,52 +500,54 @@ BU_NI inline uint64_t cell_estimate(
 #endif
 const bu_tables* T, uint32_t wbits, uint32_t comps, const uint32_t* px, uint32_t n)
 {
-	const uint32_t N = 1u << wbits;
+	const uint32_t N = 1u << wbits; // wbits is 2 or 3 here
 	const uint8_t* wt = T->weights + wbits * 32;
-	uint32_t lo[4] = { 255, 255, 255, 255 }, hi[4] = { 0, 0, 0, 0 };
-	for (uint32_t i = 0; i < n; i++)
-		for (uint32_t c = 0; c < comps; c++)
-		{
-			const uint32_t v = px_c(px[i], c);
-			if (v < lo[c]) lo[c] = v;
-			if (v > hi[c]) hi[c] = v;
-		}
-	if (comps == 3) { lo[3] = 255; hi[3] = 255; }
+	uint32_t lo4 = 0xFFFFFFFFu, hi4 = 0;
+	BU_ROLL
+	for (uint32_t i = 0; i < n; i++) { lo4 = min_u8x4(lo4, px[i]); hi4 = max_u8x4(hi4, px[i]); }
+	if (comps == 3) { lo4 |= 0xFF000000u; hi4 |= 0xFF000000u; }
+	const uint32_t lo[4] = { px_c(lo4, 0), px_c(lo4, 1), px_c(lo4, 2), px_c(lo4, 3) }, hi[4] = { px_c(hi4, 0), px_c(hi4, 1), px_c(hi4, 2), px_c(hi4, 3) };
 
-	uint32_t wc[32];
-	wc[0] = px_make(lo[0], lo[1], lo[2], lo[3]);
-	wc[N - 1] = px_make(hi[0], hi[1], hi[2], hi[3]);
+	uint32_t wc[8];
+	wc[0] = lo4;
+	wc[N - 1] = hi4;
 	{
 		const uint32_t l02 = lo[0] | (lo[2] << 16), h02 = hi[0] | (hi[2] << 16);
 		const uint32_t l13 = (comps == 4) ? (lo[1] | (lo[3] << 16)) : lo[1], h13 = (comps == 4) ? (hi[1] | (hi[3] << 16)) : hi[1];
 		const uint32_t opaque = (comps == 4) ? 0u : 0xFF000000u;
+		BU_ROLL
 		for (uint32_t i = 1; i + 1 < N; i++)
 			wc[i] = astc_lerp_x2(l02, h02, wt[i]) | (astc_lerp_x2(l13, h13, wt[i]) << 8) | opaque;
 	}
 
-	const int a[4] = { (int)hi[0] - (int)lo[0], (int)hi[1] - (int)lo[1], (int)hi[2] - (int)lo[2], (int)hi[3] - (int)lo[3] };
-	int thresh[31];
+	// Projection axis = bounding-box diagonal; selector thresholds = midpoints of the interpolated colours' projections.
+	// Only 2- and 3-bit weights are ranked (N <= 8); unused thresholds stay at INT_MAX.
+	const uint32_t a01 = pack_s16x2((int)hi[0] - (int)lo[0], (int)hi[1] - (int)lo[1]);
+	const uint32_t a23 = pack_s16x2((int)hi[2] - (int)lo[2], (comps == 4) ? (int)hi[3] - (int)lo[3] : 0);
+	int thresh[7] = { 0x7FFFFFFF, 0x7FFFFFFF, 0x7FFFFFFF, 0x7FFFFFFF, 0x7FFFFFFF, 0x7FFFFFFF, 0x7FFFFFFF };
 	{
 		int prev = 0;
+		BU_ROLL
 		for (uint32_t i = 0; i < N; i++)
 		{
-			int dot = (int)px_c(wc[i], 0) * a[0] + (int)px_c(wc[i], 1) * a[1] + (int)px_c(wc[i], 2) * a[2];
-			if (comps == 4) dot += (int)px_c(wc[i], 3) * a[3];
+			const int dot = dot_s16x4_u8x4(a01, a23, wc[i]);
 			if (i) thresh[i - 1] = (prev + dot + 1) >> 1;
 			prev = dot;
 		}
 	}
 
 	uint64_t total = 0;
+	const uint32_t cmask = (comps == 4) ? 0xFFFFFFFFu : 0x00FFFFFFu;
+	BU_ROLL
 	for (uint32_t i = 0; i < n; i++)
 	{
 		const uint32_t p = px[i];
-		int d = a[0] * (int)px_c(p, 0) + a[1] * (int)px_c(p, 1) + a[2] * (int)px_c(p, 2);
-		if (comps == 4) d += a[3] * (int)px_c(p, 3);
+		const int d = dot_s16x4_u8x4(a01, a23, p);
+		// The reference scans the thresholds from the top for the first one <= d. They are non-decreasing (bounding-box
+		// endpoints: every channel of wc[] is non-decreasing in the weight, and a[] >= 0), so that index is a count.
 		uint32_t s = 0;
-		for (int j = (int)N - 2; j >= 0; j--)
-			if (d >= thresh[j]) { s = (uint32_t)j + 1; break; }
-		total += (comps == 4) ? dist_rgba(wc[s], p) : dist_rgb(wc[s], p);
+		for (uint32_t j = 0; j < 7; j++) s += (d >= thresh[j]) ? 1u : 0u;
+		total += dist_masked(wc[s], p, cmask);
 	}
 	return total;
 }

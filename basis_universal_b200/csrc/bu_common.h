@@ -21,6 +21,28 @@
 #define BU_NI
 #endif
 
+// Small constant tables indexed at run time. A function-local const array would be rebuilt on the thread's stack at every call
+// on the device; these live in device global memory (one copy per translation unit) and as plain statics on the host.
+#if defined(__CUDACC__)
+#define BU_TABLE(type, name, dims, ...) static __device__ const type name##_dev dims = __VA_ARGS__; static const type name##_host dims = __VA_ARGS__;
+#else
+#define BU_TABLE(type, name, dims, ...) static const type name##_host dims = __VA_ARGS__;
+#endif
+#if defined(__CUDA_ARCH__)
+#define BU_TABLE_REF(name) name##_dev
+#else
+#define BU_TABLE_REF(name) name##_host
+#endif
+
+// Loops marked BU_ROLL stay rolled on the device. The encoder kernels are bound by instruction fetch (ncu: "no instruction"
+// is their top stall; hot code must fit the 32 KB L1.5 instruction cache), and these loops index thread-local arrays that
+// already live in local memory, so unrolling buys nothing but code size.
+#if defined(__CUDA_ARCH__) && !defined(BU_NO_ROLL)
+#define BU_ROLL _Pragma("unroll 1")
+#else
+#define BU_ROLL
+#endif
+
 namespace bu {
 
 BU_FI int clampi(int v, int lo, int hi) { return v < lo ? lo : (v > hi ? hi : v); }
@@ -86,7 +108,21 @@ BU_FI int dot_s16x4_u8x4(uint32_t dc01, uint32_t dc23, uint32_t p)
 	asm("dp2a.hi.s32.u32 %0, %1, %2, %3;" : "=r"(r) : "r"(dc23), "r"(p), "r"(r));
 	return r;
 }
+BU_FI uint32_t min_u8x4(uint32_t a, uint32_t b) { return __vminu4(a, b); }
+BU_FI uint32_t max_u8x4(uint32_t a, uint32_t b) { return __vmaxu4(a, b); }
 #else
+BU_FI uint32_t min_u8x4(uint32_t a, uint32_t b)
+{
+	uint32_t r = 0;
+	for (uint32_t c = 0; c < 4; c++) r |= minu(px_c(a, c), px_c(b, c)) << (c * 8);
+	return r;
+}
+BU_FI uint32_t max_u8x4(uint32_t a, uint32_t b)
+{
+	uint32_t r = 0;
+	for (uint32_t c = 0; c < 4; c++) r |= maxu(px_c(a, c), px_c(b, c)) << (c * 8);
+	return r;
+}
 BU_FI uint32_t dist_rgb(uint32_t p, uint32_t q)
 {
 	return sq_diff((int)px_c(p, 0), (int)px_c(q, 0)) + sq_diff((int)px_c(p, 1), (int)px_c(q, 1)) + sq_diff((int)px_c(p, 2), (int)px_c(q, 2));

@@ -43,11 +43,11 @@ BU_FI void bits_write(block_bits& b, uint32_t ofs, uint32_t n, uint64_t v) // ov
 }
 
 // g_uastc_mode_selector_bits (uastc_enc.cpp:3729): first bit and length of each mode's weight field.
+BU_TABLE(uint8_t, selector_field_first, [19], { 65, 69, 73, 89, 89, 68, 66, 89, 0, 97, 65, 66, 81, 94, 92, 62, 98, 61, 49 })
+BU_TABLE(uint8_t, selector_field_total, [19], { 63, 31, 46, 29, 30, 47, 62, 30, 0, 30, 63, 62, 47, 30, 31, 63, 30, 62, 79 })
 BU_FI void mode_selector_field(uint32_t mode, uint32_t& first, uint32_t& total)
 {
-	const uint8_t f[19] = { 65, 69, 73, 89, 89, 68, 66, 89, 0, 97, 65, 66, 81, 94, 92, 62, 98, 61, 49 };
-	const uint8_t t[19] = { 63, 31, 46, 29, 30, 47, 62, 30, 0, 30, 63, 62, 47, 30, 31, 63, 30, 62, 79 };
-	first = f[mode]; total = t[mode];
+	first = BU_TABLE_REF(selector_field_first)[mode]; total = BU_TABLE_REF(selector_field_total)[mode];
 }
 
 // compute_match_cost_estimate (uastc_enc.cpp:3775). The two miniz distance-extra-bits tables it indexes are

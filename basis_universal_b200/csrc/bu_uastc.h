@@ -34,6 +34,7 @@ BU_HD inline block_class classify_block(const uint32_t* px, bool only_use_la_on_
 {
 	block_class k;
 	k.solid = 1; k.has_alpha = 0; k.is_la = 1; k.pad = 0;
+	BU_ROLL
 	for (int i = 0; i < 16; i++)
 	{
 		const uint32_t p = px[i];
@@ -127,10 +128,12 @@ BU_FI uint32_t bc7_part3_to_2(uint32_t p, uint32_t k)
 BU_HD inline uint64_t estimate_pattern_error(const bu_tables* T, const uint8_t* part, uint32_t subsets, uint32_t wbits, uint32_t comps, const uint32_t* px)
 {
 	uint64_t total = 0;
+	BU_ROLL
 	for (uint32_t s = 0; s < subsets; s++)
 	{
 		uint32_t sub[16];
 		uint32_t n = 0;
+		BU_ROLL
 		for (int i = 0; i < 16; i++) if (part[i] == s) sub[n++] = px[i];
 		total += cell_estimate(T, wbits, comps, sub, n);
 	}
@@ -146,6 +149,7 @@ BU_NI inline void rank_partitions(const bu_tables* T, uint32_t kind, uint32_t wb
 	const uint32_t subsets = (kind == 3) ? 3u : 2u;
 	uint64_t err[8];
 	for (uint32_t i = 0; i < want; i++) { err[i] = UINT64_MAX; out[i] = 0; }
+	BU_ROLL
 	for (uint32_t p = 0; p < total; p++)
 	{
 		const uint64_t e = estimate_pattern_error(T, base + p * 16, subsets, wbits, comps, px);
@@ -183,7 +187,9 @@ BU_FI int unq_sum3(const bu_tables* T, uint32_t slot, const uint8_t* ep, int whi
 BU_FI void candidate_clear(candidate& c, uint32_t mode)
 {
 	c.mode = (uint8_t)mode; c.pattern = 0; c.ccs = 0; c.valid = 1; c.pad = 0; c.uastc_err = 0; c.bc7_err = 0;
+	BU_ROLL
 	for (int i = 0; i < 18; i++) c.ep[i] = 0;
+	BU_ROLL
 	for (int i = 0; i < 32; i++) c.w[i] = 0;
 }
 
@@ -196,6 +202,7 @@ BU_NI inline void gen_one_subset(const bu_tables* T, uint32_t mode, const level_
 	const uint32_t top = (1u << cfg.wbits) - 1;
 
 	uint32_t src[16];
+	BU_ROLL
 	for (int i = 0; i < 16; i++) src[i] = la ? px_make(px_c(px[i], 0), 0, 0, px_c(px[i], 3)) : px[i]; // (l,0,0,a): both channels weigh equally
 
 	cell_result r;
@@ -205,6 +212,7 @@ BU_NI inline void gen_one_subset(const bu_tables* T, uint32_t mode, const level_
 	{
 		out.ep[0] = r.astc_lo[0]; out.ep[1] = r.astc_hi[0];
 		out.ep[2] = r.astc_lo[3]; out.ep[3] = r.astc_hi[3];
+		BU_ROLL
 		for (int i = 0; i < 16; i++) out.w[i] = r.sel[i];
 		return;
 	}
@@ -213,6 +221,7 @@ BU_NI inline void gen_one_subset(const bu_tables* T, uint32_t mode, const level_
 	const bool invert = unq_sum3(T, cfg.slot, out.ep, 1) < unq_sum3(T, cfg.slot, out.ep, 0);
 	if (invert)
 		for (int c = 0; c < nc; c++) { const uint8_t t = out.ep[c * 2]; out.ep[c * 2] = out.ep[c * 2 + 1]; out.ep[c * 2 + 1] = t; }
+	BU_ROLL
 	for (int i = 0; i < 16; i++) out.w[i] = (uint8_t)(invert ? top - r.sel[i] : r.sel[i]);
 }
 
@@ -229,10 +238,12 @@ BU_NI inline void gen_multi_subset(const bu_tables* T, uint32_t mode, uint32_t p
 
 	cell_result r[3];
 	uint8_t texel_slot[16];
+	BU_ROLL
 	for (uint32_t s = 0; s < subsets; s++)
 	{
 		uint32_t sub[16];
 		uint32_t n = 0;
+		BU_ROLL
 		for (int i = 0; i < 16; i++)
 			if (part[i] == s)
 			{
@@ -252,6 +263,7 @@ BU_NI inline void gen_multi_subset(const bu_tables* T, uint32_t mode, uint32_t p
 	else if (mode != 7 && T->cp2_invert[pattern]) { fit_of_astc[0] = 1; fit_of_astc[1] = 0; }
 
 	bool invert[3] = { false, false, false };
+	BU_ROLL
 	for (uint32_t a = 0; a < subsets; a++)
 	{
 		const cell_result& q = r[fit_of_astc[a]];
@@ -271,6 +283,7 @@ BU_NI inline void gen_multi_subset(const bu_tables* T, uint32_t mode, uint32_t p
 		}
 	}
 
+	BU_ROLL
 	for (int i = 0; i < 16; i++)
 	{
 		const uint32_t f = part[i];
@@ -289,6 +302,7 @@ BU_NI inline void gen_dual_plane(const bu_tables* T, uint32_t mode, uint32_t rot
 	const uint32_t top = (1u << cfg.wbits) - 1;
 
 	uint32_t p0[16], p1[16];
+	BU_ROLL
 	for (int i = 0; i < 16; i++)
 	{
 		const uint32_t p = px[i];
@@ -338,6 +352,7 @@ BU_NI inline void gen_dual_plane(const bu_tables* T, uint32_t mode, uint32_t rot
 			invert = true;
 		}
 	}
+	BU_ROLL
 	for (int i = 0; i < 16; i++)
 	{
 		out.w[i * 2] = (uint8_t)(invert ? top - r0.sel[i] : r0.sel[i]);
@@ -356,6 +371,7 @@ BU_NI inline void decode_candidate(const bu_tables* T, const candidate& c, uint3
 	const uint8_t* wt = T->weights + wbits * 32;
 
 	uint32_t e0[3], e1[3];
+	BU_ROLL
 	for (uint32_t s = 0; s < subsets; s++)
 	{
 		const uint8_t* e = c.ep + s * comps * 2;
@@ -373,6 +389,7 @@ BU_NI inline void decode_candidate(const bu_tables* T, const candidate& c, uint3
 	}
 
 	const uint8_t* part = (subsets >= 2) ? astc_partition(T, mode, c.pattern) : nullptr;
+	BU_ROLL
 	for (int i = 0; i < 16; i++)
 	{
 		const uint32_t s = part ? part[i] : 0;
@@ -465,6 +482,10 @@ BU_FI uint32_t bc7_dq_p(uint32_t v, uint32_t pbit, uint32_t bits) { const uint32
 BU_FI uint32_t bc7_dq(uint32_t v, uint32_t bits) { v <<= (8 - bits); return v | (v >> bits); }
 BU_FI uint32_t bc7_lerp(uint32_t l, uint32_t h, uint32_t w) { return (l * (64 - w) + h * w + 32) >> 6; }
 
+// BC7 mode 6 / mode 1 weights are 4-bit; UASTC modes with 5- or 3-bit weights map onto them (transcoder.cpp:14600-14650).
+BU_TABLE(uint8_t, bc7_weight5_to_4, [32], { 0, 0, 1, 1, 2, 2, 3, 3, 4, 4, 5, 5, 6, 6, 6, 7, 8, 9, 9, 9, 10, 10, 11, 11, 12, 12, 13, 13, 14, 14, 15, 15 })
+BU_TABLE(uint8_t, bc7_weight3_to_4, [8], { 0, 2, 4, 6, 9, 11, 13, 15 })
+
 BU_NI inline void decode_bc7_transcode(const bu_tables* T, const candidate& c, uint32_t* out)
 {
 	const uint32_t mode = c.mode;
@@ -495,12 +516,13 @@ BU_NI inline void decode_bc7_transcode(const bu_tables* T, const candidate& c, u
 		if (comps == 3) { f.lo[3] = 127; f.hi[3] = 127; }
 		uint32_t l[4], h[4];
 		for (int k = 0; k < 4; k++) { l[k] = ((uint32_t)f.lo[k] << 1) | f.p0; h[k] = ((uint32_t)f.hi[k] << 1) | f.p1; }
+		BU_ROLL
 		for (int i = 0; i < 16; i++)
 		{
 			uint32_t s = c.w[i];
-			if (mode == 18) { const uint8_t t[32] = { 0, 0, 1, 1, 2, 2, 3, 3, 4, 4, 5, 5, 6, 6, 6, 7, 8, 9, 9, 9, 10, 10, 11, 11, 12, 12, 13, 13, 14, 14, 15, 15 }; s = t[s]; }
+			if (mode == 18) s = BU_TABLE_REF(bc7_weight5_to_4)[s];
 			else if (mode == 14) s = s * 5;
-			else if (mode == 5 || mode == 12) { const uint8_t t[8] = { 0, 2, 4, 6, 9, 11, 13, 15 }; s = t[s]; }
+			else if (mode == 5 || mode == 12) s = BU_TABLE_REF(bc7_weight3_to_4)[s];
 			const uint32_t w = T->bc7_weights4[s];
 			out[i] = px_make(bc7_lerp(l[0], h[0], w), bc7_lerp(l[1], h[1], w), bc7_lerp(l[2], h[2], w), bc7_lerp(l[3], h[3], w));
 		}
@@ -512,6 +534,7 @@ BU_NI inline void decode_bc7_transcode(const bu_tables* T, const candidate& c, u
 		const uint32_t subsets = (mode == 1) ? 1u : 2u;
 		uint32_t l[2][3], h[2][3];
 		const bool inv = (mode == 4) && T->cp2_invert[c.pattern];
+		BU_ROLL
 		for (uint32_t s = 0; s < subsets; s++)
 		{
 			float xl[4], xh[4];
@@ -528,6 +551,7 @@ BU_NI inline void decode_bc7_transcode(const bu_tables* T, const candidate& c, u
 			for (int k = 0; k < 3; k++) { l[b][k] = ((uint32_t)f.lo[k] << 1) | f.p0; h[b][k] = ((uint32_t)f.hi[k] << 1) | f.p1; }
 		}
 		const uint8_t* part = (mode == 4) ? T->bc7_part2 + c.pattern * 16 : nullptr;
+		BU_ROLL
 		for (int i = 0; i < 16; i++)
 		{
 			const uint32_t b = part ? part[i] : 0;
@@ -541,6 +565,7 @@ BU_NI inline void decode_bc7_transcode(const bu_tables* T, const candidate& c, u
 		// -> BC7 mode 1: two subsets, 666 endpoints with a shared p-bit, 3-bit indices
 		uint32_t l[2][3], h[2][3];
 		const bool inv = T->cp2_invert[c.pattern] != 0;
+		BU_ROLL
 		for (uint32_t s = 0; s < 2; s++)
 		{
 			float xl[4], xh[4];
@@ -556,6 +581,7 @@ BU_NI inline void decode_bc7_transcode(const bu_tables* T, const candidate& c, u
 			for (int k = 0; k < 3; k++) { l[b][k] = bc7_dq_p(f.lo[k], f.p0, 6); h[b][k] = bc7_dq_p(f.hi[k], f.p0, 6); }
 		}
 		const uint8_t* part = T->bc7_part2 + c.pattern * 16;
+		BU_ROLL
 		for (int i = 0; i < 16; i++)
 		{
 			const uint32_t b = part[i];
@@ -572,6 +598,7 @@ BU_NI inline void decode_bc7_transcode(const bu_tables* T, const candidate& c, u
 		if (mode == 3)
 		{
 			const uint32_t perm = T->cp3_perm[c.pattern];
+			BU_ROLL
 			for (uint32_t s = 0; s < 3; s++)
 			{
 				const uint32_t b = T->astc_to_bc7_perm[perm * 3 + s];
@@ -586,6 +613,7 @@ BU_NI inline void decode_bc7_transcode(const bu_tables* T, const candidate& c, u
 		else
 		{
 			const uint32_t kk = T->cp73_k[c.pattern];
+			BU_ROLL
 			for (uint32_t b = 0; b < 3; b++)
 			{
 				const uint32_t s = bc7_part3_to_2(b, kk);
@@ -597,6 +625,7 @@ BU_NI inline void decode_bc7_transcode(const bu_tables* T, const candidate& c, u
 			}
 			part = T->bc7_part73 + c.pattern * 16;
 		}
+		BU_ROLL
 		for (int i = 0; i < 16; i++)
 		{
 			const uint32_t b = part[i];
@@ -618,6 +647,7 @@ BU_NI inline void decode_bc7_transcode(const bu_tables* T, const candidate& c, u
 		}
 		else
 		{
+			BU_ROLL
 			for (uint32_t a = 0; a < 4; a++)
 			{
 				uint32_t b = a;
@@ -629,6 +659,7 @@ BU_NI inline void decode_bc7_transcode(const bu_tables* T, const candidate& c, u
 			}
 		}
 		for (int k = 0; k < 3; k++) { l[k] = bc7_dq(l[k], 7); h[k] = bc7_dq(h[k], 7); }
+		BU_ROLL
 		for (int i = 0; i < 16; i++)
 		{
 			uint32_t s0 = c.w[i * 2], s1 = c.w[i * 2 + 1];
@@ -645,6 +676,7 @@ BU_NI inline void decode_bc7_transcode(const bu_tables* T, const candidate& c, u
 		// -> BC7 mode 7: two subsets, 5555.1 endpoints with unique p-bits, 2-bit indices
 		uint32_t l[2][4], h[2][4];
 		const bool inv = T->cp2_invert[c.pattern] != 0;
+		BU_ROLL
 		for (uint32_t s = 0; s < 2; s++)
 		{
 			float xl[4], xh[4];
@@ -662,6 +694,7 @@ BU_NI inline void decode_bc7_transcode(const bu_tables* T, const candidate& c, u
 			for (int k = 0; k < 4; k++) { l[b][k] = bc7_dq_p(f.lo[k], f.p0, 5); h[b][k] = bc7_dq_p(f.hi[k], f.p1, 5); }
 		}
 		const uint8_t* part = T->bc7_part2 + c.pattern * 16;
+		BU_ROLL
 		for (int i = 0; i < 16; i++)
 		{
 			const uint32_t b = part[i];
@@ -678,6 +711,7 @@ BU_NI inline void decode_bc7_transcode(const bu_tables* T, const candidate& c, u
 BU_HD inline uint32_t block_error(const uint32_t* src, const uint32_t* dec, block_class k)
 {
 	uint32_t er = 0, eg = 0, eb = 0, ea = 0;
+	BU_ROLL
 	for (int i = 0; i < 16; i++)
 	{
 		er += sq_diff((int)px_c(src[i], 0), (int)px_c(dec[i], 0));
@@ -712,6 +746,7 @@ BU_NI inline int select_candidate(uint32_t n, const uint32_t* uastc_err, const u
 	const uint64_t uastc_w = favor_bc7 ? 0 : 100;
 
 	double best_f = 1e+20f;
+	BU_ROLL
 	for (uint32_t i = 0; i < n; i++)
 	{
 		const uint64_t overall = ((uint64_t)bc7_err[i] * bc7_w) / 100 + ((uint64_t)uastc_err[i] * uastc_w) / 100;
@@ -723,6 +758,7 @@ BU_NI inline int select_candidate(uint32_t n, const uint32_t* uastc_err, const u
 	int best = -1;
 	uint64_t best_err = UINT64_MAX;
 	const bool all = (best_f == 0.0) || favor_bc7;
+	BU_ROLL
 	for (uint32_t i = 0; i < n; i++)
 	{
 		if (!all)

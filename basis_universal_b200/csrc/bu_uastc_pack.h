@@ -23,7 +23,9 @@ BU_NI inline void canonicalize(const bu_tables* T, const candidate& c, uint8_t* 
 	const uint32_t mode = c.mode;
 	const uint32_t subsets = T->mode_subsets[mode], comps = T->mode_comps[mode], planes = T->mode_planes[mode];
 	const uint32_t wbits = T->mode_weight_bits[mode];
+	BU_ROLL
 	for (int i = 0; i < 18; i++) ep[i] = c.ep[i];
+	BU_ROLL
 	for (uint32_t i = 0; i < 16 * planes; i++) w[i] = c.w[i];
 
 	const uint8_t zero16[16] = { 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0 };
@@ -31,11 +33,14 @@ BU_NI inline void canonicalize(const bu_tables* T, const candidate& c, uint8_t* 
 	const uint8_t* part = (subsets >= 2) ? astc_partition(T, mode, c.pattern) : zero16;
 	const uint8_t* anchors = (subsets >= 2) ? astc_anchors(T, mode, c.pattern) : zero3;
 
+	BU_ROLL
 	for (uint32_t plane = 0; plane < planes; plane++)
+		BU_ROLL
 		for (uint32_t s = 0; s < subsets; s++)
 		{
 			const uint32_t anchor = anchors[s];
 			if (!(w[anchor * planes + plane] & (1u << (wbits - 1)))) continue;
+			BU_ROLL
 			for (int i = 0; i < 16; i++)
 				if (part[i] == s) w[i * planes + plane] = (uint8_t)(((1u << wbits) - 1) - w[i * planes + plane]);
 			if (planes == 2)
@@ -78,6 +83,7 @@ BU_NI inline void bc1_decode(const bc1_logical& b, uint32_t* out)
 		c[2] = px_make((r0 + r1) / 2, (g0 + g1) / 2, (b0 + b1) / 2, 255);
 		c[3] = 0;
 	}
+	BU_ROLL
 	for (int i = 0; i < 16; i++) out[i] = c[(b.sel >> (i * 2)) & 3];
 }
 
@@ -94,6 +100,7 @@ BU_NI inline void bc1_find_sels(const uint32_t* px, uint32_t lr, uint32_t lg, ui
 	for (int i = 0; i < 4; i++) dots[i] = (int)br[i] * ar + (int)bg[i] * ag + (int)bb[i] * ab;
 	const int t0 = dots[0] + dots[1], t1 = dots[1] + dots[2], t2 = dots[2] + dots[3];
 	ar *= 2; ag *= 2; ab *= 2;
+	BU_ROLL
 	for (int i = 0; i < 16; i++)
 	{
 		const int d = (int)px_c(px[i], 0) * ar + (int)px_c(px[i], 1) * ag + (int)px_c(px[i], 2) * ab;
@@ -107,6 +114,7 @@ BU_NI inline bool bc1_least_squares(const uint32_t* px, const uint8_t* sels, flo
 	uint32_t uq00[3] = { 0, 0, 0 }, ut[3] = { 0, 0, 0 };
 	const uint32_t wv[4] = { 0x000009, 0x010204, 0x040201, 0x090000 };
 	uint32_t wacc = 0;
+	BU_ROLL
 	for (int i = 0; i < 16; i++)
 	{
 		const uint32_t s = sels[i];
@@ -129,6 +137,7 @@ BU_NI inline bool bc1_least_squares(const uint32_t* px, const uint8_t* sels, flo
 		if (xl[c] < 0.0f || xh[c] > 255.0f)
 		{
 			uint32_t lo_v = 0xFFFFFFFFu, hi_v = 0;
+			BU_ROLL
 			for (int i = 0; i < 16; i++) { lo_v = minu(lo_v, px_c(px[i], c)); hi_v = maxu(hi_v, px_c(px[i], c)); }
 			if (lo_v == hi_v) { xl[c] = (float)lo_v; xh[c] = (float)hi_v; }
 		}
@@ -148,12 +157,14 @@ BU_NI inline void bc1_encode(const bu_tables* T, const uint32_t* px, bool use_se
 	if (use_sels)
 	{
 		const uint8_t tran[4] = { 0, 3, 1, 2 };
+		BU_ROLL
 		for (int i = 0; i < 16; i++) sels[i] = tran[(raw_sels_in >> (i * 2)) & 3];
 	}
 	else
 	{
 		const uint32_t fr = px_c(px[0], 0), fg = px_c(px[0], 1), fb = px_c(px[0], 2);
 		int j;
+		BU_ROLL
 		for (j = 1; j < 16; j++)
 			if (((px[j] ^ px[0]) & 0x00FFFFFFu) != 0) break;
 		if (j == 16)
@@ -174,6 +185,7 @@ BU_NI inline void bc1_encode(const bu_tables* T, const uint32_t* px, bool use_se
 		}
 
 		int total[3] = { (int)fr, (int)fg, (int)fb }, mx[3] = { (int)fr, (int)fg, (int)fb }, mn[3] = { (int)fr, (int)fg, (int)fb };
+		BU_ROLL
 		for (int i = 1; i < 16; i++)
 			for (int c = 0; c < 3; c++)
 			{
@@ -183,6 +195,7 @@ BU_NI inline void bc1_encode(const bu_tables* T, const uint32_t* px, bool use_se
 		for (int c = 0; c < 3; c++) avg[c] = (total[c] + 8) >> 4;
 
 		int icov[6] = { 0, 0, 0, 0, 0, 0 };
+		BU_ROLL
 		for (int i = 0; i < 16; i++)
 		{
 			const int r = (int)px_c(px[i], 0) - avg[0], g = (int)px_c(px[i], 1) - avg[1], b = (int)px_c(px[i], 2) - avg[2];
@@ -207,6 +220,7 @@ BU_NI inline void bc1_encode(const bu_tables* T, const uint32_t* px, bool use_se
 			sr = (int)(xr * m); sg = (int)(xg * m); sb = (int)(xb * m);
 		}
 		int low_dot = 2147483647, high_dot = (-2147483647 - 1), low_c = 0, high_c = 0;
+		BU_ROLL
 		for (int i = 0; i < 16; i++)
 		{
 			const int dot = (int)px_c(px[i], 0) * sr + (int)px_c(px[i], 1) * sg + (int)px_c(px[i], 2) * sb;
@@ -259,6 +273,7 @@ BU_NI inline void bc1_encode(const bu_tables* T, const uint32_t* px, bool use_se
 		if (lc16 < hc16) { const uint32_t t = lc16; lc16 = hc16; hc16 = t; inv = 0x55555555u; }
 		const uint8_t tr[4] = { 0, 2, 3, 1 };
 		uint32_t packed = 0;
+		BU_ROLL
 		for (int i = 0; i < 16; i++) packed |= (uint32_t)tr[sels[i]] << (i * 2);
 		out.c0 = lc16; out.c1 = hc16; out.sel = packed ^ inv;
 	}
@@ -289,6 +304,7 @@ BU_NI inline void compute_bc1_hints(const bu_tables* T, uint32_t mode, const uin
 	{
 		// transcode_uastc_to_bc1_hint1: first-plane weights mapped to BC1 selectors, endpoints by least squares
 		uint32_t sels = 0;
+		BU_ROLL
 		for (int i = 15; i >= 0; --i) sels = (sels << 2) | tran[w[i << plane_shift]];
 		bc1_encode(T, dec, true, sels, b);
 		bc1_decode(b, h1_px);
@@ -322,6 +338,7 @@ BU_NI inline void compute_bc1_hints(const bu_tables* T, uint32_t mode, const uin
 			bool invert = false;
 			if (c0 < c1) { const uint32_t t = c0; c0 = c1; c1 = t; invert = true; }
 			uint32_t sels = 0;
+			BU_ROLL
 			for (int i = 15; i >= 0; --i)
 			{
 				uint32_t s = tran[w[i << plane_shift]];
@@ -335,6 +352,7 @@ BU_NI inline void compute_bc1_hints(const bu_tables* T, uint32_t mode, const uin
 	else for (int i = 0; i < 16; i++) h0_px[i] = 0;
 
 	uint64_t et = 0, e0 = 0, e1 = 0;
+	BU_ROLL
 	for (int i = 0; i < 16; i++) { et += dist_rgb(src[i], t_px[i]); e0 += dist_rgb(src[i], h0_px[i]); e1 += dist_rgb(src[i], h1_px[i]); }
 	const float ft = sqrtf((float)et), f0 = sqrtf((float)e0), f1 = sqrtf((float)e1);
 	if (has0 && f0 <= ft * 1.075f) hint0 = true;
@@ -346,11 +364,13 @@ BU_NI inline void compute_bc1_hints(const bu_tables* T, uint32_t mode, const uin
 BU_NI inline void compute_eac_hint(const bu_tables* T, const uint32_t* dec, uint32_t mul_rad, uint32_t table_mask, uint32_t& out_table, uint32_t& out_mul)
 {
 	uint32_t mn = 255, mx = 0;
+	BU_ROLL
 	for (int i = 0; i < 16; i++) { const uint32_t a = px_c(dec[i], 3); if (a < mn) mn = a; if (a > mx) mx = a; }
 	if (mn == mx) { out_table = 13; out_mul = 1; return; }
 	const uint32_t alpha_range = mx - mn;
 	uint64_t best = UINT64_MAX;
 	out_table = 0; out_mul = 0;
+	BU_ROLL
 	for (uint32_t table = 0; table < 16; table++)
 	{
 		if (!(table_mask & (1u << table))) continue;
@@ -361,9 +381,11 @@ BU_NI inline void compute_eac_hint(const bu_tables* T, const uint32_t* dec, uint
 		const int base = clamp255i(center);
 		const int mul = (int)roundf((float)alpha_range / range);
 		const int mul_low = clampi(mul - (int)mul_rad, 1, 15), mul_high = clampi(mul + (int)mul_rad, 1, 15);
+		BU_ROLL
 		for (int m = mul_low; m <= mul_high; m++)
 		{
 			uint64_t total = 0;
+			BU_ROLL
 			for (int i = 0; i < 16; i++)
 			{
 				const int a = (int)px_c(dec[i], 3);
@@ -397,10 +419,18 @@ BU_FI ycc to_ycc(uint32_t p)
 	return v;
 }
 BU_FI uint64_t sq_u64(int d) { const uint32_t a = (uint32_t)(d < 0 ? -d : d); return (uint64_t)a * (uint64_t)a; } // one IMAD.WIDE.U32
+// uastc_enc.cpp:2645 color_diff: 4*dy^2 + dcr^2 + dcb^2 in 64 bits (|d| < 2^18, so each square needs up to 35 bits).
+// Device form: (2 dy)^2 + dcr^2 + dcb^2 as three chained signed 32x32->64 multiply-adds.
 BU_FI uint64_t ycc_diff(const ycc& a, const ycc& b)
 {
-	// uastc_enc.cpp:2645 color_diff: 4*dy^2 + dcr^2 + dcb^2 in 64 bits (|d| < 2^18, so each square needs up to 35 bits)
+#if defined(__CUDA_ARCH__)
+	const int dy2 = (a.y - b.y) * 2, dcr = a.cr - b.cr, dcb = a.cb - b.cb;
+	uint64_t r;
+	asm("{\n\t.reg .s64 t;\n\tmul.wide.s32 t, %1, %1;\n\tmad.wide.s32 t, %2, %2, t;\n\tmad.wide.s32 t, %3, %3, t;\n\tmov.b64 %0, t;\n\t}" : "=l"(r) : "r"(dy2), "r"(dcr), "r"(dcb));
+	return r;
+#else
 	return sq_u64(a.y - b.y) * 4 + sq_u64(a.cr - b.cr) + sq_u64(a.cb - b.cb);
+#endif
 }
 
 BU_FI int gray_distance2(uint32_t p, int r, int g, int b)
@@ -424,6 +454,7 @@ BU_NI inline bool etc1_estimate_flipped(const uint32_t* px)
 		upper[c] = (s00 + s10 + 4) / 8; lower[c] = (s01 + s11 + 4) / 8; left[c] = (s00 + s01 + 4) / 8; right[c] = (s10 + s11 + 4) / 8;
 	}
 	int ud = 0, ld = 0, lfd = 0, rd = 0;
+	BU_ROLL
 	for (int i = 0; i < 4; i++)
 		for (int j = 0; j < 2; j++)
 		{
@@ -436,33 +467,27 @@ BU_NI inline bool etc1_estimate_flipped(const uint32_t* px)
 }
 
 // transcoder.cpp:16547
+// The reference's per-bias switch (channel / subblock -> delta in {-2..1}), tabulated: [bias][subblock][channel].
+BU_TABLE(int8_t, etc1_bias_deltas, [32][2][3], {
+		{ { -1, -1, -1 }, { -1, -1, -1 } }, { {  0, -1, -1 }, {  0, -1, -1 } }, { { -1,  0,  0 }, {  0,  0,  0 } }, { { -1,  0, -1 }, { -1,  0, -1 } },
+		{ {  0,  0, -1 }, {  0,  0, -1 } }, { {  0, -1,  0 }, {  0,  0,  0 } }, { {  0,  0, -1 }, {  0,  0,  0 } }, { {  1,  0,  0 }, {  0,  0,  0 } },
+		{ {  0,  0,  0 }, {  0,  0,  1 } }, { { -1, -1,  0 }, { -1, -1,  0 } }, { { -2, -2, -2 }, { -2, -2, -2 } }, { {  0,  1,  0 }, {  0,  0,  0 } },
+		{ { -1,  0,  0 }, { -1,  0,  0 } }, { {  0,  0,  0 }, {  0,  0,  0 } }, { {  1,  0,  0 }, {  1,  0,  0 } }, { {  0,  0,  1 }, {  0,  0,  0 } },
+		{ {  0,  1,  0 }, {  0,  1,  0 } }, { {  1,  1,  0 }, {  1,  1,  0 } }, { {  0,  0,  0 }, { -1,  0,  0 } }, { {  0,  0,  0 }, {  0, -1,  0 } },
+		{ {  0,  0,  0 }, {  0,  0, -1 } }, { {  0,  0,  0 }, {  1,  0,  0 } }, { {  0,  0,  1 }, {  0,  0,  1 } }, { {  1,  0,  1 }, {  1,  0,  1 } },
+		{ {  0,  0,  0 }, {  0,  1,  0 } }, { {  0,  1,  1 }, {  0,  1,  1 } }, { {  1,  1,  1 }, {  1,  1,  1 } }, { { -1, -1, -1 }, {  0,  0,  0 } },
+		{ {  1,  1,  1 }, { -1, -1, -1 } }, { {  0,  0,  0 }, {  1,  1,  1 } }, { {  0,  0,  0 }, { -1, -1, -1 } }, { {  1,  1,  1 }, {  0,  0,  0 } } })
+BU_FI int etc1_bias_delta(uint32_t bias, uint32_t subblock, uint32_t c) { return BU_TABLE_REF(etc1_bias_deltas)[bias][subblock][c]; }
+
+// Order in which the bias values are tried at levels 0-3 (uastc_enc.cpp:2730).
+BU_TABLE(uint8_t, etc1_sorted_bias, [32], { 13, 0, 22, 29, 27, 12, 26, 9, 30, 31, 8, 10, 25, 2, 23, 5, 15, 7, 3, 11, 6, 17, 28, 18, 1, 19, 20, 21, 24, 4, 14, 16 })
+
+// transcoder.cpp:16547
 BU_HD inline void etc1_apply_bias(const int* in, uint32_t bias, int limit, uint32_t subblock, int* out)
 {
-	for (int c = 0; c < 3; c++)
+	for (uint32_t c = 0; c < 3; c++)
 	{
-		int delta;
-		switch (bias)
-		{
-		case 2: delta = subblock ? 0 : ((c == 0) ? -1 : 0); break;
-		case 5: delta = subblock ? 0 : ((c == 1) ? -1 : 0); break;
-		case 6: delta = subblock ? 0 : ((c == 2) ? -1 : 0); break;
-		case 7: delta = subblock ? 0 : ((c == 0) ? 1 : 0); break;
-		case 11: delta = subblock ? 0 : ((c == 1) ? 1 : 0); break;
-		case 15: delta = subblock ? 0 : ((c == 2) ? 1 : 0); break;
-		case 18: delta = subblock ? ((c == 0) ? -1 : 0) : 0; break;
-		case 19: delta = subblock ? ((c == 1) ? -1 : 0) : 0; break;
-		case 20: delta = subblock ? ((c == 2) ? -1 : 0) : 0; break;
-		case 21: delta = subblock ? ((c == 0) ? 1 : 0) : 0; break;
-		case 24: delta = subblock ? ((c == 1) ? 1 : 0) : 0; break;
-		case 8: delta = subblock ? ((c == 2) ? 1 : 0) : 0; break;
-		case 10: delta = -2; break;
-		case 27: delta = subblock ? 0 : -1; break;
-		case 28: delta = subblock ? -1 : 1; break;
-		case 29: delta = subblock ? 1 : 0; break;
-		case 30: delta = subblock ? -1 : 0; break;
-		case 31: delta = subblock ? 0 : 1; break;
-		default: { const int divs[3] = { 1, 3, 9 }; delta = (int)((bias / (uint32_t)divs[c]) % 3) - 1; break; }
-		}
+		const int delta = etc1_bias_delta(bias, subblock, c);
 		int v = in[c];
 		if (v == 0) { if (delta == -2) v += 3; else v += delta + 1; }
 		else if (v == limit) v += (delta - 1);
@@ -525,6 +550,11 @@ BU_HD inline etc1_search_opts etc1_search_setup(const bu_tables* T, uint32_t mod
 // the base's: the four candidates for a texel differ in the luma term only and
 //     color_diff = 4 (dy + 256 m)^2 + dcr^2 + dcb^2
 // is the same integer expression the reference evaluates, factored. A clamping table (base + m outside 0..255) takes the general form.
+// Texel of subset s, slot j (g_etc1_pixel_coords, etc.cpp:314): subsets are row pairs when flipped, else column pairs.
+BU_FI uint32_t etc1_subset_texel(uint32_t flip, uint32_t s, uint32_t j) { return flip ? (s * 8 + j) : (s * 2 + (j >> 2) + (j & 3) * 4); }
+
+// The loops below are deliberately kept rolled where the trip count is data dependent or the body is large: the stage is
+// bound by instruction fetch (ncu: "no instruction" is the top stall), so hot code has to stay within the 32 KB L1.5 I-cache.
 BU_NI inline void etc1_subset_search(const bu_tables* T, const etc1_search_opts& o, uint32_t flip, uint32_t s, uint32_t base_key, const int* mn, const int* mx,
 	const ycc* src_y, const ycc* dec_y, uint32_t& inten_out, uint64_t& err_out)
 {
@@ -542,16 +572,16 @@ BU_NI inline void etc1_subset_search(const bu_tables* T, const etc1_search_opts&
 	// The four modifiers of a table are (-a, -b, b, a), so min_k (dy + 256 m_k)^2 = (min(||dy| - 256 a|, ||dy| - 256 b|))^2.
 	int ady[8];
 	uint64_t chroma_sum = 0;
-	for (int j = 0; j < 8; j++)
+	for (uint32_t j = 0; j < 8; j++)
 	{
-		const int x = flip ? (j & 3) : (int)(s * 2 + (j >> 2)), y = flip ? (int)(s * 2 + (j >> 2)) : (j & 3);
-		const ycc& q = dec_y[x + y * 4];
+		const ycc& q = dec_y[etc1_subset_texel(flip, s, j)];
 		ady[j] = iabsi(base_y.y - q.y);
 		chroma_sum += sq_u64(base_y.cr - q.cr) + sq_u64(base_y.cb - q.cb);
 	}
 
 	uint32_t inten = 0;
 	uint64_t best_sub = UINT64_MAX;
+BU_ROLL
 	for (uint32_t t = 0; t < limit; t++)
 	{
 		const int mb = 256 * (int)T->etc1_inten[t * 4 + 2], ma = 256 * (int)T->etc1_inten[t * 4 + 3]; // small / large positive modifier
@@ -573,10 +603,10 @@ BU_NI inline void etc1_subset_search(const bu_tables* T, const etc1_search_opts&
 				const int m = T->etc1_inten[t * 4 + k];
 				tab[k] = to_ycc(px_make(clamp255i(base[0] + m), clamp255i(base[1] + m), clamp255i(base[2] + m), 255));
 			}
-			for (int j = 0; j < 8; j++)
+BU_ROLL
+			for (uint32_t j = 0; j < 8; j++)
 			{
-				const int x = flip ? (j & 3) : (int)(s * 2 + (j >> 2)), y = flip ? (int)(s * 2 + (j >> 2)) : (j & 3);
-				const ycc& q = dec_y[x + y * 4];
+				const ycc q = dec_y[etc1_subset_texel(flip, s, j)];
 				total += minu64(minu64(ycc_diff(tab[0], q), ycc_diff(tab[1], q)), minu64(ycc_diff(tab[2], q), ycc_diff(tab[3], q)));
 			}
 		}
@@ -596,24 +626,26 @@ BU_NI inline void etc1_subset_search(const bu_tables* T, const etc1_search_opts&
 		tab[k] = to_ycc(px_make(clamp255i(base[0] + m), clamp255i(base[1] + m), clamp255i(base[2] + m), 255));
 	}
 	uint64_t err = 0;
-	for (int j = 0; j < 8; j++)
+BU_ROLL
+	for (uint32_t j = 0; j < 8; j++)
 	{
-		const int x = flip ? (j & 3) : (int)(s * 2 + (j >> 2)), y = flip ? (int)(s * 2 + (j >> 2)) : (j & 3);
-		const int i = x + y * 4;
+		const uint32_t i = etc1_subset_texel(flip, s, j);
+		const ycc q = dec_y[i];
 		uint32_t bi = 0;
 		if (!clamped)
 		{
 			// chroma terms are equal for the four candidates: the arg-min is decided by |luma difference| alone
-			const int dy = base_y.y - dec_y[i].y;
+			const int dy = base_y.y - q.y;
 			int be = iabsi(dy + 256 * (int)T->etc1_inten[inten * 4]);
 			for (uint32_t k = 1; k < 4; k++) { const int e = iabsi(dy + 256 * (int)T->etc1_inten[inten * 4 + k]); if (e < be) { be = e; bi = k; } }
 		}
 		else
 		{
-			uint64_t be = ycc_diff(tab[0], dec_y[i]);
-			for (uint32_t k = 1; k < 4; k++) { const uint64_t e = ycc_diff(tab[k], dec_y[i]); if (e < be) { be = e; bi = k; } }
+			uint64_t be = ycc_diff(tab[0], q);
+			for (uint32_t k = 1; k < 4; k++) { const uint64_t e = ycc_diff(tab[k], q); if (e < be) { be = e; bi = k; } }
 		}
-		err += ycc_diff(src_y[i], tab[bi]);
+		const ycc chosen = (bi == 0) ? tab[0] : (bi == 1) ? tab[1] : (bi == 2) ? tab[2] : tab[3];
+		err += ycc_diff(src_y[i], chosen);
 	}
 	inten_out = inten;
 	err_out = err;
@@ -630,12 +662,12 @@ BU_NI inline void etc1_subset_search(const bu_tables* T, const etc1_search_opts&
 BU_NI inline void etc1_hint_trials(const bu_tables* T, const etc1_search_opts& o, uint32_t flip, uint32_t individ, uint32_t first, uint32_t stride,
 	const ycc* src_y, const ycc* dec_y, const uint32_t* dec, etc1_hint& best)
 {
-	const uint8_t sorted_bias[32] = { 13, 0, 22, 29, 27, 12, 26, 9, 30, 31, 8, 10, 25, 2, 23, 5, 15, 7, 3, 11, 6, 17, 28, 18, 1, 19, 20, 21, 24, 4, 14, 16 };
 	const int mul = individ ? 15 : 31;
 
 	// subset = row pair when flipped, else column pair (g_etc1_pixel_coords, etc.cpp:314)
 	int unbiased[2][3];
 	int mn[2][3], mx[2][3];
+	BU_ROLL
 	for (int s = 0; s < 2; s++)
 	{
 		uint32_t sum[3] = { 0, 0, 0 };
@@ -658,9 +690,10 @@ BU_NI inline void etc1_hint_trials(const bu_tables* T, const etc1_search_opts& o
 	uint32_t keys[2][32], n_keys[2] = { 0, 0 };
 	uint8_t trial_key[2][32];
 	uint32_t n_trials = 0;
+	BU_ROLL
 	for (uint32_t bias_iter = first; bias_iter < o.last_bias; bias_iter += stride, n_trials++)
 	{
-		const uint32_t bias = o.sorted_bias_table ? sorted_bias[bias_iter] : bias_iter;
+		const uint32_t bias = o.sorted_bias_table ? BU_TABLE_REF(etc1_sorted_bias)[bias_iter] : bias_iter;
 
 		int col[2][3];
 		for (int s = 0; s < 2; s++)
@@ -700,6 +733,7 @@ BU_NI inline void etc1_hint_trials(const bu_tables* T, const etc1_search_opts& o
 	uint8_t key_inten[2][32];
 	uint64_t key_err[2][32];
 	for (int s = 0; s < 2; s++)
+		BU_ROLL
 		for (uint32_t k = 0; k < n_keys[s]; k++)
 		{
 			uint32_t t; uint64_t e;
@@ -709,6 +743,7 @@ BU_NI inline void etc1_hint_trials(const bu_tables* T, const etc1_search_opts& o
 
 	// (3) trials in the reference's order, first strictly smaller error wins
 	uint32_t bias_iter = first;
+	BU_ROLL
 	for (uint32_t i = 0; i < n_trials; i++, bias_iter += stride)
 	{
 		const uint32_t k0 = trial_key[0][i], k1 = trial_key[1][i];
@@ -719,7 +754,7 @@ BU_NI inline void etc1_hint_trials(const bu_tables* T, const etc1_search_opts& o
 			best.order = (flip * 2 + individ) * 32 + bias_iter;
 			best.flip = (uint8_t)flip; best.diff = (uint8_t)(individ ? 0 : 1);
 			best.inten0 = key_inten[0][k0]; best.inten1 = key_inten[1][k1];
-			best.bias = (uint8_t)(o.sorted_bias_table ? sorted_bias[bias_iter] : bias_iter);
+			best.bias = (uint8_t)(o.sorted_bias_table ? BU_TABLE_REF(etc1_sorted_bias)[bias_iter] : bias_iter);
 		}
 	}
 }
@@ -821,6 +856,7 @@ BU_NI inline void pack_block(const bu_tables* T, const candidate& c, const uint8
 	{
 		const uint32_t radix = ep_trits ? 3u : 5u, full = ep_trits ? 243u : 125u;
 		uint32_t accum = 0, mulv = 1;
+		BU_ROLL
 		for (uint32_t i = 0; i < total_values; i++)
 		{
 			accum += (uint32_t)(ep[i] >> ep_bits) * mulv;
@@ -835,6 +871,7 @@ BU_NI inline void pack_block(const bu_tables* T, const candidate& c, const uint8
 			bw_put(b, accum, nb);
 		}
 	}
+	BU_ROLL
 	for (uint32_t i = 0; i < total_values; i++) bw_put(b, ep[i] & ((1u << ep_bits) - 1), ep_bits);
 
 	// weights, anchors one bit short
@@ -842,6 +879,7 @@ BU_NI inline void pack_block(const bu_tables* T, const candidate& c, const uint8
 	const uint8_t zero3[3] = { 0, 0, 0 };
 	const uint8_t* anchors = (subsets >= 2) ? astc_anchors(T, mode, c.pattern) : zero3;
 	const uint32_t plane_shift = planes - 1;
+	BU_ROLL
 	for (uint32_t i = 0; i < 16 * planes; i++)
 	{
 		uint32_t nb = wbits;

@@ -36,15 +36,24 @@ def main():
         L.b200_last_kernel_ms.restype = ctypes.c_float
         L.b200_last_kernel_ms.argtypes = [vp]
         L.b200_destroy_context.argtypes = [vp]
+        L.b200_last_error.restype = ctypes.c_char_p
+        L.b200_last_error.argtypes = [vp]
         ctx = L.b200_create_context(0)
+        if not ctx:
+            print(f"{os.path.basename(path):40s} create_context failed: {L.b200_last_error(None)}", flush=True)
+            continue
         best = None
         for r in range(args.reps):
             out.zero_()
             torch.cuda.synchronize()
-            assert L.b200_uastc_encode_blocks_device(ctx, blocks.data_ptr(), n, out.data_ptr(), args.level)
+            if not L.b200_uastc_encode_blocks_device(ctx, blocks.data_ptr(), n, out.data_ptr(), args.level):
+                print(f"{os.path.basename(path):40s} encode failed: {L.b200_last_error(ctx)}", flush=True)
+                break
             t = [L.b200_last_stage_ms(ctx, i) for i in range(3)] + [L.b200_last_kernel_ms(ctx)]
             if best is None or t[3] < best[3]:
                 best = t
+        if best is None:
+            continue
         h = hashlib.md5(out.cpu().numpy().tobytes()).hexdigest()[:12]
         print(f"{os.path.basename(path):40s} classify {best[0]:7.2f}  candidates {best[1]:7.2f}  finish {best[2]:7.2f}  total {best[3]:7.2f} ms  md5 {h}", flush=True)
         L.b200_destroy_context(ctx)
