@@ -117,6 +117,10 @@ def cpu_sample_blocks(blocks, cores):
     return blocks[:n], f"first {n} of {blocks.shape[0]} blocks ({n * 16 / 1e6:.2f} Mtexel) of the synthetic 4096^2 image, seed 1234"
 
 
+# dram__bytes_read.sum + dram__bytes_write.sum of the k_candidates launches of one step (ncu --set full, profiles/r1_v4_ncu_full_raw.csv)
+NCU_DRAM_BYTES_PER_STEP = int((1.296592 + 3.885061 + 1.809447 + 5.176113) * 1e9)
+
+
 def config_dict(world):
     return {"workload": "synthetic 4096x4096 RGBA8 (SURVEY 9.6 generator, seed 1234+rank), UASTC LDR 4x4 level 2, no RDO",
             "blocks_per_step_per_gpu": BLOCKS, "texels_per_step_per_gpu": TEXELS,
@@ -233,8 +237,10 @@ def run_gpu(args, rank, local_rank, world):
                 "gpu_launches": launches,
                 "stage_ms_per_step": {"classify_rank": stage[0] / args.steps, "candidates": k1_ms, "finish": stage[2] / args.steps},
                 "roofline": {"bound": "hbm", "kernel": "k_candidates", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                             "traffic": None, "peak_source": peak_kind,
-                             "note": "algorithmic 80 B/block (SURVEY 8d); kernel is ALU/latency-bound, see DESIGN.md section 5"},
+                             "traffic": NCU_DRAM_BYTES_PER_STEP, "peak_source": peak_kind,
+                             "note": "k_candidates = the three work-list launches of one step, timed together with CUDA events; algorithmic "
+                                     "80 B/block (SURVEY 8d); traffic = ncu dram read+write of those launches (profiles/r1_v4_summary.md), "
+                                     "mostly local-memory write-back; the stage is instruction-issue bound, see DESIGN.md section 4"},
                 "cpu_baseline": {"value": sample.shape[0] * 16 / 1e6 / cpu_t, "unit": "Mtexel/s", "cores": cores, "kind": "reference", "sample": desc},
                 "bit_exact_vs_reference_on_cpu_sample": parity}
         print(json.dumps(line), flush=True)

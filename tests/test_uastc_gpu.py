@@ -75,3 +75,36 @@ def test_full_size_properties_4096(enc, ref):
     assert dec.shape == (4096, 64)
     # checksum of the whole output, pinned by the first bit-exact GPU run (full reference run of this image, 2026-09-22)
     assert int(a.astype(np.uint64).sum()) > 0
+
+
+def _class_inputs():
+    """Inputs that leave one or two of the three slot-class work lists empty, or fill them unevenly."""
+    base = util.image_to_blocks(util.synth(128, 77)).reshape(-1, 16, 4).copy()    # 1024 blocks
+    opaque = base.copy(); opaque[:, :, 3] = 255
+    alpha = base.copy(); alpha[:, :, 3] = (base[:, :, 0] // 2 + 17)
+    gray = base.copy(); gray[:, :, 1] = gray[:, :, 0]; gray[:, :, 2] = gray[:, :, 0]; gray[:, :, 3] = 255
+    gray_alpha = gray.copy(); gray_alpha[:, :, 3] = base[:, :, 1]
+    solid = np.repeat(base[:, :1, :], 16, axis=1)
+    rng = np.random.default_rng(3)
+    mixed = np.concatenate([opaque[:300], alpha[:300], gray[:100], gray_alpha[:100], solid[:100]])
+    mixed = mixed[rng.permutation(mixed.shape[0])]                                 # classes interleaved lane by lane
+    return {"opaque": opaque, "alpha": alpha, "gray": gray, "gray_alpha": gray_alpha, "solid": solid, "mixed": mixed}
+
+
+@pytest.mark.parametrize("kind", ["opaque", "alpha", "gray", "gray_alpha", "solid", "mixed"])
+@pytest.mark.parametrize("level", [1, 2, 4])
+def test_slot_class_work_lists(enc, ref, kind, level):
+    blocks = _class_inputs()[kind].reshape(-1, 64)
+    if level == 4:
+        blocks = blocks[:160]      # level 4 runs 170 slots per block on the CPU oracle
+    assert np.array_equal(enc.encode_uastc(blocks, level), ref.encode_uastc(blocks, level, threads=os.cpu_count()))
+
+
+def test_multi_chunk_level4(enc):
+    """Level 4 processes 2^18 blocks per pass: an input just over one chunk must equal the same blocks encoded separately."""
+    tile = util.image_to_blocks(util.synth(64, 5))                                 # 256 distinct blocks
+    n = (1 << 18) + 300
+    blocks = np.resize(tile, (n, 64))
+    out = enc.encode_uastc(blocks, 4)
+    small = enc.encode_uastc(tile, 4)
+    assert np.array_equal(out, np.resize(small, (n, 16)))
