@@ -1,0 +1,192 @@
+// b200_image.cu -- the steps either side of the per-block encode, so that a raster
+// image can go in and a quality figure can come out without a host pass over the texels:
+//   k_extract_blocks   raster RGBA8 -> 64 B pixel_blocks, edge texels clamped (basis_compressor::extract_source_blocks,
+//                      encoder/basisu_comp.cpp:3207 -> image::extract_block_clamped, encoder/basisu_enc.h:3168)
+//   k_unpack_uastc     16 B UASTC blocks -> 64 B RGBA blocks (basist::unpack_uastc(blk, pPixels, srgb = false),
+//                      transcoder/basisu_transcoder.cpp:15886)
+//   k_block_metrics    |a - b| histograms of two block arrays over the texels inside the image: the integer part of
+//                      image_metrics::calc (encoder/basisu_enc.cpp:2155); the host finishes with the reference's double arithmetic
+// All three are HBM-bound streaming kernels (80 / 80 / 128 B per block).
+#include "b200_internal.h"
+#include "bu_rdo.h"
+
+using namespace bu;
+
+#include "b200_tables.cuh"
+
+// One thread per block; interior blocks of 16-byte-aligned rasters take four 128-bit loads.
+__global__ void __launch_bounds__(256) k_extract_blocks(const uint8_t* __restrict__ img, uint32_t width, uint32_t height, size_t pitch, uint32_t nbx, uint32_t nby, uint4* __restrict__ blocks)
+{
+	const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= nbx * nby) return;
+	const uint32_t bx = i % nbx, by = i / nbx;
+	uint4* dst = blocks + (size_t)i * 4;
+	const bool interior = (bx * 4 + 4 <= width) && (by * 4 + 4 <= height);
+	if (interior && ((pitch | (size_t)img) & 15) == 0)
+	{
+#pragma unroll
+		for (uint32_t y = 0; y < 4; y++)
+			dst[y] = __ldg(reinterpret_cast<const uint4*>(img + (size_t)(by * 4 + y) * pitch) + bx);
+		return;
+	}
+	for (uint32_t y = 0; y < 4; y++)
+	{
+		const uint32_t sy = min(by * 4 + y, height - 1);
+		uint32_t p[4];
+		for (uint32_t x = 0; x < 4; x++)
+		{
+			const uint32_t sx = min(bx * 4 + x, width - 1);
+			p[x] = __ldg(reinterpret_cast<const uint32_t*>(img + (size_t)sy * pitch) + sx);
+		}
+		dst[y] = make_uint4(p[0], p[1], p[2], p[3]);
+	}
+}
+
+__global__ void __launch_bounds__(128) k_unpack_uastc(const uint4* __restrict__ ublocks, uint32_t n, uint4* __restrict__ out, int* failed)
+{
+	const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= n) return;
+	const uint4 v = __ldg(ublocks + i);
+	block_bits b; b.lo = v.x | ((uint64_t)v.y << 32); b.hi = v.z | ((uint64_t)v.w << 32);
+	uint32_t px[16];
+	if (!unpack_block_texels(&d_tables, b, px)) *failed = 1;
+	uint4* dst = out + (size_t)i * 4;
+#pragma unroll
+	for (int r = 0; r < 4; r++) dst[r] = make_uint4(px[r * 4], px[r * 4 + 1], px[r * 4 + 2], px[r * 4 + 3]);
+}
+
+// hist[6][256]: R, G, B, A, 709 luma, 601 luma; sums[8]: per-channel sums of a then of b (image_metrics::m_sum_a / m_sum_b).
+// CTA-private histograms in shared memory, flushed with one atomic per non-empty bin.
+__global__ void __launch_bounds__(256) k_block_metrics(const uint4* __restrict__ a, const uint4* __restrict__ b, uint32_t nbx, uint32_t nby, uint32_t width, uint32_t height,
+	unsigned long long* __restrict__ hist, unsigned long long* __restrict__ sums)
+{
+	__shared__ uint32_t sh[6 * 256];
+	__shared__ unsigned long long ssum[8];
+	for (uint32_t k = threadIdx.x; k < 6 * 256; k += blockDim.x) sh[k] = 0;
+	if (threadIdx.x < 8) ssum[threadIdx.x] = 0;
+	__syncthreads();
+	uint32_t local_sum[8] = { 0, 0, 0, 0, 0, 0, 0, 0 };
+	const uint32_t total_rows = nbx * nby * 4; // one thread per block row (4 texels)
+	for (uint32_t r = blockIdx.x * blockDim.x + threadIdx.x; r < total_rows; r += gridDim.x * blockDim.x)
+	{
+		const uint32_t blk = r >> 2, y = r & 3, bx = blk % nbx, by = blk / nbx;
+		if (by * 4 + y >= height) continue;
+		const uint4 va = __ldg(a + r), vb = __ldg(b + r);
+		const uint32_t pa[4] = { va.x, va.y, va.z, va.w }, pb[4] = { vb.x, vb.y, vb.z, vb.w };
+		for (uint32_t x = 0; x < 4; x++)
+		{
+			if (bx * 4 + x >= width) break;
+			const uint32_t d = __vabsdiffu4(pa[x], pb[x]);
+			for (uint32_t c = 0; c < 4; c++)
+			{
+				atomicAdd(&sh[c * 256 + px_c(d, c)], 1u);
+				local_sum[c] += px_c(pa[x], c); local_sum[4 + c] += px_c(pb[x], c);
+			}
+			// color_rgba::get_709_luma / get_601_luma (enc.h:1051-1052)
+			const int la709 = (int)((13938u * px_c(pa[x], 0) + 46869u * px_c(pa[x], 1) + 4729u * px_c(pa[x], 2) + 32768u) >> 16);
+			const int lb709 = (int)((13938u * px_c(pb[x], 0) + 46869u * px_c(pb[x], 1) + 4729u * px_c(pb[x], 2) + 32768u) >> 16);
+			const int la601 = (int)((19595u * px_c(pa[x], 0) + 38470u * px_c(pa[x], 1) + 7471u * px_c(pa[x], 2) + 32768u) >> 16);
+			const int lb601 = (int)((19595u * px_c(pb[x], 0) + 38470u * px_c(pb[x], 1) + 7471u * px_c(pb[x], 2) + 32768u) >> 16);
+			atomicAdd(&sh[4 * 256 + (uint32_t)iabsi(la709 - lb709)], 1u);
+			atomicAdd(&sh[5 * 256 + (uint32_t)iabsi(la601 - lb601)], 1u);
+		}
+	}
+	for (int c = 0; c < 8; c++) if (local_sum[c]) atomicAdd(&ssum[c], (unsigned long long)local_sum[c]);
+	__syncthreads();
+	for (uint32_t k = threadIdx.x; k < 6 * 256; k += blockDim.x) if (sh[k]) atomicAdd(hist + k, (unsigned long long)sh[k]);
+	if (threadIdx.x < 8 && ssum[threadIdx.x]) atomicAdd(sums + threadIdx.x, ssum[threadIdx.x]);
+}
+
+// ---- C ABI ------------------------------------------------------------------------------------------------------------------
+
+static bool timed_begin(b200_context* ctx) { ctx->launches = 0; return cudaEventRecord(ctx->ev0, ctx->stream) == cudaSuccess; }
+static bool timed_end(b200_context* ctx)
+{
+	if (cudaEventRecord(ctx->ev1, ctx->stream) != cudaSuccess) return false;
+	if (cudaStreamSynchronize(ctx->stream) != cudaSuccess) return false;
+	return cudaEventElapsedTime(&ctx->last_ms, ctx->ev0, ctx->ev1) == cudaSuccess;
+}
+static void count_launch(b200_context* ctx) { ctx->launches++; __atomic_add_fetch(&g_b200_total_launches, 1, __ATOMIC_RELAXED); }
+
+extern "C" int b200_extract_source_blocks_device(b200_context* ctx, const void* dRGBA, uint32_t width, uint32_t height, size_t pitch_bytes, void* dBlocks)
+{
+	if (!ctx || !ctx->activate()) return 0;
+	if (!width || !height) { ctx->last_ms = 0; return 1; }
+	if (pitch_bytes < (size_t)width * 4 || (pitch_bytes & 3)) { ctx->fail("b200_extract_source_blocks: pitch must be a multiple of 4 and >= width * 4"); return 0; }
+	const uint32_t nbx = (width + 3) / 4, nby = (height + 3) / 4;
+	if (!timed_begin(ctx)) return 0;
+	k_extract_blocks<<<(nbx * nby + 255) / 256, 256, 0, ctx->stream>>>(static_cast<const uint8_t*>(dRGBA), width, height, pitch_bytes, nbx, nby, static_cast<uint4*>(dBlocks));
+	count_launch(ctx);
+	B200_CUDA_OK(ctx, cudaGetLastError());
+	if (!timed_end(ctx)) { ctx->fail("b200_extract_source_blocks: kernel failed"); return 0; }
+	return 1;
+}
+
+extern "C" int b200_extract_source_blocks(b200_context* ctx, const void* pRGBA, uint32_t width, uint32_t height, size_t pitch_bytes, void* pBlocks)
+{
+	if (!ctx || !ctx->activate()) return 0;
+	if (!width || !height) { ctx->last_ms = 0; return 1; }
+	if (!pRGBA || !pBlocks) { ctx->fail("b200_extract_source_blocks: null buffer"); return 0; }
+	const uint32_t nbx = (width + 3) / 4, nby = (height + 3) / 4;
+	const size_t in_bytes = pitch_bytes * height, out_bytes = (size_t)nbx * nby * 64;
+	if (!ctx->reserve(ctx->d_aux[0], ctx->aux_cap[0], in_bytes)) return 0;
+	if (!ctx->reserve(ctx->d_in, ctx->in_cap, out_bytes)) return 0;
+	B200_CUDA_OK(ctx, cudaMemcpyAsync(ctx->d_aux[0], pRGBA, in_bytes, cudaMemcpyHostToDevice, ctx->stream));
+	if (!b200_extract_source_blocks_device(ctx, ctx->d_aux[0], width, height, pitch_bytes, ctx->d_in)) return 0;
+	B200_CUDA_OK(ctx, cudaMemcpy(pBlocks, ctx->d_in, out_bytes, cudaMemcpyDeviceToHost));
+	return 1;
+}
+
+extern "C" int b200_uastc_unpack_blocks_device(b200_context* ctx, const void* dUastc, uint32_t num_blocks, void* dRGBA_blocks)
+{
+	if (!ctx || !ctx->activate()) return 0;
+	if (!num_blocks) { ctx->last_ms = 0; return 1; }
+	if (!ctx->reserve(ctx->d_aux[5], ctx->aux_cap[5], 256)) return 0;
+	int* d_failed = static_cast<int*>(ctx->d_aux[5]);
+	B200_CUDA_OK(ctx, cudaMemsetAsync(d_failed, 0, sizeof(int), ctx->stream));
+	if (!timed_begin(ctx)) return 0;
+	k_unpack_uastc<<<(num_blocks + 127) / 128, 128, 0, ctx->stream>>>(static_cast<const uint4*>(dUastc), num_blocks, static_cast<uint4*>(dRGBA_blocks), d_failed);
+	count_launch(ctx);
+	B200_CUDA_OK(ctx, cudaGetLastError());
+	if (!timed_end(ctx)) { ctx->fail("b200_uastc_unpack_blocks: kernel failed"); return 0; }
+	int h_failed = 0;
+	B200_CUDA_OK(ctx, cudaMemcpy(&h_failed, d_failed, sizeof(int), cudaMemcpyDeviceToHost));
+	if (h_failed) { ctx->fail("b200_uastc_unpack_blocks: invalid UASTC block (unpack_uastc returned false)"); return 0; }
+	return 1;
+}
+
+extern "C" int b200_uastc_unpack_blocks(b200_context* ctx, const void* pUastc, uint32_t num_blocks, void* pRGBA_blocks)
+{
+	if (!ctx || !ctx->activate()) return 0;
+	if (!num_blocks) { ctx->last_ms = 0; return 1; }
+	if (!pUastc || !pRGBA_blocks) { ctx->fail("b200_uastc_unpack_blocks: null buffer"); return 0; }
+	if (!ctx->reserve(ctx->d_out, ctx->out_cap, (size_t)num_blocks * 16)) return 0;
+	if (!ctx->reserve(ctx->d_in, ctx->in_cap, (size_t)num_blocks * 64)) return 0;
+	B200_CUDA_OK(ctx, cudaMemcpyAsync(ctx->d_out, pUastc, (size_t)num_blocks * 16, cudaMemcpyHostToDevice, ctx->stream));
+	if (!b200_uastc_unpack_blocks_device(ctx, ctx->d_out, num_blocks, ctx->d_in)) return 0;
+	B200_CUDA_OK(ctx, cudaMemcpy(pRGBA_blocks, ctx->d_in, (size_t)num_blocks * 64, cudaMemcpyDeviceToHost));
+	return 1;
+}
+
+extern "C" int b200_block_metrics_device(b200_context* ctx, const void* dBlocksA, const void* dBlocksB, uint32_t width, uint32_t height, b200_block_metrics* pOut)
+{
+	if (!ctx || !ctx->activate()) return 0;
+	if (!pOut) { ctx->fail("b200_block_metrics: null output"); return 0; }
+	memset(pOut, 0, sizeof(*pOut));
+	if (!width || !height) { ctx->last_ms = 0; return 1; }
+	const uint32_t nbx = (width + 3) / 4, nby = (height + 3) / 4;
+	const size_t bytes = sizeof(unsigned long long) * (6 * 256 + 8);
+	if (!ctx->reserve(ctx->d_aux[5], ctx->aux_cap[5], bytes)) return 0;
+	unsigned long long* d = static_cast<unsigned long long*>(ctx->d_aux[5]);
+	B200_CUDA_OK(ctx, cudaMemsetAsync(d, 0, bytes, ctx->stream));
+	if (!timed_begin(ctx)) return 0;
+	const uint32_t rows = nbx * nby * 4;
+	uint32_t grid = (rows + 255) / 256;
+	if (grid > 148 * 8) grid = 148 * 8; // grid-stride: one CTA-private histogram flush per resident CTA
+	k_block_metrics<<<grid, 256, 0, ctx->stream>>>(static_cast<const uint4*>(dBlocksA), static_cast<const uint4*>(dBlocksB), nbx, nby, width, height, d, d + 6 * 256);
+	count_launch(ctx);
+	B200_CUDA_OK(ctx, cudaGetLastError());
+	if (!timed_end(ctx)) { ctx->fail("b200_block_metrics: kernel failed"); return 0; }
+	B200_CUDA_OK(ctx, cudaMemcpy(pOut, d, bytes, cudaMemcpyDeviceToHost));
+	return 1;
+}

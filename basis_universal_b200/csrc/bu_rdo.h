@@ -136,6 +136,22 @@ BU_NI inline bool unpack_block_bits(const bu_tables* T, const block_bits& b, can
 	return true;
 }
 
+// basist::unpack_uastc(blk, pPixels, srgb = false) (transcoder.cpp:15886): a packed block to its 16 texels.
+BU_HD inline bool unpack_block_texels(const bu_tables* T, const block_bits& b, uint32_t* px)
+{
+	candidate c;
+	if (!unpack_block_bits(T, b, c)) { for (int k = 0; k < 16; k++) px[k] = 0; return false; }
+	if (c.mode == 8)
+	{
+		// solid colour: the R, G, B, A bytes follow the mode code (pack_uastc, uastc_enc.cpp:110; transcoder.cpp:15316)
+		const uint32_t colour = (uint32_t)bits_read(b, T->mode_huff[8 * 2 + 1], 32);
+		for (int k = 0; k < 16; k++) px[k] = colour;
+		return true;
+	}
+	decode_candidate(T, c, px);
+	return true;
+}
+
 // Weights of `c`'s mode parsed from a 128-bit block whose weight field has been spliced in (the trial of uastc_enc.cpp:3959-3971).
 BU_FI void read_weight_field(const bu_tables* T, const candidate& c, const block_bits& b, uint8_t* w)
 {

@@ -1,0 +1,90 @@
+"""Host-side mirror of the steps either side of the per-block path (include/basisu_b200.h, "either side" section):
+raster -> pixel_blocks (basis_compressor::extract_source_blocks), UASTC blocks -> texels (basist::unpack_uastc), and the
+reference's image_metrics::calc from device-built histograms. No CPU fallback: every call goes through libbasisu_b200.so."""
+import ctypes
+
+import numpy as np
+
+from ._lib import B200Error, lib
+
+
+class _BlockMetrics(ctypes.Structure):
+    _fields_ = [("hist", (ctypes.c_uint64 * 256) * 6), ("sum_a", ctypes.c_uint64 * 4), ("sum_b", ctypes.c_uint64 * 4)]
+
+
+def _p(a):
+    return a.ctypes.data_as(ctypes.c_void_p)
+
+
+class ImageOps:
+    def __init__(self, device=0):
+        self._lib = lib()
+        self._ctx = self._lib.b200_create_context(int(device))
+        if not self._ctx:
+            raise B200Error(f"b200_create_context({device}) failed: {self._lib.b200_last_error(None).decode()}")
+
+    def close(self):
+        if self._ctx:
+            self._lib.b200_destroy_context(self._ctx)
+            self._ctx = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, ok, what):
+        if not ok:
+            raise B200Error(f"{what} failed: {self._lib.b200_last_error(self._ctx).decode()}")
+
+    @property
+    def last_kernel_ms(self):
+        return float(self._lib.b200_last_kernel_ms(self._ctx))
+
+    def extract_source_blocks(self, img):
+        """(H, W, 4) uint8 (rows may be strided) -> (ceil(H/4) * ceil(W/4), 64) uint8 pixel_blocks, edges clamped."""
+        if img.ndim != 3 or img.shape[2] != 4 or img.dtype != np.uint8 or img.strides[2] != 1 or img.strides[1] != 4:
+            img = np.ascontiguousarray(img, np.uint8)
+        h, w = img.shape[:2]
+        out = np.empty((((h + 3) // 4) * ((w + 3) // 4), 64), np.uint8)
+        self._check(self._lib.b200_extract_source_blocks(self._ctx, _p(img), w, h, ctypes.c_size_t(img.strides[0] if h else 0), _p(out)), "b200_extract_source_blocks")
+        return out
+
+    def unpack_uastc(self, ublocks):
+        """(N, 16) uint8 UASTC blocks -> (N, 64) uint8 RGBA texels, [y][x] within the block."""
+        u = np.ascontiguousarray(ublocks, np.uint8).reshape(-1, 16)
+        out = np.empty((u.shape[0], 64), np.uint8)
+        self._check(self._lib.b200_uastc_unpack_blocks(self._ctx, _p(u), u.shape[0], _p(out)), "b200_uastc_unpack_blocks")
+        return out
+
+    def block_metrics_device(self, d_blocks_a, d_blocks_b, width, height):
+        """Device pointers to two block arrays of a width x height image -> (hist (6, 256) uint64, sum_a (4,), sum_b (4,))."""
+        m = _BlockMetrics()
+        ok = self._lib.b200_block_metrics_device(self._ctx, ctypes.c_void_p(d_blocks_a), ctypes.c_void_p(d_blocks_b), int(width), int(height), ctypes.byref(m))
+        self._check(ok, "b200_block_metrics_device")
+        return np.ctypeslib.as_array(m.hist).astype(np.uint64).reshape(6, 256), np.ctypeslib.as_array(m.sum_a).copy(), np.ctypeslib.as_array(m.sum_b).copy()
+
+
+def metrics_from_histograms(hist, width, height, first_chan=0, total_chans=0, avg_comp_error=True, use_601_luma=False):
+    """The floating-point tail of image_metrics::calc (encoder/basisu_enc.cpp:2205-2224), operation for operation:
+    returns dict(max, mean, mean_squared, rms, psnr). total_chans == 0 selects the luma histogram."""
+    if total_chans:
+        h = hist[first_chan:first_chan + total_chans].sum(0)
+    else:
+        h = hist[5 if use_601_luma else 4]
+    m_max, s, s2 = 0.0, 0.0, 0.0
+    for i in range(256):
+        if h[i]:
+            m_max = max(m_max, float(i))
+            v = float(i) * float(h[i])
+            s += v
+            s2 += float(i) * v
+    total_values = float(width) * float(height)
+    if avg_comp_error:
+        total_values *= float(min(max(total_chans, 1), 4))
+    mean = float(np.float32(min(max(s / total_values, 0.0), 255.0)))
+    mean_squared = float(np.float32(min(max(s2 / total_values, 0.0), 255.0 * 255.0)))
+    rms = float(np.float32(np.sqrt(mean_squared)))
+    psnr = float(np.float32(min(max(np.log10(255.0 / rms) * 20.0, 0.0), 100.0))) if rms else 100.0
+    return {"max": m_max, "mean": mean, "mean_squared": mean_squared, "rms": rms, "psnr": psnr}

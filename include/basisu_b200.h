@@ -118,6 +118,31 @@ int b200_etc1s_determine_selectors(b200_context* ctx, const void* pInput_etc_col
 int b200_etc1s_endpoint_histogram(b200_context* ctx, const void* pEtc_blocks, uint32_t num_blocks, uint32_t* pHist);
 int b200_etc1s_endpoint_histogram_device(b200_context* ctx, const void* dEtc_blocks, uint32_t num_blocks, uint32_t* dHist);
 
+/* ---- either side of the per-block path: ingest, decode, quality metric ---------------------------------------------------- */
+
+/* Raster RGBA8 image -> array of 64 B pixel_blocks in raster block order, edge texels clamped: one slice of
+ * basis_compressor::extract_source_blocks (encoder/basisu_comp.cpp:3207; image::extract_block_clamped,
+ * encoder/basisu_enc.h:3168). pitch_bytes is the distance between rows. Writes ((width+3)/4) * ((height+3)/4) blocks. */
+int b200_extract_source_blocks(b200_context* ctx, const void* pRGBA, uint32_t width, uint32_t height, size_t pitch_bytes, void* pBlocks);
+int b200_extract_source_blocks_device(b200_context* ctx, const void* dRGBA, uint32_t width, uint32_t height, size_t pitch_bytes, void* dBlocks);
+
+/* Decode UASTC LDR 4x4 blocks to 16 RGBA8 texels each (64 B, [y][x] order):
+ * bool basist::unpack_uastc(const uastc_block&, color32* pPixels, bool srgb = false) (transcoder/basisu_transcoder.cpp:15886).
+ * Returns 0 if any block is invalid (the reference returns false for that block). */
+int b200_uastc_unpack_blocks(b200_context* ctx, const void* pUastc_blocks, uint32_t num_blocks, void* pRGBA_blocks);
+int b200_uastc_unpack_blocks_device(b200_context* ctx, const void* dUastc_blocks, uint32_t num_blocks, void* dRGBA_blocks);
+
+/* The integer part of image_metrics::calc(const image& a, const image& b, ...) (encoder/basisu_enc.cpp:2155) for two images
+ * held as block arrays of a width x height image: histograms of |a - b| per channel and of the 709 / 601 luma difference over
+ * the texels inside the image (padding texels of edge blocks are not counted), plus the channel sums. The caller finishes
+ * with the reference's double arithmetic (basis_universal_b200/image.py::metrics_from_histograms restates it). */
+typedef struct b200_block_metrics
+{
+	uint64_t hist[6][256]; /* R, G, B, A, 709 luma, 601 luma */
+	uint64_t sum_a[4], sum_b[4];
+} b200_block_metrics;
+int b200_block_metrics_device(b200_context* ctx, const void* dBlocksA, const void* dBlocksB, uint32_t width, uint32_t height, b200_block_metrics* pOut);
+
 /* ---- instrumentation ------------------------------------------------------------------------------------------------- */
 
 /* Device time in milliseconds of the kernels of the last successful encode call on this context (CUDA events on the

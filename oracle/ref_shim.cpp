@@ -288,3 +288,25 @@ REF_API uint64_t ref_etc1s_encode_cluster(const uint8_t* pPixels, uint32_t n, ui
 	out4[0] = r.m_block_color_unscaled.r; out4[1] = r.m_block_color_unscaled.g; out4[2] = r.m_block_color_unscaled.b; out4[3] = (uint8_t)r.m_block_inten_table;
 	return r.m_error;
 }
+
+// ---- the steps either side of the per-block path -----------------------------------------------
+
+// basis_compressor::extract_source_blocks for one slice (comp.cpp:3207): image::extract_block_clamped per 4x4 block.
+REF_API void ref_extract_source_blocks(const uint8_t* pRGBA, uint32_t w, uint32_t h, uint8_t* pBlocks)
+{
+	image img(pRGBA, w, h, 4);
+	const uint32_t nbx = (w + 3) / 4, nby = (h + 3) / 4;
+	for (uint32_t by = 0; by < nby; by++)
+		for (uint32_t bx = 0; bx < nbx; bx++)
+			img.extract_block_clamped(reinterpret_cast<color_rgba*>(pBlocks + ((size_t)by * nbx + bx) * 64), bx * 4, by * 4, 4, 4);
+}
+
+// image_metrics::calc (enc.cpp:2155) on two RGBA images; out = { max, mean, mean_squared, rms, psnr }.
+REF_API void ref_image_metrics(const uint8_t* pA, const uint8_t* pB, uint32_t w, uint32_t h, uint32_t first_chan, uint32_t total_chans,
+	uint32_t avg_comp_error, uint32_t use_601_luma, double* out5)
+{
+	image a(pA, w, h, 4), b(pB, w, h, 4);
+	image_metrics im;
+	im.calc(a, b, first_chan, total_chans, avg_comp_error != 0, use_601_luma != 0);
+	out5[0] = im.m_max; out5[1] = im.m_mean; out5[2] = im.m_mean_squared; out5[3] = im.m_rms; out5[4] = im.m_psnr;
+}

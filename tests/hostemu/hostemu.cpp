@@ -238,3 +238,18 @@ EMU_API int emu_uastc_rdo(uint32_t n, uint8_t* blocks, const uint8_t* pixels, co
 	}
 	return 1;
 }
+
+// ---- decode (b200_uastc_unpack_blocks) -----------------------------------------------------------------------------------
+EMU_API int emu_uastc_unpack_blocks(const uint8_t* pUastc, uint32_t n, uint8_t* pOut64)
+{
+	int ok = 1;
+	for (uint32_t i = 0; i < n; i++)
+	{
+		block_bits b;
+		memcpy(&b.lo, pUastc + (size_t)i * 16, 8); memcpy(&b.hi, pUastc + (size_t)i * 16 + 8, 8);
+		uint32_t px[16];
+		if (!unpack_block_texels(&g_tables, b, px)) ok = 0;
+		memcpy(pOut64 + (size_t)i * 64, px, 64);
+	}
+	return ok;
+}

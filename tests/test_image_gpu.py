@@ -1,0 +1,112 @@
+"""GPU parity for the steps either side of the block path, through the C ABI: ingest == basis_compressor::extract_source_blocks,
+decode == basist::unpack_uastc, metrics == image_metrics::calc; plus the raster -> blocks -> UASTC -> texels -> PSNR chain
+at 4096^2 checked through size-independent properties."""
+import numpy as np
+import pytest
+
+import util
+from basis_universal_b200 import image, uastc
+from test_image_cpu import np_histograms, ref_extract, ref_metrics
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def ops():
+    o = image.ImageOps(0)
+    yield o
+    o.close()
+
+
+@pytest.fixture(scope="module")
+def ref():
+    return util.Ref()
+
+
+@pytest.mark.parametrize("shape", [(8, 8), (5, 7), (1, 1), (13, 4), (64, 37), (255, 257), (512, 768)])
+def test_extract_matches_reference(ops, ref, shape):
+    h, w = shape
+    img = np.ascontiguousarray(util.synth(max(h, w) + 3, 3)[:h, :w])
+    assert np.array_equal(ops.extract_source_blocks(img), ref_extract(ref, img))
+
+
+def test_extract_strided_rows(ops, ref):
+    big = util.synth(128, 9)
+    view = big[5:5 + 50, 8:8 + 41]          # pitch != width * 4, base not 16-byte aligned
+    assert np.array_equal(ops.extract_source_blocks(view), ref_extract(ref, np.ascontiguousarray(view)))
+
+
+def test_extract_empty(ops):
+    assert ops.extract_source_blocks(np.zeros((0, 0, 4), np.uint8)).shape == (0, 64)
+
+
+@pytest.mark.parametrize("level", [0, 1, 2, 3])
+def test_unpack_matches_reference_transcoder(ops, ref, level):
+    blocks = np.concatenate([util.edge_case_blocks(5), util.image_to_blocks(util.synth(128, 40 + level))])
+    u = ref.encode_uastc(blocks, level)
+    assert np.array_equal(ops.unpack_uastc(u), ref.unpack_uastc(u))
+
+
+def test_unpack_rejects_invalid_block(ops, ref):
+    """Blocks the reference's unpack_uastc refuses (reserved mode code / out-of-range pattern) must fail the call."""
+    import ctypes
+    rng = np.random.default_rng(4)
+    cand = rng.integers(0, 256, (4096, 16), dtype=np.uint8)
+    out = np.zeros((1, 64), np.uint8)
+    bad = [b for b in cand if not ref.lib.ref_unpack_uastc_blocks(util._ptr(np.ascontiguousarray(b)), ctypes.c_uint32(1), util._ptr(out))]
+    assert bad, "no invalid block among 4096 random ones?"
+    good = ref.encode_uastc(util.image_to_blocks(util.synth(16, 1)), 2)
+    with pytest.raises(Exception):
+        ops.unpack_uastc(np.concatenate([good, np.stack(bad[:3])]))
+    assert ops.unpack_uastc(good).shape == (16, 64)      # the context stays usable
+
+
+@pytest.mark.parametrize("shape", [(96, 96), (50, 41), (4, 4), (1, 3)])
+def test_metrics_match_image_metrics_calc(ops, ref, shape):
+    import torch
+    h, w = shape
+    a = np.ascontiguousarray(util.synth(128, 11)[:h, :w])
+    b = np.clip(a.astype(np.int32) + np.random.default_rng(2).integers(-9, 10, a.shape), 0, 255).astype(np.uint8)
+    da = torch.from_numpy(ops.extract_source_blocks(a)).cuda()
+    db = torch.from_numpy(ops.extract_source_blocks(b)).cuda()
+    torch.cuda.synchronize()
+    hist, sum_a, sum_b = ops.block_metrics_device(da.data_ptr(), db.data_ptr(), w, h)
+    assert np.array_equal(hist, np_histograms(a, b))
+    assert [int(v) for v in sum_a] == [int(a[..., c].sum()) for c in range(4)] and [int(v) for v in sum_b] == [int(b[..., c].sum()) for c in range(4)]
+    for first, total, use601 in [(0, 3, False), (0, 4, False), (3, 1, False), (0, 0, False), (0, 0, True)]:
+        assert image.metrics_from_histograms(hist, w, h, first, total, True, use601) == ref_metrics(ref, a, b, first, total, True, use601)
+
+
+def test_full_chain_4096(ops, ref):
+    """raster -> blocks -> UASTC -> texels -> PSNR, all on the device side of the ABI at BASELINE's 4096^2 size:
+    ingest equals the numpy tiling, every texel of the decode equals the reference decode on a sample, and the PSNR figures
+    equal image_metrics::calc run by the reference on the full 16.7 Mtexel pair."""
+    import torch
+    img = util.synth(4096, 1234)
+    blocks = ops.extract_source_blocks(img)
+    assert np.array_equal(blocks, util.image_to_blocks(img))
+    enc = uastc.Encoder(0)
+    u = enc.encode_uastc(blocks, 2)
+    enc.close()
+    dec = ops.unpack_uastc(u)
+    idx = np.random.default_rng(1).choice(u.shape[0], 4096, replace=False)
+    assert np.array_equal(dec[idx], ref.unpack_uastc(u[idx]))
+    da, db = torch.from_numpy(blocks).cuda(), torch.from_numpy(dec).cuda()
+    torch.cuda.synchronize()
+    hist, _, _ = ops.block_metrics_device(da.data_ptr(), db.data_ptr(), 4096, 4096)
+    assert int(hist[0].sum()) == 4096 * 4096
+    dec_img = dec.reshape(1024, 1024, 4, 4, 4).transpose(0, 2, 1, 3, 4).reshape(4096, 4096, 4)
+    for first, total in [(0, 3), (0, 4), (0, 0)]:
+        assert image.metrics_from_histograms(hist, 4096, 4096, first, total) == ref_metrics(ref, img, np.ascontiguousarray(dec_img), first, total)
+    assert 25.0 < image.metrics_from_histograms(hist, 4096, 4096, 0, 3)["psnr"] < 60.0
+
+
+def test_unpack_random_valid_bit_patterns(ops, ref):
+    """Arbitrary 128-bit patterns that the reference accepts decode to the same texels (anchor handling, BISE corner cases)."""
+    import ctypes
+    cand = np.random.default_rng(9).integers(0, 256, (8192, 16), dtype=np.uint8)
+    out = np.zeros((1, 64), np.uint8)
+    valid = np.array([bool(ref.lib.ref_unpack_uastc_blocks(util._ptr(np.ascontiguousarray(b)), ctypes.c_uint32(1), util._ptr(out))) for b in cand])
+    u = np.ascontiguousarray(cand[valid])
+    assert u.shape[0] > 1000
+    assert np.array_equal(ops.unpack_uastc(u), ref.unpack_uastc(u))
