@@ -253,6 +253,43 @@ __global__ void __launch_bounds__(256) k_etc1s_endpoint_histogram(const uint2* _
 	atomicAdd(hist + key, 2u); // two subblocks per block, weight 1 each
 }
 
+// ---- selector training set (second multi-GPU exchange point) ----------------------------------------------------------------
+// Per block: the 16 selectors as a 32-bit key (texel x + 4y at bits 2(x + 4y)) and the weight generate_selector_clusters gives
+// the block's training vector (frontend.cpp:2156-2179): colour distance between the low and high block colours of the
+// sub-block with the larger intensity table, / 300, clamped to 1..4096. Identical keys are merged by the clusterer
+// (enc.h:2228-2260), so ranks exchange (key, summed weight) pairs.
+__global__ void __launch_bounds__(256) k_etc1s_selector_training(const uint2* __restrict__ etc_blocks, uint32_t n, int perceptual, uint32_t* __restrict__ keys, uint32_t* __restrict__ weights)
+{
+	const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= n) return;
+	const uint2 w = __ldg(&etc_blocks[i]);
+	const uint32_t b0 = w.x & 255, b1 = (w.x >> 8) & 255, b2 = (w.x >> 16) & 255, b3 = w.x >> 24;
+	const uint32_t msb = ((w.y & 255) << 8) | ((w.y >> 8) & 255), lsb = (((w.y >> 16) & 255) << 8) | (w.y >> 24);
+	uint32_t key = 0;
+	for (uint32_t y = 0; y < 4; y++)
+		for (uint32_t x = 0; x < 4; x++)
+		{
+			const uint32_t bit = x * 4 + y;
+			const uint32_t raw = (((msb >> bit) & 1) << 1) | ((lsb >> bit) & 1);
+			const uint32_t sel = (0x1Eu >> (raw * 2)) & 3u; // g_etc1_to_selector_index = { 2, 3, 1, 0 }
+			key |= sel << ((x + y * 4) * 2);
+		}
+	const uint32_t inten0 = b3 >> 5, inten1 = (b3 >> 2) & 7;
+	const uint32_t sub = (inten0 > inten1) ? 0u : 1u;
+	int c5[3] = { (int)(b0 >> 3), (int)(b1 >> 3), (int)(b2 >> 3) };
+	if (sub)
+	{
+		// differential mode: second sub-block = base5 + signed 3-bit delta (always 0 for ETC1S blocks), clamped as unpack_color5 does
+		const uint32_t d3[3] = { b0 & 7, b1 & 7, b2 & 7 };
+		for (int c = 0; c < 3; c++) c5[c] = clampi(c5[c] + (int)(d3[c] >= 4 ? d3[c] - 8 : d3[c]), 0, 31);
+	}
+	uint32_t colors[4];
+	etc1s_block_colors(&d_tables, (uint32_t)c5[0], (uint32_t)c5[1], (uint32_t)c5[2], sub ? inten1 : inten0, colors);
+	const uint32_t dist = etc_color_distance(perceptual != 0, colors[0], colors[3]);
+	keys[i] = key;
+	weights[i] = min(max(dist / 300u, 1u), 4096u);
+}
+
 // ---- C ABI ------------------------------------------------------------------------------------------------------------------
 
 #define ETC_CHECK_BLOCKS(ctx, name) do { if (!(ctx)) return 0; if (!(ctx)->activate()) return 0; \
@@ -405,5 +442,35 @@ extern "C" int b200_etc1s_endpoint_histogram(b200_context* ctx, const void* pEtc
 	B200_CUDA_OK(ctx, cudaStreamSynchronize(ctx->stream));
 	if (!b200_etc1s_endpoint_histogram_device(ctx, ctx->d_aux[1], num_blocks, static_cast<uint32_t*>(ctx->d_aux[0]))) return 0;
 	B200_CUDA_OK(ctx, cudaMemcpy(pHist, ctx->d_aux[0], hist_bytes, cudaMemcpyDeviceToHost));
+	return 1;
+}
+
+extern "C" int b200_etc1s_selector_training_device(b200_context* ctx, const void* dEtc_blocks, uint32_t num_blocks, int perceptual, uint32_t* dKeys, uint32_t* dWeights)
+{
+	if (!ctx) return 0;
+	if (!ctx->activate()) return 0;
+	if (!num_blocks) return 1;
+	ctx->launches = 1; __atomic_add_fetch(&g_b200_total_launches, 1, __ATOMIC_RELAXED);
+	B200_CUDA_OK(ctx, cudaEventRecord(ctx->ev0, ctx->stream));
+	k_etc1s_selector_training<<<(num_blocks + 255) / 256, 256, 0, ctx->stream>>>(static_cast<const uint2*>(dEtc_blocks), num_blocks, perceptual, dKeys, dWeights);
+	B200_CUDA_OK(ctx, cudaGetLastError());
+	B200_CUDA_OK(ctx, cudaEventRecord(ctx->ev1, ctx->stream));
+	B200_CUDA_OK(ctx, cudaStreamSynchronize(ctx->stream));
+	B200_CUDA_OK(ctx, cudaEventElapsedTime(&ctx->last_ms, ctx->ev0, ctx->ev1));
+	return 1;
+}
+
+extern "C" int b200_etc1s_selector_training(b200_context* ctx, const void* pEtc_blocks, uint32_t num_blocks, int perceptual, uint32_t* pKeys, uint32_t* pWeights)
+{
+	if (!ctx) return 0;
+	if (!ctx->activate()) return 0;
+	if (!num_blocks) return 1;
+	if (!pEtc_blocks || !pKeys || !pWeights) { ctx->fail("b200_etc1s_selector_training: null buffer"); return 0; }
+	if (!upload(ctx, 1, pEtc_blocks, (size_t)num_blocks * 8)) return 0;
+	if (!ctx->reserve(ctx->d_aux[0], ctx->aux_cap[0], (size_t)num_blocks * 8)) return 0;
+	uint32_t* dk = static_cast<uint32_t*>(ctx->d_aux[0]);
+	if (!b200_etc1s_selector_training_device(ctx, ctx->d_aux[1], num_blocks, perceptual, dk, dk + num_blocks)) return 0;
+	B200_CUDA_OK(ctx, cudaMemcpy(pKeys, dk, (size_t)num_blocks * 4, cudaMemcpyDeviceToHost));
+	B200_CUDA_OK(ctx, cudaMemcpy(pWeights, dk + num_blocks, (size_t)num_blocks * 4, cudaMemcpyDeviceToHost));
 	return 1;
 }

@@ -30,3 +30,28 @@ def global_endpoint_training_set(ctx, blocks_x, blocks_y, all_blocks, perceptual
     allreduce_endpoint_histogram(d_hist, group)
     hist = d_hist.cpu().numpy().astype(np.uint32)
     return etc_blocks, etc1s.training_vectors_from_histogram(hist)
+
+
+def allgather_selector_training(local_keys, local_weights, group=None):
+    """local_keys / local_weights: torch int64 tensors (any length, on this rank's device) holding this shard's UNIQUE selector
+    keys and their summed weights. Returns the global unique keys (ascending) and summed weights, identical on every rank.
+    Shards differ in length, so lengths are exchanged first and the payload is padded to the longest (an all-gatherv)."""
+    import torch
+    import torch.distributed as dist
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+        keys, inv = torch.unique(local_keys, return_inverse=True)
+        return keys, torch.zeros_like(keys).index_add_(0, inv, local_weights)
+    world = dist.get_world_size(group)
+    n_local = torch.tensor([local_keys.numel()], dtype=torch.int64, device=local_keys.device)
+    lengths = [torch.zeros_like(n_local) for _ in range(world)]
+    dist.all_gather(lengths, n_local, group=group)
+    longest = int(max(int(v.item()) for v in lengths))
+    payload = torch.zeros((2, longest), dtype=torch.int64, device=local_keys.device)
+    payload[0, :local_keys.numel()] = local_keys
+    payload[1, :local_keys.numel()] = local_weights
+    gathered = [torch.zeros_like(payload) for _ in range(world)]
+    dist.all_gather(gathered, payload, group=group)
+    keys = torch.cat([g[0, :int(n.item())] for g, n in zip(gathered, lengths)])
+    weights = torch.cat([g[1, :int(n.item())] for g, n in zip(gathered, lengths)])
+    ukeys, inv = torch.unique(keys, return_inverse=True)
+    return ukeys, torch.zeros_like(ukeys).index_add_(0, inv, weights)

@@ -113,6 +113,23 @@ class Etc1sContext:
         self._check(ok, "b200_etc1s_endpoint_histogram_device")
 
 
+    def selector_training(self, etc_blocks, perceptual):
+        """(N, 8) uint8 ETC1S blocks (host) -> (keys (N,) uint32, weights (N,) uint32): generate_selector_clusters' per-block part."""
+        b = np.ascontiguousarray(etc_blocks, np.uint8)
+        keys = np.empty(b.shape[0], np.uint32)
+        weights = np.empty(b.shape[0], np.uint32)
+        self._check(self._lib.b200_etc1s_selector_training(self._ctx, _p(b), b.shape[0], int(bool(perceptual)), _p(keys), _p(weights)), "b200_etc1s_selector_training")
+        return keys, weights
+
+
+def merge_selector_training(keys, weights):
+    """Unique keys in ascending order with summed weights: what the clusterer's duplicate merge leaves (enc.h:2228-2260)."""
+    u, inv = np.unique(np.asarray(keys, np.uint32), return_inverse=True)
+    w = np.zeros(u.shape[0], np.uint64)
+    np.add.at(w, inv, np.asarray(weights, np.uint64))
+    return u, w
+
+
 def endpoint_keys(etc_blocks):
     """Host restatement of the key extraction (test oracle for the histogram kernel): bytes 0..3 of an ETC1S etc_block."""
     b = np.asarray(etc_blocks, np.uint8).astype(np.uint32)

@@ -118,6 +118,13 @@ int b200_etc1s_determine_selectors(b200_context* ctx, const void* pInput_etc_col
 int b200_etc1s_endpoint_histogram(b200_context* ctx, const void* pEtc_blocks, uint32_t num_blocks, uint32_t* pHist);
 int b200_etc1s_endpoint_histogram_device(b200_context* ctx, const void* dEtc_blocks, uint32_t num_blocks, uint32_t* dHist);
 
+/* Per block, the selector training vector of basisu_frontend::generate_selector_clusters (encoder/basisu_frontend.cpp:2156-2179):
+ * key = the 16 selectors, 2 bits each, texel (x, y) at bits 2 * (x + 4 * y); weight = clamp(color_distance(low, high block
+ * colour) / 300, 1, 4096). The clusterer merges equal vectors, so ranks all-gather their unique (key, summed weight) pairs
+ * (basis_universal_b200/distributed.py::allgather_selector_training). */
+int b200_etc1s_selector_training(b200_context* ctx, const void* pEtc_blocks, uint32_t num_blocks, int perceptual, uint32_t* pKeys, uint32_t* pWeights);
+int b200_etc1s_selector_training_device(b200_context* ctx, const void* dEtc_blocks, uint32_t num_blocks, int perceptual, uint32_t* dKeys, uint32_t* dWeights);
+
 /* ---- either side of the per-block path: ingest, decode, quality metric ---------------------------------------------------- */
 
 /* Raster RGBA8 image -> array of 64 B pixel_blocks in raster block order, edge texels clamped: one slice of

@@ -310,3 +310,23 @@ REF_API void ref_image_metrics(const uint8_t* pA, const uint8_t* pB, uint32_t w,
 	im.calc(a, b, first_chan, total_chans, avg_comp_error != 0, use_601_luma != 0);
 	out5[0] = im.m_max; out5[1] = im.m_mean; out5[2] = im.m_mean_squared; out5[3] = im.m_rms; out5[4] = im.m_psnr;
 }
+
+// The per-block part of basisu_frontend::generate_selector_clusters (frontend.cpp:2156-2179): the block's selector training
+// vector (16 selectors, here packed 2 bits each, texel x + 4y at bits 2(x+4y)) and its weight.
+REF_API void ref_selector_training(const uint8_t* pEtc_blocks, uint32_t n, uint32_t perceptual, uint32_t* pKeys, uint32_t* pWeights)
+{
+	for (uint32_t i = 0; i < n; i++)
+	{
+		const etc_block& blk = *reinterpret_cast<const etc_block*>(pEtc_blocks + (size_t)i * 8);
+		uint32_t key = 0;
+		for (uint32_t y = 0; y < 4; y++)
+			for (uint32_t x = 0; x < 4; x++)
+				key |= blk.get_selector(x, y) << ((x + y * 4) * 2);
+		const uint32_t subblock_index = (blk.get_inten_table(0) > blk.get_inten_table(1)) ? 0 : 1;
+		color_rgba block_colors[2];
+		blk.get_block_low_high_colors(block_colors, subblock_index);
+		const uint32_t dist = color_distance(perceptual != 0, block_colors[0], block_colors[1], false);
+		pKeys[i] = key;
+		pWeights[i] = clamp<uint32_t>(dist / 300, 1, 4096);
+	}
+}

@@ -84,3 +84,37 @@ def test_two_rank_endpoint_histogram_allreduce_gloo():
         p.join(180)
         assert p.exitcode == 0
     assert q.get()
+
+
+def _sel_worker(rank, world, port, q):
+    """gloo all-gatherv of per-rank unique selector keys + weights == merge over the whole image (second ETC1S exchange)."""
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from basis_universal_b200 import distributed, etc1s
+    rng = np.random.default_rng(8)
+    nbx, nby = 40, 31
+    keys = rng.integers(0, 50, nbx * nby).astype(np.uint32) * np.uint32(0x01010101)   # few distinct keys, many duplicates
+    weights = rng.integers(1, 4097, nbx * nby).astype(np.uint32)
+    first, last = sharding.block_range(nbx, nby, rank, world)
+    lk, lw = etc1s.merge_selector_training(keys[first:last], weights[first:last])
+    gk, gw = distributed.allgather_selector_training(torch.from_numpy(lk.astype(np.int64)), torch.from_numpy(lw.astype(np.int64)))
+    wk, ww = etc1s.merge_selector_training(keys, weights)
+    ok = np.array_equal(gk.numpy(), wk.astype(np.int64)) and np.array_equal(gw.numpy(), ww.astype(np.int64))
+    if rank == 0:
+        q.put(bool(ok))
+    dist.destroy_process_group()
+
+
+def test_two_rank_selector_training_allgather_gloo():
+    world = 2
+    ctx = mp.get_context("spawn")
+    q = ctx.SimpleQueue()
+    port = _free_port()
+    procs = [ctx.Process(target=_sel_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(180)
+        assert p.exitcode == 0
+    assert q.get()

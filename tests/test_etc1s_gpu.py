@@ -107,3 +107,20 @@ def test_endpoint_histogram_kernel(ctx_cpu, blocks):
     assert np.array_equal(hist, want) and int(hist.sum()) == 2 * blocks.shape[0]
     keys, vecs, weights = etc1s.training_vectors_from_histogram(hist)
     assert len(keys) > 100 and float(vecs.max()) <= 1.0 and int(weights.sum()) == 2 * blocks.shape[0]
+
+
+@pytest.mark.parametrize("perceptual", [0, 1])
+def test_selector_training_kernel(ctx_cpu, ref, blocks, perceptual):
+    """Per-block selector training vectors == the loop body of basisu_frontend::generate_selector_clusters."""
+    import ctypes
+    enc = ctx_cpu.encode_etc1s_blocks(bool(perceptual), 16)
+    rnd = np.random.default_rng(6).integers(0, 256, (2000, 8), dtype=np.uint8)
+    rnd[:, 3] |= 2                                   # differential mode (the only one ETC1S uses); deltas and selectors arbitrary
+    for b in (enc, rnd):
+        b = np.ascontiguousarray(b)
+        keys, weights = ctx_cpu.selector_training(b, perceptual)
+        wk, ww = np.zeros(b.shape[0], np.uint32), np.zeros(b.shape[0], np.uint32)
+        ref.lib.ref_selector_training(util._ptr(b), ctypes.c_uint32(b.shape[0]), ctypes.c_uint32(perceptual), util._ptr(wk), util._ptr(ww))
+        assert np.array_equal(keys, wk) and np.array_equal(weights, ww)
+    u, w = etc1s.merge_selector_training(*ctx_cpu.selector_training(enc, perceptual))
+    assert int(w.sum()) == int(ctx_cpu.selector_training(enc, perceptual)[1].astype(np.uint64).sum()) and np.all(np.diff(u.astype(np.int64)) > 0)

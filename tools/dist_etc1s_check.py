@@ -29,10 +29,16 @@ def main():
     hist = ctx.endpoint_histogram(whole)
     k2, v2, w2 = etc1s.training_vectors_from_histogram(hist)
     ok = np.array_equal(keys, k2) and np.array_equal(vecs, v2) and np.array_equal(weights, w2) and int(weights.sum()) == 2 * blocks.shape[0]
+    # second exchange: selector training set (all-gatherv of unique keys + weights)
+    lk, lw = etc1s.merge_selector_training(*ctx.selector_training(local_blocks, True))
+    gk, gw = distributed.allgather_selector_training(torch.from_numpy(lk.astype(np.int64)).cuda(), torch.from_numpy(lw.astype(np.int64)).cuda())
+    wk, ww = etc1s.merge_selector_training(*ctx.selector_training(whole, True))
+    ok_sel = np.array_equal(gk.cpu().numpy(), wk.astype(np.int64)) and np.array_equal(gw.cpu().numpy(), ww.astype(np.int64))
+    ok = ok and ok_sel
     flag = torch.tensor([1 if ok else 0], device="cuda")
     dist.all_reduce(flag, op=dist.ReduceOp.MIN)
     if rank == 0:
-        print(f"dist_etc1s_check: world {world}, {len(keys)} unique training vectors, total weight {int(weights.sum())}, identical on all ranks: {bool(flag.item())}", flush=True)
+        print(f"dist_etc1s_check: world {world}, {len(keys)} unique training vectors, total weight {int(weights.sum())}, {len(wk)} unique selector vectors; identical on all ranks: {bool(flag.item())}", flush=True)
     ctx.close()
     dist.destroy_process_group()
     sys.exit(0 if flag.item() else 1)
