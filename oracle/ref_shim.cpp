@@ -330,3 +330,6 @@ REF_API void ref_selector_training(const uint8_t* pEtc_blocks, uint32_t n, uint3
 		pWeights[i] = clamp<uint32_t>(dist / 300, 1, 4096);
 	}
 }
+
+// Turns the encoder's own debug_printf stage timers on or off (enc.h: enable_debug_printf); used by tools/bench_dropin.py.
+REF_API void ref_enable_debug_printf(int enabled) { enable_debug_printf(enabled != 0); }
