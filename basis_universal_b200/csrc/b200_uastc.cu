@@ -20,10 +20,10 @@ using namespace bu;
 #define BU_CAND_MINB 10
 #endif
 #ifndef BU_FIN_MINB
-#define BU_FIN_MINB 1
+#define BU_FIN_MINB 10
 #endif
 #ifndef BU_CLS_MINB
-#define BU_CLS_MINB 1
+#define BU_CLS_MINB 8
 #endif
 
 struct block_meta { block_class k; block_ranks ranks; }; // 16 B

@@ -631,20 +631,24 @@ BU_ROLL
 	{
 		const uint32_t i = etc1_subset_texel(flip, s, j);
 		const ycc q = dec_y[i];
-		uint32_t bi = 0;
+		ycc chosen;
 		if (!clamped)
 		{
-			// chroma terms are equal for the four candidates: the arg-min is decided by |luma difference| alone
+			// chroma terms are equal for the four candidates: the arg-min is decided by |luma difference| alone, and the chosen
+			// colour is base + m on every channel, i.e. (y + 256 m, cr, cb) in the metric's space
 			const int dy = base_y.y - q.y;
-			int be = iabsi(dy + 256 * (int)T->etc1_inten[inten * 4]);
-			for (uint32_t k = 1; k < 4; k++) { const int e = iabsi(dy + 256 * (int)T->etc1_inten[inten * 4 + k]); if (e < be) { be = e; bi = k; } }
+			int bm = (int)T->etc1_inten[inten * 4];
+			int be = iabsi(dy + 256 * bm);
+			for (uint32_t k = 1; k < 4; k++) { const int m = (int)T->etc1_inten[inten * 4 + k]; const int e = iabsi(dy + 256 * m); if (e < be) { be = e; bm = m; } }
+			chosen.y = base_y.y + 256 * bm; chosen.cr = base_y.cr; chosen.cb = base_y.cb;
 		}
 		else
 		{
+			uint32_t bi = 0;
 			uint64_t be = ycc_diff(tab[0], q);
 			for (uint32_t k = 1; k < 4; k++) { const uint64_t e = ycc_diff(tab[k], q); if (e < be) { be = e; bi = k; } }
+			chosen = (bi == 0) ? tab[0] : (bi == 1) ? tab[1] : (bi == 2) ? tab[2] : tab[3];
 		}
-		const ycc chosen = (bi == 0) ? tab[0] : (bi == 1) ? tab[1] : (bi == 2) ? tab[2] : tab[3];
 		err += ycc_diff(src_y[i], chosen);
 	}
 	inten_out = inten;
