@@ -130,12 +130,6 @@ def merge_selector_training(keys, weights):
     return u, w
 
 
-def endpoint_keys(etc_blocks):
-    """Host restatement of the key extraction (test oracle for the histogram kernel): bytes 0..3 of an ETC1S etc_block."""
-    b = np.asarray(etc_blocks, np.uint8).astype(np.uint32)
-    return ((b[:, 0] >> 3) << 13) | ((b[:, 1] >> 3) << 8) | ((b[:, 2] >> 3) << 3) | (b[:, 3] >> 5)
-
-
 _INTEN_LOW_HIGH = np.array([[-8, 8], [-17, 17], [-29, 29], [-42, 42], [-60, 60], [-80, 80], [-106, 106], [-183, 183]], np.int32)  # g_etc1_inten_tables[t][0], [t][3]
 
 

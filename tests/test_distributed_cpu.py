@@ -11,6 +11,8 @@ import torch.multiprocessing as mp
 
 from basis_universal_b200 import sharding
 
+import util
+
 
 def _free_port():
     s = socket.socket()
@@ -62,9 +64,9 @@ def _hist_worker(rank, world, port, q):
     nbx, nby = 24, 19
     blocks = rng.integers(0, 256, (nbx * nby, 8), dtype=np.uint8)
     first, last = sharding.block_range(nbx, nby, rank, world)
-    local = torch.from_numpy(np.bincount(etc1s.endpoint_keys(blocks[first:last]), minlength=1 << 18).astype(np.int32) * 2)
+    local = torch.from_numpy(np.bincount(util.endpoint_keys(blocks[first:last]), minlength=1 << 18).astype(np.int32) * 2)
     distributed.allreduce_endpoint_histogram(local)
-    whole = np.bincount(etc1s.endpoint_keys(blocks), minlength=1 << 18) * 2
+    whole = np.bincount(util.endpoint_keys(blocks), minlength=1 << 18) * 2
     keys, vecs, weights = etc1s.training_vectors_from_histogram(local.numpy().astype(np.uint32))
     ok = bool(np.array_equal(local.numpy(), whole)) and int(weights.sum()) == 2 * nbx * nby and vecs.shape == (len(keys), 6)
     if rank == 0:

@@ -103,7 +103,7 @@ def test_calls_fail_loudly_without_blocks():
 def test_endpoint_histogram_kernel(ctx_cpu, blocks):
     enc = ctx_cpu.encode_etc1s_blocks(True, 16)
     hist = ctx_cpu.endpoint_histogram(enc)
-    want = np.bincount(etc1s.endpoint_keys(enc), minlength=1 << 18).astype(np.uint32) * 2
+    want = np.bincount(util.endpoint_keys(enc), minlength=1 << 18).astype(np.uint32) * 2
     assert np.array_equal(hist, want) and int(hist.sum()) == 2 * blocks.shape[0]
     keys, vecs, weights = etc1s.training_vectors_from_histogram(hist)
     assert len(keys) > 100 and float(vecs.max()) <= 1.0 and int(weights.sum()) == 2 * blocks.shape[0]

@@ -290,3 +290,10 @@ def rdo_test_image():
     """A crop of a natural image (RDO modifies ~half of its blocks) tiled with part of the synthetic image (alpha modes)."""
     g = np.load(os.path.join(GOLDEN, "kodim03_uastc_l0.npz"))
     return np.ascontiguousarray(np.concatenate([g["image"][:128, :256], synth(256, 77)[:64]], 0))
+
+
+def endpoint_keys(etc_blocks):
+    """numpy restatement of k_etc1s_endpoint_histogram's key extraction (r5<<13 | g5<<8 | b5<<3 | inten from bytes 0..3 of an
+    ETC1S etc_block): the checker for the histogram kernel and the stand-in for it in the CPU-only gloo test."""
+    b = np.asarray(etc_blocks, np.uint8).astype(np.uint32)
+    return ((b[:, 0] >> 3) << 13) | ((b[:, 1] >> 3) << 8) | ((b[:, 2] >> 3) << 3) | (b[:, 3] >> 5)

@@ -96,7 +96,7 @@ def main():
     enc = ctx.encode_etc1s_blocks(True, args.perms)
     ctx.endpoint_histogram(enc)
     wall, hist = timed(lambda: ctx.endpoint_histogram(enc))
-    want = np.bincount(etc1s.endpoint_keys(enc), minlength=1 << 18).astype(np.uint32) * 2
+    want = np.bincount(util.endpoint_keys(enc), minlength=1 << 18).astype(np.uint32) * 2
     line("endpoint_histogram", n, "blocks", wall, ctx.last_kernel_ms, None, None, n, bool(np.array_equal(hist, want)))
     ctx.close()
 
