@@ -37,3 +37,12 @@ def golden():
     import numpy as np
     import util
     return np.load(os.path.join(util.GOLDEN, "uastc_blocks.npz"))
+
+
+@pytest.fixture(scope="session")
+def golden_real():
+    """Blocks sampled from the reference's own test images (photographs, alpha, line art, 1x1 solids) with the reference's
+    output at several flag sets (tests/golden/make_golden.py)."""
+    import numpy as np
+    import util
+    return np.load(os.path.join(util.GOLDEN, "uastc_real_images.npz"))

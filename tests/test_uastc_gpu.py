@@ -108,3 +108,10 @@ def test_multi_chunk_level4(enc):
     out = enc.encode_uastc(blocks, 4)
     small = enc.encode_uastc(tile, 4)
     assert np.array_equal(out, np.resize(small, (n, 16)))
+
+
+@pytest.mark.parametrize("flags", [0, 1, 2, 3, 2 | 512, 2 | 64 | 256])
+def test_golden_real_images_bit_exact(enc, golden_real, flags):
+    """2882 blocks sampled from the reference's own test images (kodim photographs, alpha0, wikipedia, xmen, tough, the 1x1
+    solids): exercises the LA modes 15-17 and the solid path that the synthetic bench image never reaches."""
+    assert np.array_equal(enc.encode_uastc(golden_real["blocks"], flags), golden_real[f"uastc_flags_{flags}"])
