@@ -53,6 +53,8 @@ def lib():
         L.b200_etc1s_selector_training_device.restype = i32
         L.b200_etc1s_selector_training_device.argtypes = [vp, vp, u32, i32, vp, vp]
         sz = ctypes.c_size_t
+        L.b200_uastc_encode_image.restype = i32
+        L.b200_uastc_encode_image.argtypes = [vp, vp, u32, u32, sz, vp, u32]
         L.b200_extract_source_blocks.restype = i32
         L.b200_extract_source_blocks.argtypes = [vp, vp, u32, u32, sz, vp]
         L.b200_extract_source_blocks_device.restype = i32
@@ -83,7 +85,7 @@ def lib():
 
 EXPORTS = [
     "b200_device_count", "b200_create_context", "b200_destroy_context", "b200_last_error",
-    "b200_uastc_encode_blocks", "b200_uastc_encode_blocks_device", "b200_uastc_rdo",
+    "b200_uastc_encode_blocks", "b200_uastc_encode_blocks_device", "b200_uastc_encode_image", "b200_uastc_rdo",
     "b200_etc1s_set_flavour", "b200_etc1s_set_pixel_blocks", "b200_etc1s_endpoint_histogram", "b200_etc1s_endpoint_histogram_device",
     "b200_etc1s_selector_training", "b200_etc1s_selector_training_device",
     "b200_extract_source_blocks", "b200_extract_source_blocks_device", "b200_uastc_unpack_blocks", "b200_uastc_unpack_blocks_device", "b200_block_metrics_device", "b200_etc1s_encode_blocks", "b200_etc1s_encode_pixel_clusters",

@@ -190,3 +190,23 @@ extern "C" int b200_block_metrics_device(b200_context* ctx, const void* dBlocksA
 	B200_CUDA_OK(ctx, cudaMemcpy(pOut, d, bytes, cudaMemcpyDeviceToHost));
 	return 1;
 }
+
+extern "C" int b200_uastc_encode_image(b200_context* ctx, const void* pRGBA, uint32_t width, uint32_t height, size_t pitch_bytes, void* pOut, uint32_t flags)
+{
+	if (!ctx || !ctx->activate()) return 0;
+	if (!width || !height) { ctx->last_ms = 0; ctx->launches = 0; return 1; }
+	if (!pRGBA || !pOut) { ctx->fail("b200_uastc_encode_image: null buffer"); return 0; }
+	const uint32_t nbx = (width + 3) / 4, nby = (height + 3) / 4, n = nbx * nby;
+	const size_t in_bytes = pitch_bytes * height;
+	if (!ctx->reserve(ctx->d_aux[0], ctx->aux_cap[0], in_bytes)) return 0;
+	if (!ctx->reserve(ctx->d_in, ctx->in_cap, (size_t)n * 64)) return 0;
+	if (!ctx->reserve(ctx->d_out, ctx->out_cap, (size_t)n * 16)) return 0;
+	B200_CUDA_OK(ctx, cudaMemcpyAsync(ctx->d_aux[0], pRGBA, in_bytes, cudaMemcpyHostToDevice, ctx->stream));
+	if (!b200_extract_source_blocks_device(ctx, ctx->d_aux[0], width, height, pitch_bytes, ctx->d_in)) return 0;
+	const float extract_ms = ctx->last_ms;
+	if (!b200_uastc_encode_blocks_device(ctx, ctx->d_in, n, ctx->d_out, flags)) return 0;
+	ctx->last_ms += extract_ms;
+	ctx->launches += 1; // the ingest kernel
+	B200_CUDA_OK(ctx, cudaMemcpy(pOut, ctx->d_out, (size_t)n * 16, cudaMemcpyDeviceToHost));
+	return 1;
+}

@@ -123,3 +123,15 @@ class Encoder:
         """Device-resident form: raw device pointers (e.g. torch tensor .data_ptr()) to (N,64) and (N,16) uint8 buffers."""
         ok = self._lib.b200_uastc_encode_blocks_device(self._ctx, ctypes.c_void_p(d_blocks_ptr), int(num_blocks), ctypes.c_void_p(d_out_ptr), int(flags))
         self._check(ok, "b200_uastc_encode_blocks_device")
+
+    def encode_image(self, image, flags=cPackUASTCLevelDefault):
+        """(H, W, 4) uint8 raster (rows may be strided) -> (ceil(H/4) * ceil(W/4), 16) uint8 UASTC blocks: ingest and encode both on
+        the device (b200_uastc_encode_image)."""
+        img = image
+        if img.ndim != 3 or img.shape[2] != 4 or img.dtype != np.uint8 or img.strides[2] != 1 or img.strides[1] != 4:
+            img = np.ascontiguousarray(img, np.uint8)
+        h, w = img.shape[:2]
+        out = np.empty((((h + 3) // 4) * ((w + 3) // 4), 16), np.uint8)
+        ok = self._lib.b200_uastc_encode_image(self._ctx, img.ctypes.data_as(ctypes.c_void_p), w, h, ctypes.c_size_t(img.strides[0] if h else 0), out.ctypes.data_as(ctypes.c_void_p), int(flags))
+        self._check(ok, "b200_uastc_encode_image")
+        return out

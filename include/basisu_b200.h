@@ -50,6 +50,11 @@ int b200_uastc_encode_blocks(b200_context* ctx, const void* pBlocks, uint32_t nu
  * stream and the call returns after the stream has been synchronised. */
 int b200_uastc_encode_blocks_device(b200_context* ctx, const void* dBlocks, uint32_t num_blocks, void* dOut, uint32_t flags);
 
+/* Raster in, blocks out: basis_compressor::extract_source_blocks (encoder/basisu_comp.cpp:3207) followed by the encode loop
+ * (comp.cpp:2006-2064) for one slice, without the intermediate pixel_block array ever existing on the host. pRGBA is a HOST
+ * pointer to height rows of width RGBA8 texels, pitch_bytes apart; pOut receives ((width+3)/4) * ((height+3)/4) blocks. */
+int b200_uastc_encode_image(b200_context* ctx, const void* pRGBA, uint32_t width, uint32_t height, size_t pitch_bytes, void* pOut, uint32_t flags);
+
 /* RDO post-pass, in place. Same contract as
  *     bool basisu::uastc_rdo(uint32_t num_blocks, basist::uastc_block* pBlocks, const color_rgba* pBlock_pixels,
  *                            const uastc_rdo_params& params, uint32_t flags, job_pool*, uint32_t total_jobs)

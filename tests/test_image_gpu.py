@@ -110,3 +110,15 @@ def test_unpack_random_valid_bit_patterns(ops, ref):
     u = np.ascontiguousarray(cand[valid])
     assert u.shape[0] > 1000
     assert np.array_equal(ops.unpack_uastc(u), ref.unpack_uastc(u))
+
+
+@pytest.mark.parametrize("shape", [(64, 64), (50, 41), (1, 1), (4, 260)])
+def test_encode_image_equals_extract_then_encode(ops, ref, shape):
+    """Raster in, UASTC out in one call == the reference's extract_source_blocks followed by encode_uastc per block."""
+    h, w = shape
+    img = np.ascontiguousarray(util.synth(max(h, w) + 8, 17)[:h, :w])
+    enc = uastc.Encoder(0)
+    got = enc.encode_image(img, 2)
+    assert enc.last_launch_count >= 4
+    enc.close()
+    assert np.array_equal(got, ref.encode_uastc(ref_extract(ref, img), 2))
