@@ -83,7 +83,8 @@ __global__ void __launch_bounds__(RDO_THREADS) k_rdo_chain(uint4* blocks, const 
 			for (int r = 0; r < 4; r++) { const uint4 v = __ldg(pp + r); px[r * 4] = v.x; px[r * 4 + 1] = v.y; px[r * 4 + 2] = v.z; px[r * 4 + 3] = v.w; }
 		}
 		st.smooth_scale = rdo_smooth_scale(p, px);
-		const uint64_t cur_err = rdo_block_error(T, st.cur, px);
+		bc7_endpoints_of(T, st.cur, st.bc7);
+		const uint64_t cur_err = rdo_block_error(T, st.cur, st.bc7, px);
 		st.cur_ms_err = (float)cur_err * (1.0f / 64.0f);
 		st.cur_rms_err = sqrtf(st.cur_ms_err);
 		mode_selector_field(st.cur.mode, st.first_sel_bit, st.total_sel_bits);

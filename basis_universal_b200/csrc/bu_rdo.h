@@ -171,13 +171,15 @@ BU_FI void read_weight_field(const bu_tables* T, const candidate& c, const block
 }
 
 // (uastc_err + bc7_err) / 2 with the RGBA metric (uastc_enc.cpp:3869-3888).
-BU_NI inline uint64_t rdo_block_error(const bu_tables* T, const candidate& c, const uint32_t* px)
+// E: the BC7 endpoints of the block's transcode (bc7_endpoints_of). They depend on the UASTC endpoints only, so the trials of
+// one step, which change weights only, share the current block's.
+BU_NI inline uint64_t rdo_block_error(const bu_tables* T, const candidate& c, const bc7_endpoints& E, const uint32_t* px)
 {
 	uint32_t dec[16];
 	uint64_t ue = 0, be = 0;
 	decode_candidate(T, c, dec);
 	for (int i = 0; i < 16; i++) ue += dist_rgba(px[i], dec[i]);
-	decode_bc7_transcode(T, c, dec);
+	bc7_texels(T, c, E, dec);
 	for (int i = 0; i < 16; i++) be += dist_rgba(px[i], dec[i]);
 	return (ue + be) / 2;
 }
@@ -204,6 +206,7 @@ BU_HD inline float rdo_smooth_scale(const rdo_params& p, const uint32_t* px)
 struct rdo_step
 {
 	candidate cur;            // unpacked current block
+	bc7_endpoints bc7;        // its BC7-transcode endpoints (shared by every trial of the step)
 	block_bits bits;          // its 128 bits
 	uint32_t first_sel_bit, total_sel_bits;
 	uint64_t cur_sel_bits;
@@ -222,7 +225,7 @@ BU_NI inline bool rdo_trial(const bu_tables* T, const rdo_params& p, const rdo_s
 	if (st.total_sel_bits > 64) bits_write(trial_bits, st.first_sel_bit + 64, st.total_sel_bits - 64, bits_read(prev, st.first_sel_bit + 64, st.total_sel_bits - 64));
 	candidate tc = st.cur;
 	read_weight_field(T, tc, trial_bits, tc.w);
-	const uint64_t err = rdo_block_error(T, tc, px);
+	const uint64_t err = rdo_block_error(T, tc, st.bc7, px);
 	const float ms = (float)err * (1.0f / 64.0f);
 	const float rms = sqrtf(ms);
 	if (rms > st.cur_rms_err * p.max_allowed_rms_increase_ratio) return false;

@@ -486,7 +486,11 @@ BU_FI uint32_t bc7_lerp(uint32_t l, uint32_t h, uint32_t w) { return (l * (64 - 
 BU_TABLE(uint8_t, bc7_weight5_to_4, [32], { 0, 0, 1, 1, 2, 2, 3, 3, 4, 4, 5, 5, 6, 6, 6, 7, 8, 9, 9, 9, 10, 10, 11, 11, 12, 12, 13, 13, 14, 14, 15, 15 })
 BU_TABLE(uint8_t, bc7_weight3_to_4, [8], { 0, 2, 4, 6, 9, 11, 13, 15 })
 
-BU_NI inline void decode_bc7_transcode(const bu_tables* T, const candidate& c, uint32_t* out)
+// The BC7 endpoints of the transcode depend on the UASTC endpoints (and pattern / rotation) only, the texels on those endpoints
+// and the weights: the two halves are separate so that uastc_rdo's trials, which splice weights only, fit the p-bits once.
+struct bc7_endpoints { uint32_t l[3][4], h[3][4]; }; // [BC7 subset][channel]
+
+BU_NI inline void bc7_endpoints_of(const bu_tables* T, const candidate& c, bc7_endpoints& E)
 {
 	const uint32_t mode = c.mode;
 	const uint32_t range = T->mode_endpoint_range[mode];
@@ -514,25 +518,13 @@ BU_NI inline void decode_bc7_transcode(const bu_tables* T, const candidate& c, u
 		pbit_fit f;
 		fit_unique_pbits(comps == 2 ? 4 : comps, 7, xl, xh, f);
 		if (comps == 3) { f.lo[3] = 127; f.hi[3] = 127; }
-		uint32_t l[4], h[4];
-		for (int k = 0; k < 4; k++) { l[k] = ((uint32_t)f.lo[k] << 1) | f.p0; h[k] = ((uint32_t)f.hi[k] << 1) | f.p1; }
-		BU_ROLL
-		for (int i = 0; i < 16; i++)
-		{
-			uint32_t s = c.w[i];
-			if (mode == 18) s = BU_TABLE_REF(bc7_weight5_to_4)[s];
-			else if (mode == 14) s = s * 5;
-			else if (mode == 5 || mode == 12) s = BU_TABLE_REF(bc7_weight3_to_4)[s];
-			const uint32_t w = T->bc7_weights4[s];
-			out[i] = px_make(bc7_lerp(l[0], h[0], w), bc7_lerp(l[1], h[1], w), bc7_lerp(l[2], h[2], w), bc7_lerp(l[3], h[3], w));
-		}
+		for (int k = 0; k < 4; k++) { E.l[0][k] = ((uint32_t)f.lo[k] << 1) | f.p0; E.h[0][k] = ((uint32_t)f.hi[k] << 1) | f.p1; }
 		return;
 	}
 	case 1: case 4:
 	{
 		// -> BC7 mode 3: two subsets, 777.1 endpoints with unique p-bits, 2-bit indices. Mode 1 replicates one endpoint pair.
 		const uint32_t subsets = (mode == 1) ? 1u : 2u;
-		uint32_t l[2][3], h[2][3];
 		const bool inv = (mode == 4) && T->cp2_invert[c.pattern];
 		BU_ROLL
 		for (uint32_t s = 0; s < subsets; s++)
@@ -548,22 +540,13 @@ BU_NI inline void decode_bc7_transcode(const bu_tables* T, const candidate& c, u
 			pbit_fit f;
 			fit_unique_pbits(3, 7, xl, xh, f);
 			const uint32_t b = inv ? 1 - s : s;
-			for (int k = 0; k < 3; k++) { l[b][k] = ((uint32_t)f.lo[k] << 1) | f.p0; h[b][k] = ((uint32_t)f.hi[k] << 1) | f.p1; }
-		}
-		const uint8_t* part = (mode == 4) ? T->bc7_part2 + c.pattern * 16 : nullptr;
-		BU_ROLL
-		for (int i = 0; i < 16; i++)
-		{
-			const uint32_t b = part ? part[i] : 0;
-			const uint32_t w = T->weights[2 * 32 + c.w[i]];
-			out[i] = px_make(bc7_lerp(l[b][0], h[b][0], w), bc7_lerp(l[b][1], h[b][1], w), bc7_lerp(l[b][2], h[b][2], w), 255);
+			for (int k = 0; k < 3; k++) { E.l[b][k] = ((uint32_t)f.lo[k] << 1) | f.p0; E.h[b][k] = ((uint32_t)f.hi[k] << 1) | f.p1; }
 		}
 		return;
 	}
 	case 2:
 	{
 		// -> BC7 mode 1: two subsets, 666 endpoints with a shared p-bit, 3-bit indices
-		uint32_t l[2][3], h[2][3];
 		const bool inv = T->cp2_invert[c.pattern] != 0;
 		BU_ROLL
 		for (uint32_t s = 0; s < 2; s++)
@@ -578,23 +561,13 @@ BU_NI inline void decode_bc7_transcode(const bu_tables* T, const candidate& c, u
 			pbit_fit f;
 			fit_shared_pbits(3, 6, xl, xh, f);
 			const uint32_t b = inv ? 1 - s : s;
-			for (int k = 0; k < 3; k++) { l[b][k] = bc7_dq_p(f.lo[k], f.p0, 6); h[b][k] = bc7_dq_p(f.hi[k], f.p0, 6); }
-		}
-		const uint8_t* part = T->bc7_part2 + c.pattern * 16;
-		BU_ROLL
-		for (int i = 0; i < 16; i++)
-		{
-			const uint32_t b = part[i];
-			const uint32_t w = T->weights[3 * 32 + c.w[i]];
-			out[i] = px_make(bc7_lerp(l[b][0], h[b][0], w), bc7_lerp(l[b][1], h[b][1], w), bc7_lerp(l[b][2], h[b][2], w), 255);
+			for (int k = 0; k < 3; k++) { E.l[b][k] = bc7_dq_p(f.lo[k], f.p0, 6); E.h[b][k] = bc7_dq_p(f.hi[k], f.p0, 6); }
 		}
 		return;
 	}
 	case 3: case 7:
 	{
 		// -> BC7 mode 2: three subsets, 555 endpoints, 2-bit indices
-		uint32_t l[3][3], h[3][3];
-		const uint8_t* part;
 		if (mode == 3)
 		{
 			const uint32_t perm = T->cp3_perm[c.pattern];
@@ -604,11 +577,10 @@ BU_NI inline void decode_bc7_transcode(const bu_tables* T, const candidate& c, u
 				const uint32_t b = T->astc_to_bc7_perm[perm * 3 + s];
 				for (int k = 0; k < 3; k++)
 				{
-					l[b][k] = bc7_dq(((uint32_t)u[c.ep[k * 2 + s * 6]] * 31 + 127) / 255, 5);
-					h[b][k] = bc7_dq(((uint32_t)u[c.ep[k * 2 + 1 + s * 6]] * 31 + 127) / 255, 5);
+					E.l[b][k] = bc7_dq(((uint32_t)u[c.ep[k * 2 + s * 6]] * 31 + 127) / 255, 5);
+					E.h[b][k] = bc7_dq(((uint32_t)u[c.ep[k * 2 + 1 + s * 6]] * 31 + 127) / 255, 5);
 				}
 			}
-			part = T->bc7_part3 + c.pattern * 16;
 		}
 		else
 		{
@@ -619,18 +591,10 @@ BU_NI inline void decode_bc7_transcode(const bu_tables* T, const candidate& c, u
 				const uint32_t s = bc7_part3_to_2(b, kk);
 				for (int k = 0; k < 3; k++)
 				{
-					l[b][k] = bc7_dq(((uint32_t)u[c.ep[k * 2 + s * 6]] * 31 + 127) / 255, 5);
-					h[b][k] = bc7_dq(((uint32_t)u[c.ep[k * 2 + 1 + s * 6]] * 31 + 127) / 255, 5);
+					E.l[b][k] = bc7_dq(((uint32_t)u[c.ep[k * 2 + s * 6]] * 31 + 127) / 255, 5);
+					E.h[b][k] = bc7_dq(((uint32_t)u[c.ep[k * 2 + 1 + s * 6]] * 31 + 127) / 255, 5);
 				}
 			}
-			part = T->bc7_part73 + c.pattern * 16;
-		}
-		BU_ROLL
-		for (int i = 0; i < 16; i++)
-		{
-			const uint32_t b = part[i];
-			const uint32_t w = T->weights[2 * 32 + c.w[i]];
-			out[i] = px_make(bc7_lerp(l[b][0], h[b][0], w), bc7_lerp(l[b][1], h[b][1], w), bc7_lerp(l[b][2], h[b][2], w), 255);
 		}
 		return;
 	}
@@ -638,7 +602,6 @@ BU_NI inline void decode_bc7_transcode(const bu_tables* T, const candidate& c, u
 	{
 		// -> BC7 mode 5: 777 colour + 8-bit alpha, separate 2-bit index planes, channel rotation
 		uint32_t l[4], h[4];
-		const uint32_t rotation = ((uint32_t)c.ccs + 1) & 3;
 		if (comps == 2)
 		{
 			l[0] = ((uint32_t)u[c.ep[0]] * 127 + 127) / 255; h[0] = ((uint32_t)u[c.ep[1]] * 127 + 127) / 255;
@@ -659,22 +622,12 @@ BU_NI inline void decode_bc7_transcode(const bu_tables* T, const candidate& c, u
 			}
 		}
 		for (int k = 0; k < 3; k++) { l[k] = bc7_dq(l[k], 7); h[k] = bc7_dq(h[k], 7); }
-		BU_ROLL
-		for (int i = 0; i < 16; i++)
-		{
-			uint32_t s0 = c.w[i * 2], s1 = c.w[i * 2 + 1];
-			if (mode == 13) { s0 = s0 ? 3 : 0; s1 = s1 ? 3 : 0; }
-			const uint32_t w0 = T->weights[2 * 32 + s0], w1 = T->weights[2 * 32 + s1];
-			uint32_t v[4] = { bc7_lerp(l[0], h[0], w0), bc7_lerp(l[1], h[1], w0), bc7_lerp(l[2], h[2], w0), bc7_lerp(l[3], h[3], w1) };
-			if (rotation >= 1) { const uint32_t t = v[3]; v[3] = v[rotation - 1]; v[rotation - 1] = t; }
-			out[i] = px_make(v[0], v[1], v[2], v[3]);
-		}
+		for (int k = 0; k < 4; k++) { E.l[0][k] = l[k]; E.h[0][k] = h[k]; }
 		return;
 	}
 	default: // 9, 16
 	{
 		// -> BC7 mode 7: two subsets, 5555.1 endpoints with unique p-bits, 2-bit indices
-		uint32_t l[2][4], h[2][4];
 		const bool inv = T->cp2_invert[c.pattern] != 0;
 		BU_ROLL
 		for (uint32_t s = 0; s < 2; s++)
@@ -691,19 +644,107 @@ BU_NI inline void decode_bc7_transcode(const bu_tables* T, const candidate& c, u
 			pbit_fit f;
 			fit_unique_pbits(4, 5, xl, xh, f);
 			const uint32_t b = inv ? 1 - s : s;
-			for (int k = 0; k < 4; k++) { l[b][k] = bc7_dq_p(f.lo[k], f.p0, 5); h[b][k] = bc7_dq_p(f.hi[k], f.p1, 5); }
+			for (int k = 0; k < 4; k++) { E.l[b][k] = bc7_dq_p(f.lo[k], f.p0, 5); E.h[b][k] = bc7_dq_p(f.hi[k], f.p1, 5); }
 		}
+		return;
+	}
+	}
+}
+
+BU_NI inline void bc7_texels(const bu_tables* T, const candidate& c, const bc7_endpoints& E, uint32_t* out)
+{
+	const uint32_t mode = c.mode;
+	switch (mode)
+	{
+	case 0: case 5: case 10: case 12: case 14: case 15: case 18:
+	{
+		const uint32_t* l = E.l[0];
+		const uint32_t* h = E.h[0];
+		BU_ROLL
+		for (int i = 0; i < 16; i++)
+		{
+			uint32_t s = c.w[i];
+			if (mode == 18) s = BU_TABLE_REF(bc7_weight5_to_4)[s];
+			else if (mode == 14) s = s * 5;
+			else if (mode == 5 || mode == 12) s = BU_TABLE_REF(bc7_weight3_to_4)[s];
+			const uint32_t w = T->bc7_weights4[s];
+			out[i] = px_make(bc7_lerp(l[0], h[0], w), bc7_lerp(l[1], h[1], w), bc7_lerp(l[2], h[2], w), bc7_lerp(l[3], h[3], w));
+		}
+		return;
+	}
+	case 1: case 4:
+	{
+		const uint8_t* part = (mode == 4) ? T->bc7_part2 + c.pattern * 16 : nullptr;
+		BU_ROLL
+		for (int i = 0; i < 16; i++)
+		{
+			const uint32_t b = part ? part[i] : 0;
+			const uint32_t w = T->weights[2 * 32 + c.w[i]];
+			out[i] = px_make(bc7_lerp(E.l[b][0], E.h[b][0], w), bc7_lerp(E.l[b][1], E.h[b][1], w), bc7_lerp(E.l[b][2], E.h[b][2], w), 255);
+		}
+		return;
+	}
+	case 2:
+	{
+		const uint8_t* part = T->bc7_part2 + c.pattern * 16;
+		BU_ROLL
+		for (int i = 0; i < 16; i++)
+		{
+			const uint32_t b = part[i];
+			const uint32_t w = T->weights[3 * 32 + c.w[i]];
+			out[i] = px_make(bc7_lerp(E.l[b][0], E.h[b][0], w), bc7_lerp(E.l[b][1], E.h[b][1], w), bc7_lerp(E.l[b][2], E.h[b][2], w), 255);
+		}
+		return;
+	}
+	case 3: case 7:
+	{
+		const uint8_t* part = (mode == 3) ? T->bc7_part3 + c.pattern * 16 : T->bc7_part73 + c.pattern * 16;
+		BU_ROLL
+		for (int i = 0; i < 16; i++)
+		{
+			const uint32_t b = part[i];
+			const uint32_t w = T->weights[2 * 32 + c.w[i]];
+			out[i] = px_make(bc7_lerp(E.l[b][0], E.h[b][0], w), bc7_lerp(E.l[b][1], E.h[b][1], w), bc7_lerp(E.l[b][2], E.h[b][2], w), 255);
+		}
+		return;
+	}
+	case 6: case 11: case 13: case 17:
+	{
+		const uint32_t* l = E.l[0];
+		const uint32_t* h = E.h[0];
+		const uint32_t rotation = ((uint32_t)c.ccs + 1) & 3;
+		BU_ROLL
+		for (int i = 0; i < 16; i++)
+		{
+			uint32_t s0 = c.w[i * 2], s1 = c.w[i * 2 + 1];
+			if (mode == 13) { s0 = s0 ? 3 : 0; s1 = s1 ? 3 : 0; }
+			const uint32_t w0 = T->weights[2 * 32 + s0], w1 = T->weights[2 * 32 + s1];
+			uint32_t v[4] = { bc7_lerp(l[0], h[0], w0), bc7_lerp(l[1], h[1], w0), bc7_lerp(l[2], h[2], w0), bc7_lerp(l[3], h[3], w1) };
+			if (rotation >= 1) { const uint32_t t = v[3]; v[3] = v[rotation - 1]; v[rotation - 1] = t; }
+			out[i] = px_make(v[0], v[1], v[2], v[3]);
+		}
+		return;
+	}
+	default: // 9, 16
+	{
 		const uint8_t* part = T->bc7_part2 + c.pattern * 16;
 		BU_ROLL
 		for (int i = 0; i < 16; i++)
 		{
 			const uint32_t b = part[i];
 			const uint32_t w = T->weights[2 * 32 + c.w[i]];
-			out[i] = px_make(bc7_lerp(l[b][0], h[b][0], w), bc7_lerp(l[b][1], h[b][1], w), bc7_lerp(l[b][2], h[b][2], w), bc7_lerp(l[b][3], h[b][3], w));
+			out[i] = px_make(bc7_lerp(E.l[b][0], E.h[b][0], w), bc7_lerp(E.l[b][1], E.h[b][1], w), bc7_lerp(E.l[b][2], E.h[b][2], w), bc7_lerp(E.l[b][3], E.h[b][3], w));
 		}
 		return;
 	}
 	}
+}
+
+BU_HD inline void decode_bc7_transcode(const bu_tables* T, const candidate& c, uint32_t* out)
+{
+	bc7_endpoints E;
+	bc7_endpoints_of(T, c, E);
+	bc7_texels(T, c, E, out);
 }
 
 // ---- candidate scoring (uastc_enc.cpp:2510 compute_block_error + 3471-3488 metric selection) --------------------------------

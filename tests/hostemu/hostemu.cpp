@@ -169,7 +169,8 @@ static bool rdo_chain(uint32_t first, uint32_t last, uint8_t* blocks, const uint
 		uint32_t px[16];
 		memcpy(px, pixels + (size_t)bi * 64, 64);
 		st.smooth_scale = rdo_smooth_scale(p, px);
-		const uint64_t cur_err = rdo_block_error(T, st.cur, px);
+		bc7_endpoints_of(T, st.cur, st.bc7);
+		const uint64_t cur_err = rdo_block_error(T, st.cur, st.bc7, px);
 		st.cur_ms_err = (float)cur_err * (1.0f / 64.0f);
 		st.cur_rms_err = sqrtf(st.cur_ms_err);
 		mode_selector_field(st.cur.mode, st.first_sel_bit, st.total_sel_bits);
