@@ -68,30 +68,65 @@ __global__ void __launch_bounds__(RDO_THREADS) k_rdo_chain(uint4* blocks, const 
 	__shared__ float s_t[RDO_THREADS / 32];
 	__shared__ uint32_t s_i[RDO_THREADS / 32];
 	__shared__ uint32_t s_winner;
+	// Everything a step needs that depends on the block alone (its unpacked form, source texels, error, smoothness scale,
+	// selector field) is independent of the steps before it: each of the CTA's 8 warps prepares one of the next 8 blocks, then
+	// the 8 steps run in order with all 256 threads on the trials.
+	enum { PRO_OK = 0, PRO_SOLID = 1, PRO_SKIP = 2, PRO_BAD = 3 };
+	struct prologue { rdo_step st; uint32_t px[16]; uint32_t state; };
+	__shared__ prologue s_pro[RDO_THREADS / 32];
 
-	for (uint32_t bi = first; bi < last; bi++)
+	for (uint32_t base = first; base < last; base += RDO_THREADS / 32)
 	{
-		rdo_step st;
-		st.bits = ld_bits(blocks + bi);
-		if (!unpack_block_bits(T, st.bits, st.cur)) { if (!tid) *failed = 1; return; }
-		if (st.cur.mode == 8) continue;
-
-		uint32_t px[16];
 		{
-			const uint4* pp = pixels + (size_t)bi * 4;
+			const uint32_t bi = base + (tid >> 5);
+			if (bi < last)
+			{
+				rdo_step st;
+				uint32_t px[16];
+				uint32_t state = PRO_OK;
+				st.bits = ld_bits(blocks + bi);
+				if (!unpack_block_bits(T, st.bits, st.cur)) state = PRO_BAD;
+				else if (st.cur.mode == 8) state = PRO_SOLID;
+				else
+				{
+					const uint4* pp = pixels + (size_t)bi * 4;
 #pragma unroll
-			for (int r = 0; r < 4; r++) { const uint4 v = __ldg(pp + r); px[r * 4] = v.x; px[r * 4 + 1] = v.y; px[r * 4 + 2] = v.z; px[r * 4 + 3] = v.w; }
+					for (int r = 0; r < 4; r++) { const uint4 v = __ldg(pp + r); px[r * 4] = v.x; px[r * 4 + 1] = v.y; px[r * 4 + 2] = v.z; px[r * 4 + 3] = v.w; }
+					st.smooth_scale = rdo_smooth_scale(p, px);
+					bc7_endpoints_of(T, st.cur, st.bc7);
+					const uint64_t cur_err = rdo_block_error(T, st.cur, st.bc7, px);
+					st.cur_ms_err = (float)cur_err * (1.0f / 64.0f);
+					st.cur_rms_err = sqrtf(st.cur_ms_err);
+					mode_selector_field(st.cur.mode, st.first_sel_bit, st.total_sel_bits);
+					const uint32_t n0 = st.total_sel_bits < 64 ? st.total_sel_bits : 64;
+					st.cur_sel_bits = bits_read(st.bits, st.first_sel_bit, n0);
+					if (st.cur_rms_err >= p.skip_block_rms_thresh) state = PRO_SKIP;
+				}
+				if ((tid & 31) == 0)
+				{
+					prologue& P = s_pro[tid >> 5];
+					P.state = state;
+					if (state == PRO_OK || state == PRO_SKIP)
+					{
+						P.st = st;
+						for (int k = 0; k < 16; k++) P.px[k] = px[k];
+					}
+				}
+			}
 		}
-		st.smooth_scale = rdo_smooth_scale(p, px);
-		bc7_endpoints_of(T, st.cur, st.bc7);
-		const uint64_t cur_err = rdo_block_error(T, st.cur, st.bc7, px);
-		st.cur_ms_err = (float)cur_err * (1.0f / 64.0f);
-		st.cur_rms_err = sqrtf(st.cur_ms_err);
-		mode_selector_field(st.cur.mode, st.first_sel_bit, st.total_sel_bits);
-		const uint32_t n0 = st.total_sel_bits < 64 ? st.total_sel_bits : 64;
-		st.cur_sel_bits = bits_read(st.bits, st.first_sel_bit, n0);
+		__syncthreads();
 
-		if (st.cur_rms_err >= p.skip_block_rms_thresh)
+	for (uint32_t bi = base; bi < last && bi < base + RDO_THREADS / 32; bi++)
+	{
+		const prologue& P = s_pro[bi - base];
+		if (P.state == PRO_BAD) { if (!tid) *failed = 1; return; }
+		if (P.state == PRO_SOLID) continue;
+		const rdo_step st = P.st;
+		uint32_t px[16];
+		for (int k = 0; k < 16; k++) px[k] = P.px[k];
+		const uint32_t n0 = st.total_sel_bits < 64 ? st.total_sel_bits : 64;
+
+		if (P.state == PRO_SKIP)
 		{
 			if (!tid) hist_set(hist, hmask, st.first_sel_bit, st.cur_sel_bits, bi);
 			__syncthreads();
@@ -156,6 +191,8 @@ __global__ void __launch_bounds__(RDO_THREADS) k_rdo_chain(uint4* blocks, const 
 			}
 		}
 		__syncthreads();
+	}
+		__syncthreads(); // s_pro is rewritten by the next batch
 	}
 }
 
