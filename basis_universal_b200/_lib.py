@@ -63,6 +63,10 @@ def lib():
         L.b200_uastc_unpack_blocks.argtypes = [vp, vp, u32, vp]
         L.b200_uastc_unpack_blocks_device.restype = i32
         L.b200_uastc_unpack_blocks_device.argtypes = [vp, vp, u32, vp]
+        L.b200_etc1_unpack_blocks.restype = i32
+        L.b200_etc1_unpack_blocks.argtypes = [vp, vp, u32, vp]
+        L.b200_etc1_unpack_blocks_device.restype = i32
+        L.b200_etc1_unpack_blocks_device.argtypes = [vp, vp, u32, vp]
         L.b200_block_metrics_device.restype = i32
         L.b200_block_metrics_device.argtypes = [vp, vp, vp, u32, u32, vp]
         L.b200_etc1s_set_flavour.restype = i32
@@ -88,7 +92,7 @@ EXPORTS = [
     "b200_uastc_encode_blocks", "b200_uastc_encode_blocks_device", "b200_uastc_encode_image", "b200_uastc_rdo",
     "b200_etc1s_set_flavour", "b200_etc1s_set_pixel_blocks", "b200_etc1s_endpoint_histogram", "b200_etc1s_endpoint_histogram_device",
     "b200_etc1s_selector_training", "b200_etc1s_selector_training_device",
-    "b200_extract_source_blocks", "b200_extract_source_blocks_device", "b200_uastc_unpack_blocks", "b200_uastc_unpack_blocks_device", "b200_block_metrics_device", "b200_etc1s_encode_blocks", "b200_etc1s_encode_pixel_clusters",
+    "b200_extract_source_blocks", "b200_extract_source_blocks_device", "b200_uastc_unpack_blocks", "b200_uastc_unpack_blocks_device", "b200_block_metrics_device", "b200_etc1_unpack_blocks", "b200_etc1_unpack_blocks_device", "b200_etc1s_encode_blocks", "b200_etc1s_encode_pixel_clusters",
     "b200_etc1s_refine_endpoint_clusterization", "b200_etc1s_find_optimal_selector_clusters_for_each_block",
     "b200_etc1s_determine_selectors", "b200_last_kernel_ms", "b200_last_launch_count", "b200_last_stage_ms",
     "b200_timer_start", "b200_timer_stop_ms", "b200_global_launch_count",

@@ -55,6 +55,54 @@ __global__ void __launch_bounds__(128) k_unpack_uastc(const uint4* __restrict__ 
 	for (int r = 0; r < 4; r++) dst[r] = make_uint4(px[r * 4], px[r * 4 + 1], px[r * 4 + 2], px[r * 4 + 3]);
 }
 
+// ETC1 block -> 16 RGBA texels: basisu::unpack_etc1(block, pDst, preserve_alpha = false) (encoder/basisu_etc.cpp:604). Handles
+// the whole ETC1 format (individual and differential colours, both flip orientations), not only the ETC1S subset.
+__global__ void __launch_bounds__(256) k_unpack_etc1(const uint2* __restrict__ eblocks, uint32_t n, uint4* __restrict__ out, int* failed)
+{
+	const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= n) return;
+	const uint2 w = __ldg(eblocks + i);
+	const uint32_t b[3] = { w.x & 255u, (w.x >> 8) & 255u, (w.x >> 16) & 255u }, b3 = w.x >> 24;
+	const bool diff = (b3 & 2u) != 0, flip = (b3 & 1u) != 0;
+	const uint32_t table[2] = { b3 >> 5, (b3 >> 2) & 7u };
+	int base[2][3];
+	bool ok = true;
+	for (int c = 0; c < 3; c++)
+	{
+		if (diff)
+		{
+			const int c5 = (int)(b[c] >> 3);
+			int d = (int)(b[c] & 7u); if (d >= 4) d -= 8;
+			int c5b = c5 + d;
+			if ((unsigned)c5b > 31u) { ok = false; c5b = clampi(c5b, 0, 31); } // unpack_color5 (etc.cpp:413): clamp and report
+			base[0][c] = (c5 << 3) | (c5 >> 2);
+			base[1][c] = (c5b << 3) | (c5b >> 2);
+		}
+		else
+		{
+			const int c4a = (int)(b[c] >> 4), c4b = (int)(b[c] & 15u);
+			base[0][c] = (c4a << 4) | c4a;
+			base[1][c] = (c4b << 4) | c4b;
+		}
+	}
+	if (!ok) *failed = 1;
+	const uint32_t msb = ((w.y & 255u) << 8) | ((w.y >> 8) & 255u), lsb = (((w.y >> 16) & 255u) << 8) | (w.y >> 24);
+	uint32_t px[16];
+	for (uint32_t y = 0; y < 4; y++)
+		for (uint32_t x = 0; x < 4; x++)
+		{
+			const uint32_t bit = x * 4 + y;
+			const uint32_t raw = (((msb >> bit) & 1u) << 1) | ((lsb >> bit) & 1u);
+			const uint32_t sel = (0x1Eu >> (raw * 2)) & 3u; // g_etc1_to_selector_index = { 2, 3, 1, 0 }
+			const uint32_t sub = flip ? (y >> 1) : (x >> 1);
+			const int m = d_tables.etc1_inten[table[sub] * 4 + sel];
+			px[x + y * 4] = px_make((uint32_t)clamp255i(base[sub][0] + m), (uint32_t)clamp255i(base[sub][1] + m), (uint32_t)clamp255i(base[sub][2] + m), 255u);
+		}
+	uint4* dst = out + (size_t)i * 4;
+#pragma unroll
+	for (int r = 0; r < 4; r++) dst[r] = make_uint4(px[r * 4], px[r * 4 + 1], px[r * 4 + 2], px[r * 4 + 3]);
+}
+
 // hist[6][256]: R, G, B, A, 709 luma, 601 luma; sums[8]: per-channel sums of a then of b (image_metrics::m_sum_a / m_sum_b).
 // CTA-private histograms in shared memory, flushed with one atomic per non-empty bin.
 __global__ void __launch_bounds__(256) k_block_metrics(const uint4* __restrict__ a, const uint4* __restrict__ b, uint32_t nbx, uint32_t nby, uint32_t width, uint32_t height,
@@ -209,4 +257,35 @@ extern "C" int b200_uastc_encode_image(b200_context* ctx, const void* pRGBA, uin
 	ctx->launches += 1; // the ingest kernel
 	B200_CUDA_OK(ctx, cudaMemcpy(pOut, ctx->d_out, (size_t)n * 16, cudaMemcpyDeviceToHost));
 	return 1;
+}
+
+extern "C" int b200_etc1_unpack_blocks_device(b200_context* ctx, const void* dEtc1, uint32_t num_blocks, void* dRGBA_blocks)
+{
+	if (!ctx || !ctx->activate()) return 0;
+	if (!num_blocks) { ctx->last_ms = 0; return 1; }
+	if (!ctx->reserve(ctx->d_aux[5], ctx->aux_cap[5], 256)) return 0;
+	int* d_failed = static_cast<int*>(ctx->d_aux[5]);
+	B200_CUDA_OK(ctx, cudaMemsetAsync(d_failed, 0, sizeof(int), ctx->stream));
+	if (!timed_begin(ctx)) return 0;
+	k_unpack_etc1<<<(num_blocks + 255) / 256, 256, 0, ctx->stream>>>(static_cast<const uint2*>(dEtc1), num_blocks, static_cast<uint4*>(dRGBA_blocks), d_failed);
+	count_launch(ctx);
+	B200_CUDA_OK(ctx, cudaGetLastError());
+	if (!timed_end(ctx)) { ctx->fail("b200_etc1_unpack_blocks: kernel failed"); return 0; }
+	int h_failed = 0;
+	B200_CUDA_OK(ctx, cudaMemcpy(&h_failed, d_failed, sizeof(int), cudaMemcpyDeviceToHost));
+	if (h_failed) { ctx->fail("b200_etc1_unpack_blocks: a differential base colour overflowed (unpack_etc1 returned false); texels were clamped"); return 0; }
+	return 1;
+}
+
+extern "C" int b200_etc1_unpack_blocks(b200_context* ctx, const void* pEtc1, uint32_t num_blocks, void* pRGBA_blocks)
+{
+	if (!ctx || !ctx->activate()) return 0;
+	if (!num_blocks) { ctx->last_ms = 0; return 1; }
+	if (!pEtc1 || !pRGBA_blocks) { ctx->fail("b200_etc1_unpack_blocks: null buffer"); return 0; }
+	if (!ctx->reserve(ctx->d_out, ctx->out_cap, (size_t)num_blocks * 8)) return 0;
+	if (!ctx->reserve(ctx->d_in, ctx->in_cap, (size_t)num_blocks * 64)) return 0;
+	B200_CUDA_OK(ctx, cudaMemcpyAsync(ctx->d_out, pEtc1, (size_t)num_blocks * 8, cudaMemcpyHostToDevice, ctx->stream));
+	const int ok = b200_etc1_unpack_blocks_device(ctx, ctx->d_out, num_blocks, ctx->d_in);
+	B200_CUDA_OK(ctx, cudaMemcpy(pRGBA_blocks, ctx->d_in, (size_t)num_blocks * 64, cudaMemcpyDeviceToHost)); // texels are defined (clamped) even then
+	return ok;
 }

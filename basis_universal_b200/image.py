@@ -58,6 +58,16 @@ class ImageOps:
         self._check(self._lib.b200_uastc_unpack_blocks(self._ctx, _p(u), u.shape[0], _p(out)), "b200_uastc_unpack_blocks")
         return out
 
+    def unpack_etc1(self, eblocks, strict=True):
+        """(N, 8) uint8 ETC1 blocks -> (N, 64) uint8 RGBA texels. strict=False returns the (clamped) texels even when a block's
+        differential colour overflows, as basisu::unpack_etc1 does while returning false."""
+        e = np.ascontiguousarray(eblocks, np.uint8).reshape(-1, 8)
+        out = np.empty((e.shape[0], 64), np.uint8)
+        ok = self._lib.b200_etc1_unpack_blocks(self._ctx, _p(e), e.shape[0], _p(out))
+        if strict:
+            self._check(ok, "b200_etc1_unpack_blocks")
+        return out
+
     def block_metrics_device(self, d_blocks_a, d_blocks_b, width, height):
         """Device pointers to two block arrays of a width x height image -> (hist (6, 256) uint64, sum_a (4,), sum_b (4,))."""
         m = _BlockMetrics()

@@ -144,6 +144,13 @@ int b200_extract_source_blocks_device(b200_context* ctx, const void* dRGBA, uint
 int b200_uastc_unpack_blocks(b200_context* ctx, const void* pUastc_blocks, uint32_t num_blocks, void* pRGBA_blocks);
 int b200_uastc_unpack_blocks_device(b200_context* ctx, const void* dUastc_blocks, uint32_t num_blocks, void* dRGBA_blocks);
 
+/* Decode ETC1 blocks (the whole format, of which the frontend's ETC1S blocks are a subset) to 16 RGBA8 texels each:
+ * bool basisu::unpack_etc1(const etc_block&, color_rgba* pDst, bool preserve_alpha = false) (encoder/basisu_etc.cpp:604).
+ * Returns 0 if a differential base colour overflowed in some block (the reference returns false for it); the texels are
+ * written, clamped, exactly as the reference writes them. */
+int b200_etc1_unpack_blocks(b200_context* ctx, const void* pEtc1_blocks, uint32_t num_blocks, void* pRGBA_blocks);
+int b200_etc1_unpack_blocks_device(b200_context* ctx, const void* dEtc1_blocks, uint32_t num_blocks, void* dRGBA_blocks);
+
 /* The integer part of image_metrics::calc(const image& a, const image& b, ...) (encoder/basisu_enc.cpp:2155) for two images
  * held as block arrays of a width x height image: histograms of |a - b| per channel and of the 709 / 601 luma difference over
  * the texels inside the image (padding texels of edge blocks are not counted), plus the channel sums. The caller finishes

@@ -122,3 +122,26 @@ def test_encode_image_equals_extract_then_encode(ops, ref, shape):
     assert enc.last_launch_count >= 4
     enc.close()
     assert np.array_equal(got, ref.encode_uastc(ref_extract(ref, img), 2))
+
+
+def test_unpack_etc1_matches_reference(ops, ref):
+    """Arbitrary ETC1 bit patterns (individual / differential, flipped or not, overflowing deltas) and real ETC1S blocks."""
+    import ctypes
+    from basis_universal_b200 import etc1s
+    rnd = np.random.default_rng(12).integers(0, 256, (20000, 8), dtype=np.uint8)
+    c = etc1s.Etc1sContext(0)
+    c.set_pixel_blocks(util.image_to_blocks(util.synth(256, 8)))
+    real = c.encode_etc1s_blocks(True, 16)
+    c.close()
+    for e in (rnd, real):
+        want = np.zeros((e.shape[0], 64), np.uint8)
+        ref.lib.ref_unpack_etc1_blocks(util._ptr(np.ascontiguousarray(e)), ctypes.c_uint32(e.shape[0]), util._ptr(want))
+        assert np.array_equal(ops.unpack_etc1(e, strict=False), want)
+    assert ops.unpack_etc1(real).shape == (real.shape[0], 64)           # ETC1S blocks never overflow
+    d = rnd[:, :3].astype(np.int32)
+    delta = np.where((d & 7) >= 4, (d & 7) - 8, d & 7)
+    overflow = ((rnd[:, 3] & 2) != 0) & ((((d >> 3) + delta) < 0) | (((d >> 3) + delta) > 31)).any(1)
+    assert overflow.any()
+    with pytest.raises(Exception):
+        ops.unpack_etc1(rnd)
+    assert ops.unpack_etc1(rnd[~overflow]).shape[0] == int((~overflow).sum())
