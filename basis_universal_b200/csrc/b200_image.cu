@@ -74,7 +74,7 @@ __global__ void __launch_bounds__(256) k_unpack_etc1(const uint2* __restrict__ e
 			const int c5 = (int)(b[c] >> 3);
 			int d = (int)(b[c] & 7u); if (d >= 4) d -= 8;
 			int c5b = c5 + d;
-			if ((unsigned)c5b > 31u) { ok = false; c5b = clampi(c5b, 0, 31); } // unpack_color5 (etc.cpp:413): clamp and report
+			if ((unsigned)c5b > 31u) { ok = false; c5b = clampi(c5b, 0, 31); } // unpack_color5 (etc.cpp:413) reports this
 			base[0][c] = (c5 << 3) | (c5 >> 2);
 			base[1][c] = (c5b << 3) | (c5b >> 2);
 		}
@@ -96,7 +96,8 @@ __global__ void __launch_bounds__(256) k_unpack_etc1(const uint2* __restrict__ e
 			const uint32_t sel = (0x1Eu >> (raw * 2)) & 3u; // g_etc1_to_selector_index = { 2, 3, 1, 0 }
 			const uint32_t sub = flip ? (y >> 1) : (x >> 1);
 			const int m = d_tables.etc1_inten[table[sub] * 4 + sel];
-			px[x + y * 4] = px_make((uint32_t)clamp255i(base[sub][0] + m), (uint32_t)clamp255i(base[sub][1] + m), (uint32_t)clamp255i(base[sub][2] + m), 255u);
+			// an overflowing block: unpack_etc1 returns false before writing any texel (etc.cpp:620); zeros are written here
+			px[x + y * 4] = ok ? px_make((uint32_t)clamp255i(base[sub][0] + m), (uint32_t)clamp255i(base[sub][1] + m), (uint32_t)clamp255i(base[sub][2] + m), 255u) : 0u;
 		}
 	uint4* dst = out + (size_t)i * 4;
 #pragma unroll
@@ -273,7 +274,7 @@ extern "C" int b200_etc1_unpack_blocks_device(b200_context* ctx, const void* dEt
 	if (!timed_end(ctx)) { ctx->fail("b200_etc1_unpack_blocks: kernel failed"); return 0; }
 	int h_failed = 0;
 	B200_CUDA_OK(ctx, cudaMemcpy(&h_failed, d_failed, sizeof(int), cudaMemcpyDeviceToHost));
-	if (h_failed) { ctx->fail("b200_etc1_unpack_blocks: a differential base colour overflowed (unpack_etc1 returned false); texels were clamped"); return 0; }
+	if (h_failed) { ctx->fail("b200_etc1_unpack_blocks: a differential base colour overflowed (unpack_etc1 returns false for that block); its texels were zeroed"); return 0; }
 	return 1;
 }
 
@@ -286,6 +287,6 @@ extern "C" int b200_etc1_unpack_blocks(b200_context* ctx, const void* pEtc1, uin
 	if (!ctx->reserve(ctx->d_in, ctx->in_cap, (size_t)num_blocks * 64)) return 0;
 	B200_CUDA_OK(ctx, cudaMemcpyAsync(ctx->d_out, pEtc1, (size_t)num_blocks * 8, cudaMemcpyHostToDevice, ctx->stream));
 	const int ok = b200_etc1_unpack_blocks_device(ctx, ctx->d_out, num_blocks, ctx->d_in);
-	B200_CUDA_OK(ctx, cudaMemcpy(pRGBA_blocks, ctx->d_in, (size_t)num_blocks * 64, cudaMemcpyDeviceToHost)); // texels are defined (clamped) even then
+	B200_CUDA_OK(ctx, cudaMemcpy(pRGBA_blocks, ctx->d_in, (size_t)num_blocks * 64, cudaMemcpyDeviceToHost)); // valid blocks are decoded even then
 	return ok;
 }

@@ -59,8 +59,8 @@ class ImageOps:
         return out
 
     def unpack_etc1(self, eblocks, strict=True):
-        """(N, 8) uint8 ETC1 blocks -> (N, 64) uint8 RGBA texels. strict=False returns the (clamped) texels even when a block's
-        differential colour overflows, as basisu::unpack_etc1 does while returning false."""
+        """(N, 8) uint8 ETC1 blocks -> (N, 64) uint8 RGBA texels. strict=False returns the texels even when some block's
+        differential colour overflows (basisu::unpack_etc1 returns false for such a block and writes nothing: zeros here)."""
         e = np.ascontiguousarray(eblocks, np.uint8).reshape(-1, 8)
         out = np.empty((e.shape[0], 64), np.uint8)
         ok = self._lib.b200_etc1_unpack_blocks(self._ctx, _p(e), e.shape[0], _p(out))

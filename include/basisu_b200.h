@@ -146,8 +146,8 @@ int b200_uastc_unpack_blocks_device(b200_context* ctx, const void* dUastc_blocks
 
 /* Decode ETC1 blocks (the whole format, of which the frontend's ETC1S blocks are a subset) to 16 RGBA8 texels each:
  * bool basisu::unpack_etc1(const etc_block&, color_rgba* pDst, bool preserve_alpha = false) (encoder/basisu_etc.cpp:604).
- * Returns 0 if a differential base colour overflowed in some block (the reference returns false for it); the texels are
- * written, clamped, exactly as the reference writes them. */
+ * Returns 0 if a differential base colour overflowed in some block: the reference returns false for such a block without
+ * writing its texels; here they are written as zeros, and every valid block is decoded regardless. */
 int b200_etc1_unpack_blocks(b200_context* ctx, const void* pEtc1_blocks, uint32_t num_blocks, void* pRGBA_blocks);
 int b200_etc1_unpack_blocks_device(b200_context* ctx, const void* dEtc1_blocks, uint32_t num_blocks, void* dRGBA_blocks);
 
