@@ -35,7 +35,9 @@ class uastc_rdo_params(ctypes.Structure):
 
 def extract_blocks(image):
     """(H, W, 4) uint8 -> (num_blocks, 64) uint8 in raster block order; edge texels are clamped like
-    image::extract_block_clamped (encoder/basisu_enc.h:3168)."""
+    image::extract_block_clamped (encoder/basisu_enc.h:3168). Plain numpy tiling for callers that marshal pixel_blocks on the
+    host, as the reference's compressor does; it is not used by any encode call (the device form is
+    image.ImageOps.extract_source_blocks, or Encoder.encode_image which ingests and encodes in one call)."""
     image = np.asarray(image, np.uint8)
     h, w, c = image.shape
     if c != 4:
