@@ -157,3 +157,14 @@ def test_hostemu_matches_golden_real_images(emu, golden_real, flags):
 
 def test_oracle_reproduces_golden_real_images(ref, golden_real):
     assert np.array_equal(ref.encode_uastc(golden_real["blocks"][::8], 2), golden_real["uastc_flags_2"][::8])
+
+
+def test_python_wrappers_raise_without_a_gpu():
+    """No silent CPU path: on a machine without a CUDA device every wrapper constructor fails with the library's message."""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    from basis_universal_b200 import B200Error, etc1s, image, uastc
+    for ctor in (uastc.Encoder, etc1s.Etc1sContext, image.ImageOps):
+        with pytest.raises(B200Error):
+            ctor(0)
