@@ -546,7 +546,8 @@ const bu_tables* T, uint32_t wbits, uint32_t comps, const uint32_t* px, uint32_t
 		// The reference scans the thresholds from the top for the first one <= d. They are non-decreasing (bounding-box
 		// endpoints: every channel of wc[] is non-decreasing in the weight, and a[] >= 0), so that index is a count.
 		uint32_t s = 0;
-		for (uint32_t j = 0; j < 7; j++) s += (d >= thresh[j]) ? 1u : 0u;
+		if (N == 4) s = ((d >= thresh[0]) ? 1u : 0u) + ((d >= thresh[1]) ? 1u : 0u) + ((d >= thresh[2]) ? 1u : 0u);
+		else for (uint32_t j = 0; j < 7; j++) s += (d >= thresh[j]) ? 1u : 0u;
 		total += dist_masked(wc[s], p, cmask);
 	}
 	return total;
