@@ -83,6 +83,12 @@ def lib():
         L.b200_etc1s_find_optimal_selector_clusters_for_each_block.argtypes = [vp, vp, u32, vp, vp, vp, i32]
         L.b200_etc1s_determine_selectors.restype = i32
         L.b200_etc1s_determine_selectors.argtypes = [vp, vp, vp, i32]
+        L.b200_tsvq_generate.restype = i32
+        L.b200_tsvq_generate.argtypes = [vp, u32, u32, vp, sz, sz, u32, u32, u32, i32, vp]
+        L.b200_etc1s_encode_endpoint_clusters.restype = i32
+        L.b200_etc1s_encode_endpoint_clusters.argtypes = [vp, vp, u32, vp, vp, i32, u32]
+        L.b200_etc1s_optimize_selector_codebook.restype = i32
+        L.b200_etc1s_optimize_selector_codebook.argtypes = [vp, vp, u32, vp, vp, vp, i32]
         _lib = L
     return _lib
 
@@ -96,4 +102,5 @@ EXPORTS = [
     "b200_etc1s_refine_endpoint_clusterization", "b200_etc1s_find_optimal_selector_clusters_for_each_block",
     "b200_etc1s_determine_selectors", "b200_last_kernel_ms", "b200_last_launch_count", "b200_last_stage_ms",
     "b200_timer_start", "b200_timer_stop_ms", "b200_global_launch_count",
+    "b200_tsvq_generate", "b200_etc1s_encode_endpoint_clusters", "b200_etc1s_optimize_selector_codebook",
 ]

@@ -34,11 +34,14 @@ extern "C" b200_context* b200_create_context(int device_index)
 	return ctx;
 }
 
+void b200_tsvq_release(b200_context* ctx); // b200_tsvq.cu
+
 extern "C" void b200_destroy_context(b200_context* ctx)
 {
 	if (!ctx) return;
 	cudaSetDevice(ctx->device);
 	cudaStreamSynchronize(ctx->stream);
+	b200_tsvq_release(ctx);
 	void* bufs[] = { ctx->d_in, ctx->d_out, ctx->d_meta, ctx->d_cands, ctx->d_slots, ctx->d_lists, ctx->d_etc_blocks };
 	for (void* p : bufs) if (p) cudaFree(p);
 	for (void* p : ctx->d_aux) if (p) cudaFree(p);

@@ -60,11 +60,27 @@ __device__ __forceinline__ uint64_t warp_sum_u64(uint64_t v)
 	return v;
 }
 
+// Where a cluster's texels come from: an explicit (texel, weight) list (the reference's seam), or the cluster's blocks read in
+// place from the resident source-block array, every texel with weight 1 (b200_etc1s_encode_endpoint_clusters).
+struct px_list_src
+{
+	const uint32_t* __restrict__ px; const uint32_t* __restrict__ wts; uint64_t n;
+	__device__ __forceinline__ uint32_t pixel(uint64_t i) const { return px[i]; }
+	__device__ __forceinline__ uint32_t weight(uint64_t i) const { return wts[i]; }
+};
+struct px_blocks_src
+{
+	const uint32_t* __restrict__ blocks; const uint32_t* __restrict__ bidx; uint64_t n; // n = 16 * number of blocks
+	__device__ __forceinline__ uint32_t pixel(uint64_t i) const { return __ldg(blocks + (size_t)__ldg(bidx + (i >> 4)) * 16 + (i & 15)); }
+	__device__ __forceinline__ uint32_t weight(uint64_t) const { return 1u; }
+};
+
 // Weighted error of base colour (r5,g5,b5) against the cluster's texels for every non-pruned intensity table; returns the
 // best (first strictly smaller) table and its error. Uniform across the warp.
-__device__ void cluster_evaluate(const bu_tables* T, bool perceptual, const uint32_t* __restrict__ px, const uint32_t* __restrict__ wts, uint64_t n,
+template<typename Src> __device__ void cluster_evaluate(const bu_tables* T, bool perceptual, const Src& src,
 	uint32_t lane, uint32_t spread, uint32_t r5, uint32_t g5, uint32_t b5, etc1s_solution& best, bool prune)
 {
+	const uint64_t n = src.n;
 	uint64_t trial_err = (uint64_t)INT64_MAX;
 	uint32_t trial_inten = 0;
 	bool valid = false;
@@ -76,12 +92,12 @@ __device__ void cluster_evaluate(const bu_tables* T, bool perceptual, const uint
 		uint64_t total = 0;
 		for (uint64_t i = lane; i < n; i += 32)
 		{
-			const uint32_t p = px[i];
+			const uint32_t p = src.pixel(i);
 			uint32_t be = etc_color_distance(perceptual, p, colors[0]);
 			be = min(be, etc_color_distance(perceptual, p, colors[1]));
 			be = min(be, etc_color_distance(perceptual, p, colors[2]));
 			be = min(be, etc_color_distance(perceptual, p, colors[3]));
-			total += (uint64_t)be * (uint64_t)wts[i];
+			total += (uint64_t)be * (uint64_t)src.weight(i);
 		}
 		total = warp_sum_u64(total);
 		if (total < trial_err) { trial_err = total; trial_inten = inten; valid = true; }
@@ -101,23 +117,16 @@ __device__ __forceinline__ bool warp_bloom_test_and_set(uint32_t& my_word, uint3
 	return true;
 }
 
-__global__ void __launch_bounds__(128) k_etc1s_pixel_clusters(const b200_pixel_cluster* __restrict__ clusters, uint32_t total_clusters,
-	const uint32_t* __restrict__ pixels, const uint32_t* __restrict__ weights, uint64_t* __restrict__ out, int perceptual_i, uint32_t total_perms, int flavour)
+// One warp optimises one cluster (etc1_optimizer over the cluster's texels); returns the packed base colour + intensity table.
+template<typename Src> __device__ uint64_t cluster_optimize(const bu_tables* T, bool perceptual, const Src& src, uint32_t lane, uint32_t total_perms, int flavour)
 {
-	const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
-	if (warp >= total_clusters) return;
-	const bu_tables* T = &d_tables;
-	const bool perceptual = perceptual_i != 0;
-	const uint64_t n = clusters[warp].total_pixels;
-	const uint32_t* px = pixels + clusters[warp].first_pixel_index;
-	const uint32_t* wts = weights + clusters[warp].first_pixel_index;
-
+	const uint64_t n = src.n;
 	uint32_t mn[3] = { 255, 255, 255 }, mx[3] = { 0, 0, 0 };
 	uint64_t sum[3] = { 0, 0, 0 }, tw = 0;
 	for (uint64_t i = lane; i < n; i += 32)
 	{
-		const uint32_t p = px[i];
-		const uint64_t w = wts[i];
+		const uint32_t p = src.pixel(i);
+		const uint64_t w = src.weight(i);
 		for (uint32_t c = 0; c < 3; c++)
 		{
 			const uint32_t v = px_c(p, c);
@@ -149,17 +158,81 @@ __global__ void __launch_bounds__(128) k_etc1s_pixel_clusters(const b200_pixel_c
 	if (cpu) warp_bloom_test_and_set(bloom_word, lane, r0, g0, b0);
 	etc1s_solution best;
 	best.err = UINT64_MAX; best.r5 = best.g5 = best.b5 = best.inten = 0; best.lsb_plane = best.msb_plane = 0; best.valid = 0;
-	cluster_evaluate(T, perceptual, px, wts, n, lane, spread, r0, g0, b0, best, prune);
+	cluster_evaluate(T, perceptual, src, lane, spread, r0, g0, b0, best, prune);
 	if (best.err != 0)
 		for (uint32_t perm = 0; perm < total_perms; perm++)
 		{
 			uint32_t r1, g1, b1;
 			if (!etc1s_cluster_fit_step(T, best, avg, perm, r1, g1, b1, flavour)) continue;
 			if (cpu && !warp_bloom_test_and_set(bloom_word, lane, r1, g1, b1)) continue;
-			cluster_evaluate(T, perceptual, px, wts, n, lane, spread, r1, g1, b1, best, prune);
+			cluster_evaluate(T, perceptual, src, lane, spread, r1, g1, b1, best, prune);
 			if (best.err == 0) break;
 		}
-	if (lane == 0) out[warp] = etc1s_pack(best.r5, best.g5, best.b5, best.inten, 0, 0); // the kernel defines no selectors for clusters
+	return etc1s_pack(best.r5, best.g5, best.b5, best.inten, 0, 0); // the kernel defines no selectors for clusters
+}
+
+__global__ void __launch_bounds__(128) k_etc1s_pixel_clusters(const b200_pixel_cluster* __restrict__ clusters, uint32_t total_clusters,
+	const uint32_t* __restrict__ pixels, const uint32_t* __restrict__ weights, uint64_t* __restrict__ out, int perceptual_i, uint32_t total_perms, int flavour)
+{
+	const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+	if (warp >= total_clusters) return;
+	px_list_src src;
+	src.px = pixels + clusters[warp].first_pixel_index; src.wts = weights + clusters[warp].first_pixel_index; src.n = clusters[warp].total_pixels;
+	const uint64_t r = cluster_optimize(&d_tables, perceptual_i != 0, src, lane, total_perms, flavour);
+	if (lane == 0) out[warp] = r;
+}
+
+// Endpoint clusters as CSR lists of block indices into the resident source blocks; `order` lists the clusters largest first
+// so that the long ones start early (a cluster is one warp's serial work).
+__global__ void __launch_bounds__(128) k_etc1s_endpoint_clusters(const uint32_t* __restrict__ blocks, const uint32_t* __restrict__ offsets, const uint32_t* __restrict__ bidx,
+	const uint32_t* __restrict__ order, uint32_t total_clusters, uint64_t* __restrict__ out, int perceptual_i, uint32_t total_perms, int flavour)
+{
+	const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+	if (warp >= total_clusters) return;
+	const uint32_t c = order[warp];
+	px_blocks_src src;
+	src.blocks = blocks; src.bidx = bidx + offsets[c]; src.n = (uint64_t)(offsets[c + 1] - offsets[c]) * 16;
+	uint64_t r = 0;
+	if (src.n) r = cluster_optimize(&d_tables, perceptual_i != 0, src, lane, total_perms, flavour);
+	if (lane == 0) out[c] = r;
+}
+
+// ---- create_optimized_selector_codebook: one warp per selector cluster ---------------------------------------------------------
+// Lane = (half, texel): the two half-warps take alternate member blocks; each lane accumulates, for its texel, the error of the
+// four block colours of every member block (decoded from the block's own endpoint) against the source texel.
+__global__ void __launch_bounds__(128) k_etc1s_selector_codebook(const uint32_t* __restrict__ blocks, const uint2* __restrict__ etc_blocks, const uint32_t* __restrict__ offsets,
+	const uint32_t* __restrict__ bidx, uint32_t total_clusters, uint32_t* __restrict__ out, int perceptual_i)
+{
+	const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+	if (warp >= total_clusters) return;
+	const bool perceptual = perceptual_i != 0;
+	const uint32_t first = offsets[warp], last = offsets[warp + 1];
+	const uint32_t texel = lane & 15; // x + 4 * y
+	uint64_t err[4] = { 0, 0, 0, 0 };
+	for (uint32_t k = first + (lane >> 4); k < last; k += 2)
+	{
+		const uint32_t bi = __ldg(bidx + k);
+		const uint32_t w = __ldg(&etc_blocks[bi]).x; // bytes 0..3: R5<<3 | dR3, G5<<3 | dG3, B5<<3 | dB3, inten0<<5 | inten1<<2 | diff | flip
+		uint32_t colors[4];
+		etc1s_block_colors(&d_tables, (w >> 3) & 31, (w >> 11) & 31, (w >> 19) & 31, (w >> 29) & 7, colors); // get_block_colors(., 0): subblock 0's base + table
+		const uint32_t p = __ldg(blocks + (size_t)bi * 16 + texel);
+#pragma unroll
+		for (int s = 0; s < 4; s++) err[s] += etc_color_distance(perceptual, colors[s], p);
+	}
+	uint32_t best = 0;
+	uint64_t best_err = 0;
+#pragma unroll
+	for (int s = 0; s < 4; s++)
+	{
+		uint32_t lo = (uint32_t)err[s], hi = (uint32_t)(err[s] >> 32);
+		lo = __shfl_xor_sync(0xffffffffu, lo, 16); hi = __shfl_xor_sync(0xffffffffu, hi, 16);
+		const uint64_t e = err[s] + (((uint64_t)hi << 32) | lo);
+		if (s == 0 || e < best_err) { best_err = e; best = (uint32_t)s; } // first strictly smaller (frontend.cpp:2326-2336)
+	}
+	uint32_t packed = (lane < 16) ? (best << (texel * 2)) : 0u;
+#pragma unroll
+	for (int m = 8; m >= 1; m >>= 1) packed |= __shfl_xor_sync(0xffffffffu, packed, m);
+	if (lane == 0) out[warp] = (first == last) ? 0u : packed;
 }
 
 // ---- refine_endpoint_clusterization ------------------------------------------------------------------------------------------
@@ -473,4 +546,61 @@ extern "C" int b200_etc1s_selector_training(b200_context* ctx, const void* pEtc_
 	B200_CUDA_OK(ctx, cudaMemcpy(pKeys, dk, (size_t)num_blocks * 4, cudaMemcpyDeviceToHost));
 	B200_CUDA_OK(ctx, cudaMemcpy(pWeights, dk + num_blocks, (size_t)num_blocks * 4, cudaMemcpyDeviceToHost));
 	return 1;
+}
+
+extern "C" int b200_etc1s_encode_endpoint_clusters(b200_context* ctx, void* pOutput_blocks, uint32_t total_clusters, const uint32_t* pCluster_offsets,
+	const uint32_t* pCluster_block_indices, int perceptual, uint32_t total_perms)
+{
+	ETC_CHECK_BLOCKS(ctx, "b200_etc1s_encode_endpoint_clusters");
+	if (!total_clusters) return 1;
+	if (total_perms > 165) { ctx->fail("b200_etc1s_encode_endpoint_clusters: total_perms > 165"); return 0; }
+	if (!pOutput_blocks || !pCluster_offsets || !pCluster_block_indices) { ctx->fail("b200_etc1s_encode_endpoint_clusters: null buffer"); return 0; }
+	const uint32_t total_indices = pCluster_offsets[total_clusters];
+	for (uint32_t i = 0; i < total_indices; i++)
+		if (pCluster_block_indices[i] >= ctx->etc_total_blocks) { ctx->fail("b200_etc1s_encode_endpoint_clusters: block index out of range"); return 0; }
+	// Launch order: clusters bucketed by size class (floor(log2(size))), largest class first
+	uint32_t* order = static_cast<uint32_t*>(malloc((size_t)total_clusters * 4));
+	if (!order) { ctx->fail("b200_etc1s_encode_endpoint_clusters: out of host memory"); return 0; }
+	{
+		uint32_t counts[33] = { 0 }, ofs[33];
+		auto cls = [&](uint32_t c) { const uint32_t sz = pCluster_offsets[c + 1] - pCluster_offsets[c]; uint32_t b = 0; while (b < 32 && (1u << b) <= sz) b++; return 32 - b; };
+		for (uint32_t i = 0; i < total_clusters; i++) counts[cls(i)]++;
+		uint32_t acc = 0;
+		for (int b = 0; b < 33; b++) { ofs[b] = acc; acc += counts[b]; }
+		for (uint32_t i = 0; i < total_clusters; i++) order[ofs[cls(i)]++] = i;
+	}
+	bool ok = upload(ctx, 1, pCluster_offsets, ((size_t)total_clusters + 1) * 4) && upload(ctx, 2, pCluster_block_indices, (size_t)total_indices * 4) && upload(ctx, 3, order, (size_t)total_clusters * 4);
+	if (ok) ok = ctx->reserve(ctx->d_aux[0], ctx->aux_cap[0], (size_t)total_clusters * 8);
+	if (ok && cudaStreamSynchronize(ctx->stream) != cudaSuccess) ok = false; // `order` is pageable host memory about to be freed
+	free(order);
+	if (!ok) return 0;
+	ctx->launches = 1; __atomic_add_fetch(&g_b200_total_launches, 1, __ATOMIC_RELAXED);
+	B200_CUDA_OK(ctx, cudaEventRecord(ctx->ev0, ctx->stream));
+	const uint32_t warps_per_cta = 4;
+	k_etc1s_endpoint_clusters<<<(total_clusters + warps_per_cta - 1) / warps_per_cta, warps_per_cta * 32, 0, ctx->stream>>>(static_cast<const uint32_t*>(ctx->d_etc_blocks),
+		static_cast<const uint32_t*>(ctx->d_aux[1]), static_cast<const uint32_t*>(ctx->d_aux[2]), static_cast<const uint32_t*>(ctx->d_aux[3]), total_clusters,
+		static_cast<uint64_t*>(ctx->d_aux[0]), perceptual, total_perms, ctx->etc_flavour);
+	return finish(ctx, pOutput_blocks, 0, (size_t)total_clusters * 8);
+}
+
+extern "C" int b200_etc1s_optimize_selector_codebook(b200_context* ctx, const void* pEtc_blocks, uint32_t total_clusters, const uint32_t* pCluster_offsets,
+	const uint32_t* pCluster_block_indices, uint32_t* pOutput_selectors, int perceptual)
+{
+	ETC_CHECK_BLOCKS(ctx, "b200_etc1s_optimize_selector_codebook");
+	if (!total_clusters) return 1;
+	if (!pEtc_blocks || !pCluster_offsets || !pCluster_block_indices || !pOutput_selectors) { ctx->fail("b200_etc1s_optimize_selector_codebook: null buffer"); return 0; }
+	const uint32_t n = ctx->etc_total_blocks, total_indices = pCluster_offsets[total_clusters];
+	for (uint32_t i = 0; i < total_indices; i++)
+		if (pCluster_block_indices[i] >= n) { ctx->fail("b200_etc1s_optimize_selector_codebook: block index out of range"); return 0; }
+	if (!upload(ctx, 1, pEtc_blocks, (size_t)n * 8)) return 0;
+	if (!upload(ctx, 2, pCluster_offsets, ((size_t)total_clusters + 1) * 4)) return 0;
+	if (!upload(ctx, 3, pCluster_block_indices, (size_t)total_indices * 4)) return 0;
+	if (!ctx->reserve(ctx->d_aux[0], ctx->aux_cap[0], (size_t)total_clusters * 4)) return 0;
+	ctx->launches = 1; __atomic_add_fetch(&g_b200_total_launches, 1, __ATOMIC_RELAXED);
+	B200_CUDA_OK(ctx, cudaEventRecord(ctx->ev0, ctx->stream));
+	const uint32_t warps_per_cta = 4;
+	k_etc1s_selector_codebook<<<(total_clusters + warps_per_cta - 1) / warps_per_cta, warps_per_cta * 32, 0, ctx->stream>>>(static_cast<const uint32_t*>(ctx->d_etc_blocks),
+		static_cast<const uint2*>(ctx->d_aux[1]), static_cast<const uint32_t*>(ctx->d_aux[2]), static_cast<const uint32_t*>(ctx->d_aux[3]), total_clusters,
+		static_cast<uint32_t*>(ctx->d_aux[0]), perceptual);
+	return finish(ctx, pOutput_selectors, 0, (size_t)total_clusters * 4);
 }

@@ -157,11 +157,18 @@ static bool timed_end(b200_context* ctx)
 }
 static void count_launch(b200_context* ctx) { ctx->launches++; __atomic_add_fetch(&g_b200_total_launches, 1, __ATOMIC_RELAXED); }
 
+static bool raster_pitch_ok(b200_context* ctx, const char* who, uint32_t width, size_t pitch_bytes)
+{
+	if (pitch_bytes >= (size_t)width * 4 && !(pitch_bytes & 3)) return true;
+	snprintf(ctx->err, sizeof(ctx->err), "%s: pitch must be a multiple of 4 and >= width * 4", who);
+	return false;
+}
+
 extern "C" int b200_extract_source_blocks_device(b200_context* ctx, const void* dRGBA, uint32_t width, uint32_t height, size_t pitch_bytes, void* dBlocks)
 {
 	if (!ctx || !ctx->activate()) return 0;
 	if (!width || !height) { ctx->last_ms = 0; return 1; }
-	if (pitch_bytes < (size_t)width * 4 || (pitch_bytes & 3)) { ctx->fail("b200_extract_source_blocks: pitch must be a multiple of 4 and >= width * 4"); return 0; }
+	if (!raster_pitch_ok(ctx, "b200_extract_source_blocks", width, pitch_bytes)) return 0;
 	const uint32_t nbx = (width + 3) / 4, nby = (height + 3) / 4;
 	if (!timed_begin(ctx)) return 0;
 	k_extract_blocks<<<(nbx * nby + 255) / 256, 256, 0, ctx->stream>>>(static_cast<const uint8_t*>(dRGBA), width, height, pitch_bytes, nbx, nby, static_cast<uint4*>(dBlocks));
@@ -177,7 +184,9 @@ extern "C" int b200_extract_source_blocks(b200_context* ctx, const void* pRGBA, 
 	if (!width || !height) { ctx->last_ms = 0; return 1; }
 	if (!pRGBA || !pBlocks) { ctx->fail("b200_extract_source_blocks: null buffer"); return 0; }
 	const uint32_t nbx = (width + 3) / 4, nby = (height + 3) / 4;
-	const size_t in_bytes = pitch_bytes * height, out_bytes = (size_t)nbx * nby * 64;
+	if (!raster_pitch_ok(ctx, "b200_extract_source_blocks", width, pitch_bytes)) return 0;
+	// The last row only guarantees width * 4 valid bytes (a sub-rectangle of a larger image ends there).
+	const size_t in_bytes = pitch_bytes * (height - 1) + (size_t)width * 4, out_bytes = (size_t)nbx * nby * 64;
 	if (!ctx->reserve(ctx->d_aux[0], ctx->aux_cap[0], in_bytes)) return 0;
 	if (!ctx->reserve(ctx->d_in, ctx->in_cap, out_bytes)) return 0;
 	B200_CUDA_OK(ctx, cudaMemcpyAsync(ctx->d_aux[0], pRGBA, in_bytes, cudaMemcpyHostToDevice, ctx->stream));
@@ -246,7 +255,8 @@ extern "C" int b200_uastc_encode_image(b200_context* ctx, const void* pRGBA, uin
 	if (!width || !height) { ctx->last_ms = 0; ctx->launches = 0; return 1; }
 	if (!pRGBA || !pOut) { ctx->fail("b200_uastc_encode_image: null buffer"); return 0; }
 	const uint32_t nbx = (width + 3) / 4, nby = (height + 3) / 4, n = nbx * nby;
-	const size_t in_bytes = pitch_bytes * height;
+	if (!raster_pitch_ok(ctx, "b200_uastc_encode_image", width, pitch_bytes)) return 0;
+	const size_t in_bytes = pitch_bytes * (height - 1) + (size_t)width * 4; // see b200_extract_source_blocks
 	if (!ctx->reserve(ctx->d_aux[0], ctx->aux_cap[0], in_bytes)) return 0;
 	if (!ctx->reserve(ctx->d_in, ctx->in_cap, (size_t)n * 64)) return 0;
 	if (!ctx->reserve(ctx->d_out, ctx->out_cap, (size_t)n * 16)) return 0;

@@ -31,6 +31,7 @@ struct b200_context
 	// ETC1S: source blocks of the current slice (b200_etc1s_set_pixel_blocks)
 	void* d_etc_blocks; size_t etc_blocks_cap; uint32_t etc_total_blocks;
 	int etc_flavour; // B200_ETC1S_FLAVOUR_*
+	void* tsvq; // b200_tsvq.cu: host-side result storage + device scratch of b200_tsvq_generate
 
 	void fail(const char* msg) { snprintf(err, sizeof(err), "%s", msg); }
 	void fail_cuda(const char* what, cudaError_t e) { snprintf(err, sizeof(err), "%s: %s", what, cudaGetErrorString(e)); }

@@ -122,6 +122,70 @@ class Etc1sContext:
         return keys, weights
 
 
+class TsvqResult(ctypes.Structure):
+    """b200_tsvq_result (include/basisu_b200.h)"""
+    _fields_ = [("num_unique", ctypes.c_uint32), ("num_clusters", ctypes.c_uint32), ("cluster_offsets", ctypes.POINTER(ctypes.c_uint32)),
+                ("cluster_indices", ctypes.POINTER(ctypes.c_uint32)), ("num_parent_clusters", ctypes.c_uint32), ("parent_offsets", ctypes.POINTER(ctypes.c_uint32)),
+                ("parent_indices", ctypes.POINTER(ctypes.c_uint32)), ("rounds", ctypes.c_uint32), ("nodes_split", ctypes.c_uint32)]
+
+
+def _csr(clusters):
+    """list of index arrays -> (offsets (n+1,) uint32, indices uint32)"""
+    sizes = np.array([len(c) for c in clusters], np.uint32)
+    off = np.zeros(len(clusters) + 1, np.uint32)
+    np.cumsum(sizes, out=off[1:])
+    idx = np.concatenate([np.asarray(c, np.uint32) for c in clusters]) if len(clusters) and off[-1] else np.zeros(0, np.uint32)
+    return off, np.ascontiguousarray(idx, np.uint32)
+
+
+def _tsvq_generate(self, vecs, weights, max_codebook_size, max_parent_codebook_size=0, max_threads=1, even_odd_input_pairs_equal=False):
+    """generate_hierarchical_codebook_threaded (enc.h:2219) on the device. vecs: (N, 6) or (N, 16) float32, weights: (N,) uint64.
+    Returns (clusters, parent_clusters, info): lists of uint32 arrays of training-vector indices in the reference's order."""
+    vecs = np.ascontiguousarray(vecs, np.float32)
+    n, dim = vecs.shape
+    rec = np.zeros(n, np.dtype([("v", "<f4", (dim,)), ("w", "<u8")], align=True))  # the layout of std::pair<vecNF, uint64_t>
+    rec["v"] = vecs
+    rec["w"] = np.asarray(weights, np.uint64)
+    res = TsvqResult()
+    ok = self._lib.b200_tsvq_generate(self._ctx, dim, n, _p(rec), ctypes.c_size_t(rec.dtype.itemsize), ctypes.c_size_t(rec.dtype.fields["w"][1]),
+                                      int(max_codebook_size), int(max_parent_codebook_size), int(max_threads), int(bool(even_odd_input_pairs_equal)), ctypes.byref(res))
+    self._check(ok, "b200_tsvq_generate")
+
+    def unpack(count, off_p, idx_p):
+        if not count:
+            return []
+        off = np.ctypeslib.as_array(off_p, (count + 1,)).copy()
+        idx = np.ctypeslib.as_array(idx_p, (int(off[-1]),)).copy()
+        return [idx[off[i]:off[i + 1]] for i in range(count)]
+    info = {"num_unique": res.num_unique, "rounds": res.rounds, "nodes_split": res.nodes_split, "device_ms": self.last_kernel_ms}
+    return unpack(res.num_clusters, res.cluster_offsets, res.cluster_indices), unpack(res.num_parent_clusters, res.parent_offsets, res.parent_indices), info
+
+
+def _encode_endpoint_clusters(self, clusters, perceptual, total_perms):
+    """generate_endpoint_codebook step 0 (frontend.cpp:1214): clusters = list of block-index arrays -> (n, 8) uint8 etc_blocks (colour + intensity table)."""
+    off, idx = _csr(clusters)
+    out = np.zeros((len(clusters), 8), np.uint8)
+    self._check(self._lib.b200_etc1s_encode_endpoint_clusters(self._ctx, _p(out), len(clusters), _p(off), _p(idx), int(bool(perceptual)), int(total_perms)),
+                "b200_etc1s_encode_endpoint_clusters")
+    return out
+
+
+def _optimize_selector_codebook(self, etc_blocks, clusters, perceptual):
+    """create_optimized_selector_codebook (frontend.cpp:2259): -> (n,) uint32, texel (x, y) of cluster c at bits 2 * (x + 4 * y)."""
+    b = np.ascontiguousarray(etc_blocks, np.uint8)
+    assert b.shape == (self.total_blocks, 8)
+    off, idx = _csr(clusters)
+    out = np.zeros(len(clusters), np.uint32)
+    self._check(self._lib.b200_etc1s_optimize_selector_codebook(self._ctx, _p(b), len(clusters), _p(off), _p(idx), _p(out), int(bool(perceptual))),
+                "b200_etc1s_optimize_selector_codebook")
+    return out
+
+
+Etc1sContext.tsvq_generate = _tsvq_generate
+Etc1sContext.encode_endpoint_clusters = _encode_endpoint_clusters
+Etc1sContext.optimize_selector_codebook = _optimize_selector_codebook
+
+
 def merge_selector_training(keys, weights):
     """Unique keys in ascending order with summed weights: what the clusterer's duplicate merge leaves (enc.h:2228-2260)."""
     u, inv = np.unique(np.asarray(keys, np.uint32), return_inverse=True)
@@ -134,8 +198,9 @@ _INTEN_LOW_HIGH = np.array([[-8, 8], [-17, 17], [-29, 29], [-42, 42], [-60, 60],
 
 
 def training_vectors_from_histogram(hist):
-    """Global weighted unique endpoint training set from the (all-reduced) key histogram, as the reference builds it
-    (frontend.cpp:843-857): vec6F = (low rgb, high rgb) * (1/255), weight = count. Returned in ascending key order."""
+    """Endpoint training vectors from the (all-reduced) key histogram (frontend.cpp:843-857): per non-zero key, vec6F = (low rgb,
+    high rgb) * (1/255) and weight = count, in ascending key order. Distinct keys can give the same vector: merge_training_vectors
+    (or the device clusterer, which merges duplicates itself) produces the reference's unique set."""
     keys = np.nonzero(hist)[0].astype(np.uint32)
     r5, g5, b5, inten = (keys >> 13) & 31, (keys >> 8) & 31, (keys >> 3) & 31, keys & 7
     base = np.stack([(r5 << 3) | (r5 >> 2), (g5 << 3) | (g5 >> 2), (b5 << 3) | (b5 >> 2)], -1).astype(np.int32)
@@ -143,3 +208,12 @@ def training_vectors_from_histogram(hist):
     high = np.clip(base + _INTEN_LOW_HIGH[inten, 1:2], 0, 255)
     vecs = np.concatenate([low, high], -1).astype(np.float32) * np.float32(1.0 / 255.0)
     return keys, vecs, hist[keys].astype(np.uint64)
+
+
+def merge_training_vectors(vecs, weights):
+    """Distinct keys can clamp to the same vector (e.g. intensity table 7 around mid grey gives (0,0,0,1,1,1) for thousands of keys);
+    the clusterer's std::map merges those (enc.h:2228-2260). Returns the unique vectors in lexicographic order with summed weights."""
+    u, inv = np.unique(np.asarray(vecs, np.float32), axis=0, return_inverse=True)
+    w = np.zeros(u.shape[0], np.uint64)
+    np.add.at(w, inv.reshape(-1), np.asarray(weights, np.uint64))
+    return u, w

@@ -130,7 +130,7 @@ class Encoder:
         """(H, W, 4) uint8 raster (rows may be strided) -> (ceil(H/4) * ceil(W/4), 16) uint8 UASTC blocks: ingest and encode both on
         the device (b200_uastc_encode_image)."""
         img = image
-        if img.ndim != 3 or img.shape[2] != 4 or img.dtype != np.uint8 or img.strides[2] != 1 or img.strides[1] != 4:
+        if img.ndim != 3 or img.shape[2] != 4 or img.dtype != np.uint8 or img.strides[2] != 1 or img.strides[1] != 4 or img.strides[0] < img.shape[1] * 4:  # negative or overlapping row strides are copied
             img = np.ascontiguousarray(img, np.uint8)
         h, w = img.shape[:2]
         out = np.empty((((h + 3) // 4) * ((w + 3) // 4), 16), np.uint8)

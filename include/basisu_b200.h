@@ -111,6 +111,54 @@ int b200_etc1s_find_optimal_selector_clusters_for_each_block(b200_context* ctx, 
 /* opencl_determine_selectors (opencl.h:137). */
 int b200_etc1s_determine_selectors(b200_context* ctx, const void* pInput_etc_color5_and_inten, void* pOutput_blocks, int perceptual);
 
+/* ---- ETC1S codebook stages: the wider seam (no OpenCL counterpart in the reference) ------------------------------------------ */
+
+/* Tree-structured vector quantisation of a weighted training set: the device form of
+ *     template<typename Quantizer> bool basisu::generate_hierarchical_codebook_threaded(Quantizer& q, uint32_t max_codebook_size,
+ *         uint32_t max_parent_codebook_size, basisu::vector<uint_vec>& codebook, basisu::vector<uint_vec>& parent_codebook,
+ *         uint32_t max_threads, job_pool*, bool even_odd_input_pairs_equal)                      (encoder/basisu_enc.h:2219)
+ * with Quantizer = tree_vector_quant<vec6F> (endpoints, frontend.cpp:868) or <vec16F> (selectors, frontend.cpp:2140), i.e.
+ * dim = 6 or 16. Same algorithm: identical training vectors are merged in lexicographic order with summed weights
+ * (enc.h:2228-2260); the tree is grown best-first by node variance (tree_vector_quant::generate, enc.h:1631-1676), each split
+ * along the principal axis (enc.h:1802-1846) and refined by <= 6 k-means passes (enc.h:1962-2095); with >= 2^18 unique vectors
+ * and max_threads > 1 the two-level scheme of enc.h:2112-2214 (max_threads top clusters, one sub-tree each) is followed.
+ * The sums over a node's members are parallel reductions in a fixed order (deterministic, but not the reference's serial float
+ * order), so clusterings agree with the CPU up to float rounding; the ETC1S gate is +-0.02 dB PSNR, not bit-exactness.
+ *
+ * pTraining: HOST pointer to num_training records `stride_bytes` apart, each holding `dim` floats at offset 0 and a uint64_t
+ * weight at offset `weight_offset_bytes` (the layout of std::pair<vecNF, uint64_t>, passed as is).
+ * The result arrays are owned by the context and stay valid until the next b200_tsvq_generate call on it: clusters in the
+ * reference's order (leaf nodes by node index), each listing training-vector indices in the reference's order. */
+typedef struct b200_tsvq_result
+{
+	uint32_t num_unique;             /* unique training vectors after merging duplicates */
+	uint32_t num_clusters;           /* codebook.size() */
+	const uint32_t* cluster_offsets; /* num_clusters + 1 */
+	const uint32_t* cluster_indices; /* num_training training-vector indices */
+	uint32_t num_parent_clusters;    /* parent_codebook.size(); 0 if max_parent_codebook_size == 0 */
+	const uint32_t* parent_offsets;  /* num_parent_clusters + 1 */
+	const uint32_t* parent_indices;
+	uint32_t rounds, nodes_split;    /* instrumentation: device rounds and node splits computed (speculative ones included) */
+} b200_tsvq_result;
+int b200_tsvq_generate(b200_context* ctx, uint32_t dim, uint32_t num_training, const void* pTraining, size_t stride_bytes, size_t weight_offset_bytes,
+	uint32_t max_codebook_size, uint32_t max_parent_codebook_size, uint32_t max_threads, int even_odd_input_pairs_equal, b200_tsvq_result* pResult);
+
+/* basisu_frontend::generate_endpoint_codebook, step 0 (encoder/basisu_frontend.cpp:1214-1610): one ETC1S colour + intensity
+ * table per endpoint cluster, optimised over every texel of the cluster's blocks. Clusters arrive as CSR lists of block indices
+ * into the array given to b200_etc1s_set_pixel_blocks, so the host neither gathers nor de-duplicates texels (the reference's
+ * OpenCL path radix-sorts every cluster's texels on one host thread first, frontend.cpp:1250-1445). Output: one etc_block per
+ * cluster carrying base colour and intensity table, as opencl_encode_etc1s_pixel_clusters writes them. Same flavours as
+ * b200_etc1s_encode_pixel_clusters; the CPU_OPTIMIZER result equals the CPU etc1_optimizer's on the gathered texels. */
+int b200_etc1s_encode_endpoint_clusters(b200_context* ctx, void* pOutput_blocks, uint32_t total_clusters, const uint32_t* pCluster_offsets,
+	const uint32_t* pCluster_block_indices, int perceptual, uint32_t total_perms);
+
+/* basisu_frontend::create_optimized_selector_codebook (encoder/basisu_frontend.cpp:2259-2345): for every selector cluster and
+ * each of the 16 texels, the selector (0..3) minimising the summed colour error over the cluster's blocks, each block decoded
+ * with its own endpoint (pEtc_blocks: the frontend's m_encoded_blocks, 8 B each, all blocks of the slice). Output: one u32 per
+ * cluster, texel (x, y) at bits 2 * (x + 4 * y); 0 for an empty cluster (the reference leaves those entries untouched). */
+int b200_etc1s_optimize_selector_codebook(b200_context* ctx, const void* pEtc_blocks, uint32_t total_clusters, const uint32_t* pCluster_offsets,
+	const uint32_t* pCluster_block_indices, uint32_t* pOutput_selectors, int perceptual);
+
 /* ---- ETC1S multi-GPU exchange point -------------------------------------------------------------------------------------- */
 
 /* Histogram of the 18-bit endpoint training keys (r5<<13 | g5<<8 | b5<<3 | inten) of `num_blocks` ETC1S blocks, each block

@@ -6,7 +6,7 @@
 // ETC1S frontend's five per-block stages on the B200, with zero changes to basisu_frontend.cpp or basisu_tool.cpp.
 // Failure semantics are the reference's: any call returning false makes the frontend null its context, set
 // m_opencl_failed and recompute that stage on the CPU (encoder/basisu_frontend.cpp:757-762).
-#include "encoder/basisu_opencl.h"
+#include "basisu_b200_seam.h"
 #include "basisu_b200.h"
 
 namespace basisu
@@ -93,5 +93,75 @@ namespace basisu
 	{
 		if (!p) return false;
 		return report(p, b200_etc1s_determine_selectors(p->m_ctx, pInput_etc_color5_and_inten, pOutput_blocks, perceptual), "opencl_determine_selectors");
+	}
+
+	// ---- extensions of the seam (integration/basisu_b200_seam.h) ----------------------------------------------------------
+
+	bool opencl_b200_encode_uastc_image(opencl_context_ptr p, const color_rgba* pImage, uint32_t width, uint32_t height, uint32_t pitch_in_pixels,
+		void* pDst_blocks, uint32_t uastc_flags)
+	{
+		if (!p) return false;
+		return report(p, b200_uastc_encode_image(p->m_ctx, pImage, width, height, (size_t)pitch_in_pixels * sizeof(color_rgba), pDst_blocks, uastc_flags), "opencl_b200_encode_uastc_image");
+	}
+
+	bool opencl_b200_uastc_rdo(opencl_context_ptr p, uint32_t num_blocks, basist::uastc_block* pBlocks, const color_rgba* pBlock_pixels,
+		const uastc_rdo_params& params, uint32_t flags, uint32_t total_jobs)
+	{
+		if (!p) return false;
+		b200_uastc_rdo_params q;
+		q.lz_dict_size = params.m_lz_dict_size; q.lambda = params.m_lambda;
+		q.max_allowed_rms_increase_ratio = params.m_max_allowed_rms_increase_ratio;
+		q.skip_block_rms_thresh = params.m_skip_block_rms_thresh;
+		q.endpoint_refinement = params.m_endpoint_refinement ? 1u : 0u;
+		q.max_smooth_block_std_dev = params.m_max_smooth_block_std_dev;
+		q.smooth_block_max_error_scale = params.m_smooth_block_max_error_scale;
+		q.lz_literal_cost = params.m_lz_literal_cost;
+		return report(p, b200_uastc_rdo(p->m_ctx, num_blocks, pBlocks, pBlock_pixels, &q, flags, total_jobs), "opencl_b200_uastc_rdo");
+	}
+
+	bool opencl_b200_generate_hierarchical_codebook(opencl_context_ptr p, uint32_t dim, const void* pTraining_vecs, uint32_t num_training_vecs,
+		size_t stride_bytes, size_t weight_offset_bytes, uint32_t max_codebook_size, uint32_t max_parent_codebook_size,
+		basisu::vector<uint_vec>& codebook, basisu::vector<uint_vec>& parent_codebook, uint32_t max_threads, bool even_odd_input_pairs_equal)
+	{
+		if (!p) return false;
+		b200_tsvq_result r;
+		if (!report(p, b200_tsvq_generate(p->m_ctx, dim, num_training_vecs, pTraining_vecs, stride_bytes, weight_offset_bytes, max_codebook_size, max_parent_codebook_size,
+			max_threads, even_odd_input_pairs_equal, &r), "opencl_b200_generate_hierarchical_codebook"))
+			return false;
+		debug_printf("b200_tsvq_generate: dim %u, %u training vectors, %u unique, %u clusters, %u parent clusters, %u device rounds, %u node splits, %3.3f ms on the device\n",
+			dim, num_training_vecs, r.num_unique, r.num_clusters, r.num_parent_clusters, r.rounds, r.nodes_split, b200_last_kernel_ms(p->m_ctx));
+		codebook.resize(0);
+		codebook.resize(r.num_clusters);
+		for (uint32_t i = 0; i < r.num_clusters; i++)
+		{
+			const uint32_t n = r.cluster_offsets[i + 1] - r.cluster_offsets[i];
+			codebook[i].resize(n);
+			if (n) memcpy(codebook[i].data(), r.cluster_indices + r.cluster_offsets[i], (size_t)n * sizeof(uint32_t));
+		}
+		parent_codebook.resize(0);
+		parent_codebook.resize(r.num_parent_clusters);
+		for (uint32_t i = 0; i < r.num_parent_clusters; i++)
+		{
+			const uint32_t n = r.parent_offsets[i + 1] - r.parent_offsets[i];
+			parent_codebook[i].resize(n);
+			if (n) memcpy(parent_codebook[i].data(), r.parent_indices + r.parent_offsets[i], (size_t)n * sizeof(uint32_t));
+		}
+		return true;
+	}
+
+	bool opencl_b200_encode_etc1s_endpoint_clusters(opencl_context_ptr p, etc_block* pOutput_blocks, uint32_t total_clusters,
+		const uint32_t* pCluster_offsets, const uint32_t* pCluster_block_indices, bool perceptual, uint32_t total_perms)
+	{
+		if (!p) return false;
+		return report(p, b200_etc1s_encode_endpoint_clusters(p->m_ctx, pOutput_blocks, total_clusters, pCluster_offsets, pCluster_block_indices, perceptual, total_perms),
+			"opencl_b200_encode_etc1s_endpoint_clusters");
+	}
+
+	bool opencl_b200_optimize_selector_codebook(opencl_context_ptr p, const etc_block* pEtc_blocks, uint32_t total_clusters,
+		const uint32_t* pCluster_offsets, const uint32_t* pCluster_block_indices, uint32_t* pOutput_selectors, bool perceptual)
+	{
+		if (!p) return false;
+		return report(p, b200_etc1s_optimize_selector_codebook(p->m_ctx, pEtc_blocks, total_clusters, pCluster_offsets, pCluster_block_indices, pOutput_selectors, perceptual),
+			"opencl_b200_optimize_selector_codebook");
 	}
 } // namespace basisu

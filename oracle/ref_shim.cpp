@@ -333,3 +333,77 @@ REF_API void ref_selector_training(const uint8_t* pEtc_blocks, uint32_t n, uint3
 
 // Turns the encoder's own debug_printf stage timers on or off (enc.h: enable_debug_printf); used by tools/bench_dropin.py.
 REF_API void ref_enable_debug_printf(int enabled) { enable_debug_printf(enabled != 0); }
+
+// ---- the ETC1S codebook stages (endpoint/selector VQ, selector codebook) ---------------------------------------
+
+// generate_hierarchical_codebook_threaded (enc.h:2219) over tree_vector_quant<vec6F> (dim 6) or <vec16F> (dim 16), exactly as the
+// frontend calls it (frontend.cpp:868, 2140). Outputs are CSR lists of training-vector indices; *_off arrays need n + 1 entries.
+template<typename Vec> static int ref_tsvq_t(uint32_t n, const float* pVecs, const uint64_t* pWeights, uint32_t max_codebook, uint32_t max_parent, uint32_t max_threads, bool even_odd,
+	uint32_t* cl_off, uint32_t* cl_idx, uint32_t* pNum_clusters, uint32_t* pa_off, uint32_t* pa_idx, uint32_t* pNum_parents)
+{
+	tree_vector_quant<Vec> q;
+	for (uint32_t i = 0; i < n; i++)
+	{
+		Vec v;
+		for (uint32_t c = 0; c < Vec::num_elements; c++) v[c] = pVecs[(size_t)i * Vec::num_elements + c];
+		q.add_training_vec(v, pWeights[i]);
+	}
+	job_pool pool(max_threads ? max_threads : 1);
+	basisu::vector<uint_vec> codebook, parent_codebook;
+	if (!generate_hierarchical_codebook_threaded(q, max_codebook, max_parent, codebook, parent_codebook, max_threads, &pool, even_odd))
+		return 0;
+	uint32_t k = 0;
+	cl_off[0] = 0;
+	for (uint32_t i = 0; i < codebook.size(); i++) { for (uint32_t j = 0; j < codebook[i].size(); j++) cl_idx[k++] = codebook[i][j]; cl_off[i + 1] = k; }
+	*pNum_clusters = (uint32_t)codebook.size();
+	k = 0;
+	pa_off[0] = 0;
+	for (uint32_t i = 0; i < parent_codebook.size(); i++) { for (uint32_t j = 0; j < parent_codebook[i].size(); j++) pa_idx[k++] = parent_codebook[i][j]; pa_off[i + 1] = k; }
+	*pNum_parents = (uint32_t)parent_codebook.size();
+	return 1;
+}
+
+REF_API int ref_tsvq(uint32_t dim, uint32_t n, const float* pVecs, const uint64_t* pWeights, uint32_t max_codebook, uint32_t max_parent, uint32_t max_threads, uint32_t even_odd,
+	uint32_t* cl_off, uint32_t* cl_idx, uint32_t* pNum_clusters, uint32_t* pa_off, uint32_t* pa_idx, uint32_t* pNum_parents)
+{
+	ref_init();
+	if (dim == 6) return ref_tsvq_t<vec6F>(n, pVecs, pWeights, max_codebook, max_parent, max_threads, even_odd != 0, cl_off, cl_idx, pNum_clusters, pa_off, pa_idx, pNum_parents);
+	if (dim == 16) return ref_tsvq_t<vec16F>(n, pVecs, pWeights, max_codebook, max_parent, max_threads, even_odd != 0, cl_off, cl_idx, pNum_clusters, pa_off, pa_idx, pNum_parents);
+	return 0;
+}
+
+// basisu_frontend::create_optimized_selector_codebook (frontend.cpp:2259-2345) for clusters given as CSR block lists:
+// out[c] = the 16 optimised selectors of cluster c, texel (x, y) at bits 2 * (x + 4 * y); 0 for an empty cluster.
+REF_API void ref_optimize_selector_codebook(const uint8_t* pPixel_blocks, const uint8_t* pEtc_blocks, uint32_t total_clusters, const uint32_t* pOffsets, const uint32_t* pBlock_indices,
+	uint32_t perceptual, uint32_t* pOut)
+{
+	for (uint32_t c = 0; c < total_clusters; c++)
+	{
+		uint64_t total_err[4][4][4];
+		memset(total_err, 0, sizeof(total_err));
+		for (uint32_t k = pOffsets[c]; k < pOffsets[c + 1]; k++)
+		{
+			const uint32_t bi = pBlock_indices[k];
+			const etc_block& blk = *reinterpret_cast<const etc_block*>(pEtc_blocks + (size_t)bi * 8);
+			color_rgba blk_colors[4];
+			blk.get_block_colors(blk_colors, 0);
+			const color_rgba* px = reinterpret_cast<const color_rgba*>(pPixel_blocks + (size_t)bi * 64);
+			for (uint32_t y = 0; y < 4; y++)
+				for (uint32_t x = 0; x < 4; x++)
+					for (uint32_t s = 0; s < 4; s++)
+						total_err[y][x][s] += color_distance(perceptual != 0, blk_colors[s], px[x + y * 4], false);
+		}
+		uint32_t packed = 0;
+		if (pOffsets[c + 1] > pOffsets[c])
+			for (uint32_t y = 0; y < 4; y++)
+				for (uint32_t x = 0; x < 4; x++)
+				{
+					uint64_t best_err = total_err[y][x][0];
+					uint32_t best_sel = 0;
+					for (uint32_t s = 1; s < 4; s++)
+						if (total_err[y][x][s] < best_err) { best_err = total_err[y][x][s]; best_sel = s; }
+					packed |= best_sel << ((x + y * 4) * 2);
+				}
+		pOut[c] = packed;
+	}
+}

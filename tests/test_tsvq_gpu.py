@@ -1,0 +1,197 @@
+"""GPU parity for the ETC1S codebook stages behind the wider seam (include/basisu_b200.h):
+  b200_tsvq_generate                     vs generate_hierarchical_codebook_threaded (enc.h:2219) in the compiled reference
+  b200_etc1s_encode_endpoint_clusters    vs the CPU path of generate_endpoint_codebook (frontend.cpp:1493-1549)
+  b200_etc1s_optimize_selector_codebook  vs create_optimized_selector_codebook (frontend.cpp:2259-2345)
+The last two are integer stages: bit-exact. The clusterer's sums are parallel reductions instead of the reference's serial float
+sums, so its bar is the codebook itself: same cluster count, (nearly) the same partition, distortion within 0.1 %."""
+import ctypes
+
+import numpy as np
+import pytest
+
+import util
+from util import _ptr
+from basis_universal_b200 import etc1s
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    c = etc1s.Etc1sContext(0)
+    yield c
+    c.close()
+
+
+def ref_tsvq(ref, vecs, weights, max_codebook, max_parent, max_threads=1, even_odd=False):
+    vecs = np.ascontiguousarray(vecs, np.float32); weights = np.ascontiguousarray(weights, np.uint64)
+    n, dim = vecs.shape
+    cl_off = np.zeros(n + 1, np.uint32); cl_idx = np.zeros(n, np.uint32); pa_off = np.zeros(n + 1, np.uint32); pa_idx = np.zeros(n, np.uint32)
+    nc = ctypes.c_uint32(0); npar = ctypes.c_uint32(0)
+    ok = ref.lib.ref_tsvq(dim, n, _ptr(vecs), _ptr(weights), int(max_codebook), int(max_parent), int(max_threads), int(even_odd), _ptr(cl_off), _ptr(cl_idx), ctypes.byref(nc),
+                          _ptr(pa_off), _ptr(pa_idx), ctypes.byref(npar))
+    assert ok
+    return [cl_idx[cl_off[i]:cl_off[i + 1]] for i in range(nc.value)], [pa_idx[pa_off[i]:pa_off[i + 1]] for i in range(npar.value)]
+
+
+def distortion(vecs, weights, clusters):
+    """weighted sum of squared distances to the cluster centroids (what the tree minimises)"""
+    v = vecs.astype(np.float64); w = weights.astype(np.float64)
+    total = 0.0
+    for c in clusters:
+        ww = w[c][:, None]
+        mean = (v[c] * ww).sum(0) / ww.sum()
+        total += float((((v[c] - mean) ** 2) * ww).sum())
+    return total
+
+
+def labels(n, clusters):
+    lab = np.full(n, -1, np.int64)
+    for i, c in enumerate(clusters):
+        lab[c] = i
+    return lab
+
+
+def check_partition(n, clusters):
+    allidx = np.concatenate(clusters)
+    assert allidx.shape[0] == n and np.array_equal(np.sort(allidx), np.arange(n)), "clusters must partition the training set"
+
+
+def endpoint_training(ref, img, comp_level=1):
+    """init_endpoint_training_vectors (frontend.cpp:825-866): per block, low/high block colours / 255, inserted twice with weight 1."""
+    blocks = util.image_to_blocks(img)
+    etc = np.zeros((blocks.shape[0], 8), np.uint8)
+    ref.lib.ref_etc1s_encode_blocks(_ptr(blocks), ctypes.c_uint32(blocks.shape[0]), _ptr(etc), 0, comp_level)
+    hist = np.bincount(util.endpoint_keys(etc), minlength=1 << 18).astype(np.uint32)
+    keys = util.endpoint_keys(etc)
+    _, kvecs, _ = etc1s.training_vectors_from_histogram(hist)
+    lut = np.zeros((1 << 18, 6), np.float32)
+    lut[np.nonzero(hist)[0]] = kvecs
+    vecs = np.repeat(lut[keys], 2, axis=0)
+    return blocks, etc, vecs, np.ones(vecs.shape[0], np.uint64)
+
+
+@pytest.mark.parametrize("max_codebook,max_parent", [(300, 16), (37, 0), (2416, 16)])
+def test_tsvq_endpoints_matches_reference(ctx, ref, max_codebook, max_parent):
+    g = np.load(util.GOLDEN + "/kodim03_uastc_l0.npz")
+    img = np.ascontiguousarray(np.concatenate([g["image"][:256, :512], util.synth(512, 5)[:128]], 0))
+    _, _, vecs, weights = endpoint_training(ref, img)
+    want, want_par = ref_tsvq(ref, vecs, weights, max_codebook, max_parent, 1, True)
+    got, got_par, info = ctx.tsvq_generate(vecs, weights, max_codebook, max_parent, 1, True)
+    n = vecs.shape[0]
+    check_partition(n, got)
+    assert len(got) == len(want) and len(got_par) == len(want_par)
+    if got_par:
+        check_partition(n, got_par)
+    d_ref, d_gpu = distortion(vecs, weights, want), distortion(vecs, weights, got)
+    same = float(np.mean(labels(n, got) == labels(n, want)))
+    print(f"endpoints {max_codebook}/{max_parent}: {info['num_unique']} unique of {n}, {len(got)} clusters, {info['rounds']} rounds, {info['nodes_split']} splits, "
+          f"{info['device_ms']:.2f} ms; distortion ref {d_ref:.6f} gpu {d_gpu:.6f}; identical labels {same:.4f}")
+    assert abs(d_gpu - d_ref) <= 1e-3 * d_ref
+    assert same >= 0.98
+    # every child cluster lies inside one parent cluster (frontend.cpp:918-940 verifies this and aborts otherwise)
+    if got_par:
+        plab = labels(n, got_par)
+        for c in got:
+            assert np.all(plab[c] == plab[c[0]])
+
+
+def selector_training(ref, etc):
+    keys = np.zeros(etc.shape[0], np.uint32); wts = np.zeros(etc.shape[0], np.uint32)
+    ref.lib.ref_selector_training(_ptr(etc), ctypes.c_uint32(etc.shape[0]), 0, _ptr(keys), _ptr(wts))
+    vecs = ((keys[:, None] >> (2 * np.arange(16, dtype=np.uint32))[None, :]) & 3).astype(np.float32)
+    return vecs, wts.astype(np.uint64)
+
+
+@pytest.mark.parametrize("max_codebook,max_parent", [(400, 16), (2731, 32)])
+def test_tsvq_selectors_matches_reference(ctx, ref, max_codebook, max_parent):
+    g = np.load(util.GOLDEN + "/kodim03_uastc_l0.npz")
+    img = np.ascontiguousarray(g["image"][:384, :768])
+    blocks, etc, _, _ = endpoint_training(ref, img)
+    c5i = np.stack([etc[:, 0] >> 3, etc[:, 1] >> 3, etc[:, 2] >> 3, etc[:, 3] >> 5], -1).astype(np.uint8)
+    enc = np.zeros_like(etc)
+    ref.lib.ref_etc1s_determine_selectors(_ptr(blocks), ctypes.c_uint32(blocks.shape[0]), _ptr(np.ascontiguousarray(c5i)), _ptr(enc), 0)
+    vecs, weights = selector_training(ref, enc)
+    want, want_par = ref_tsvq(ref, vecs, weights, max_codebook, max_parent, 1, False)
+    got, got_par, info = ctx.tsvq_generate(vecs, weights, max_codebook, max_parent, 1, False)
+    n = vecs.shape[0]
+    check_partition(n, got)
+    assert len(got) == len(want) and len(got_par) == len(want_par)
+    d_ref, d_gpu = distortion(vecs, weights, want), distortion(vecs, weights, got)
+    same = float(np.mean(labels(n, got) == labels(n, want)))
+    print(f"selectors {max_codebook}/{max_parent}: {info['num_unique']} unique of {n}, {len(got)} clusters, {info['rounds']} rounds, {info['nodes_split']} splits, "
+          f"{info['device_ms']:.2f} ms; distortion ref {d_ref:.4f} gpu {d_gpu:.4f}; identical labels {same:.4f}")
+    assert abs(d_gpu - d_ref) <= 1e-3 * d_ref
+    assert same >= 0.98
+
+
+def test_tsvq_small_and_degenerate_sets(ctx, ref):
+    rng = np.random.default_rng(3)
+    # fewer unique vectors than the codebook; a single vector; two vectors; many duplicates
+    for n, dim, cb in [(1, 6, 8), (2, 16, 8), (50, 6, 100), (500, 16, 7)]:
+        vecs = rng.integers(0, 4, (n, dim)).astype(np.float32)
+        weights = rng.integers(1, 9, n).astype(np.uint64)
+        want, _ = ref_tsvq(ref, vecs, weights, cb, 0)
+        got, _, _ = ctx.tsvq_generate(vecs, weights, cb, 0)
+        check_partition(n, got)
+        assert len(got) == len(want), (n, dim, cb)
+        assert abs(distortion(vecs, weights, got) - distortion(vecs, weights, want)) <= 1e-3 * max(distortion(vecs, weights, want), 1e-9) + 1e-9
+
+
+def test_tsvq_two_level_path(ctx, ref):
+    """>= 2^18 unique vectors and max_threads > 1: max_threads top clusters, one sub-tree each (enc.h:2112-2214)."""
+    rng = np.random.default_rng(11)
+    n = 280000
+    vecs = rng.integers(0, 4, (n, 16)).astype(np.float32)
+    weights = rng.integers(1, 30, n).astype(np.uint64)
+    got, got_par, info = ctx.tsvq_generate(vecs, weights, 1024, 32, 8, False)
+    assert info["num_unique"] >= 1 << 18
+    check_partition(n, got)
+    check_partition(n, got_par)
+    want, want_par = ref_tsvq(ref, vecs, weights, 1024, 32, 8, False)
+    print(f"two-level: {len(got)} clusters / {len(got_par)} parents (reference {len(want)} / {len(want_par)}), {info['rounds']} rounds, {info['device_ms']:.1f} ms")
+    assert len(got) == len(want) and len(got_par) == len(want_par)
+    d_ref, d_gpu = distortion(vecs, weights, want), distortion(vecs, weights, got)
+    assert abs(d_gpu - d_ref) <= 2e-3 * d_ref
+
+
+@pytest.mark.parametrize("perceptual", [0, 1])
+@pytest.mark.parametrize("comp_level,perms", [(1, 16), (2, 64)])
+def test_endpoint_clusters_match_cpu_optimizer(ctx, ref, perceptual, comp_level, perms):
+    img = util.synth(256, 9)
+    blocks = util.image_to_blocks(img)
+    ctx.set_pixel_blocks(blocks)
+    rng = np.random.default_rng(17)
+    n = blocks.shape[0]
+    order = rng.permutation(n).astype(np.uint32)
+    cuts = np.sort(rng.choice(np.arange(1, n), 60, replace=False))
+    clusters = [c for c in np.split(order, cuts)] + [np.zeros(0, np.uint32)]   # ragged sizes plus an empty cluster
+    got = ctx.encode_endpoint_clusters(clusters, perceptual, perms)
+    for i, c in enumerate(clusters):
+        if not len(c):
+            continue
+        px = np.ascontiguousarray(blocks[c].reshape(-1, 4))
+        out4 = np.zeros(4, np.uint8)
+        ref.lib.ref_etc1s_encode_cluster.restype = ctypes.c_uint64
+        ref.lib.ref_etc1s_encode_cluster(_ptr(px), ctypes.c_uint32(px.shape[0]), perceptual, comp_level, _ptr(out4))
+        assert (got[i, 0] >> 3, got[i, 1] >> 3, got[i, 2] >> 3, got[i, 3] >> 5) == tuple(int(v) for v in out4), (i, len(c))
+
+
+@pytest.mark.parametrize("perceptual", [0, 1])
+def test_selector_codebook_matches_reference(ctx, ref, perceptual):
+    img = util.synth(256, 21)
+    blocks = util.image_to_blocks(img)
+    n = blocks.shape[0]
+    ctx.set_pixel_blocks(blocks)
+    etc = np.zeros((n, 8), np.uint8)
+    ref.lib.ref_etc1s_encode_blocks(_ptr(blocks), ctypes.c_uint32(n), _ptr(etc), perceptual, 1)
+    rng = np.random.default_rng(23)
+    order = rng.permutation(n).astype(np.uint32)
+    cuts = np.sort(rng.choice(np.arange(1, n), 99, replace=False))
+    clusters = [c for c in np.split(order, cuts)] + [np.zeros(0, np.uint32)]
+    got = ctx.optimize_selector_codebook(etc, clusters, perceptual)
+    off = np.zeros(len(clusters) + 1, np.uint32); np.cumsum([len(c) for c in clusters], out=off[1:])
+    idx = np.ascontiguousarray(np.concatenate(clusters), np.uint32)
+    want = np.zeros(len(clusters), np.uint32)
+    ref.lib.ref_optimize_selector_codebook(_ptr(blocks), _ptr(etc), len(clusters), _ptr(off), _ptr(idx), perceptual, _ptr(want))
+    assert np.array_equal(got, want)

@@ -22,6 +22,7 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--dims", type=int, nargs="+", default=[1024, 2048])
     ap.add_argument("--quality", type=int, default=128)
+    ap.add_argument("--debug", action="store_true", help="turn the encoder's debug_printf on: per-stage timers of both runs go to stdout")
     args = ap.parse_args()
     lib = ctypes.CDLL(DROPIN)
     lib.ref_compress_image.restype = ctypes.c_void_p
@@ -33,12 +34,18 @@ def main():
         img[..., 3] = 255
         img = np.ascontiguousarray(img)
         compress(lib, img[:64, :64].copy(), args.quality | cFlagThreaded | cFlagUseOpenCL)  # warm-up: context, module load
+        if args.debug:
+            lib.ref_enable_debug_printf(1); print(f"==== B200 seam run, {dim}x{dim}", flush=True)
         t0 = time.perf_counter(); gpu = compress(lib, img, args.quality | cFlagThreaded | cFlagUseOpenCL); t_gpu = time.perf_counter() - t0
+        if args.debug:
+            print(f"==== CPU run, {dim}x{dim}", flush=True)
         t0 = time.perf_counter(); cpu = compress(lib, img, args.quality | cFlagThreaded); t_cpu = time.perf_counter() - t0
+        if args.debug:
+            lib.ref_enable_debug_printf(0)
         (g_rgb, g_y), (c_rgb, c_y) = psnr(lib, gpu, img), psnr(lib, cpu, img)
         print(json.dumps({"config": f"ETC1S q{args.quality} {dim}x{dim} through basis_compress()", "cpu_s": round(t_cpu, 3), "b200_seam_s": round(t_gpu, 3),
                           "cpu_bytes": len(cpu), "b200_bytes": len(gpu), "cpu_psnr_rgb_y": [round(c_rgb, 4), round(c_y, 4)], "b200_psnr_rgb_y": [round(g_rgb, 4), round(g_y, 4)],
-                          "host_threads": os.cpu_count()}), flush=True)
+                          "host_threads": os.cpu_count(), "affinity": len(os.sched_getaffinity(0))}), flush=True)
 
 
 if __name__ == "__main__":
