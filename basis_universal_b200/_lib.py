@@ -44,6 +44,10 @@ def lib():
             f.argtypes = [vp, vp, u32, vp, u32]
         L.b200_uastc_rdo.restype = i32
         L.b200_uastc_rdo.argtypes = [vp, u32, vp, vp, vp, u32, u32]
+        for name in ("b200_uastc_rdo_batch", "b200_uastc_rdo_batch_device"):
+            f = getattr(L, name)
+            f.restype = i32
+            f.argtypes = [vp, u32, vp, vp, vp, vp, u32, u32]
         L.b200_etc1s_endpoint_histogram.restype = i32
         L.b200_etc1s_endpoint_histogram.argtypes = [vp, vp, u32, vp]
         L.b200_etc1s_endpoint_histogram_device.restype = i32
@@ -95,7 +99,7 @@ def lib():
 
 EXPORTS = [
     "b200_device_count", "b200_create_context", "b200_destroy_context", "b200_last_error",
-    "b200_uastc_encode_blocks", "b200_uastc_encode_blocks_device", "b200_uastc_encode_image", "b200_uastc_rdo",
+    "b200_uastc_encode_blocks", "b200_uastc_encode_blocks_device", "b200_uastc_encode_image", "b200_uastc_rdo", "b200_uastc_rdo_batch", "b200_uastc_rdo_batch_device",
     "b200_etc1s_set_flavour", "b200_etc1s_set_pixel_blocks", "b200_etc1s_endpoint_histogram", "b200_etc1s_endpoint_histogram_device",
     "b200_etc1s_selector_training", "b200_etc1s_selector_training_device",
     "b200_extract_source_blocks", "b200_extract_source_blocks_device", "b200_uastc_unpack_blocks", "b200_uastc_unpack_blocks_device", "b200_block_metrics_device", "b200_etc1_unpack_blocks", "b200_etc1_unpack_blocks_device", "b200_etc1s_encode_blocks", "b200_etc1s_encode_pixel_clusters",

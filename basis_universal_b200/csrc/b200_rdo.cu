@@ -1,7 +1,8 @@
 // b200_rdo.cu -- UASTC RDO post-pass on sm_100a: b200_uastc_rdo (include/basisu_b200.h), the batch form of
 // basisu::uastc_rdo (encoder/basisu_uastc_enc.h:139; implementation uastc_enc.cpp:3824-4164).
 //
-//   k_rdo_chain    one 256-thread CTA per chain (the reference splits the slice into `total_jobs` contiguous chains,
+//   k_rdo_chain    one 256-thread CTA per chain; all chains of all slices of a batch in ONE launch (b200_uastc_rdo_batch: 8 tiles x 4
+//                  chains = 32 concurrent CTAs instead of 4) (the reference splits each slice into `total_jobs` contiguous chains,
 //                  uastc_enc.cpp:4116-4154, and the result depends on that split, so it is reproduced exactly).
 //                  Per block: every thread scores the splice of one of the previous <= 256 blocks' selector bits
 //                  (bu_rdo.h::rdo_trial); a block-wide (cost, distance) arg-min picks the winner with the reference's
@@ -54,12 +55,13 @@ __device__ __forceinline__ void st_bits(uint4* p, const block_bits& b) { uint4 v
 
 #define RDO_THREADS 256
 
-__global__ void __launch_bounds__(RDO_THREADS) k_rdo_chain(uint4* blocks, const uint4* __restrict__ pixels, uint32_t n, uint32_t per_job,
+// chains[c] = { first block, one past the last block } of chain c in the (possibly multi-slice) block array
+__global__ void __launch_bounds__(RDO_THREADS) k_rdo_chain(uint4* blocks, const uint4* __restrict__ pixels, const uint2* __restrict__ chains,
 	hist_entry* hist_all, uint32_t hist_cap, uint8_t* modified, rdo_params p, int* failed)
 {
 	const bu_tables* T = &d_tables;
-	const uint32_t first = blockIdx.x * per_job;
-	const uint32_t last = (first + per_job < n) ? first + per_job : n;
+	const uint32_t first = chains[blockIdx.x].x;
+	const uint32_t last = chains[blockIdx.x].y;
 	hist_entry* hist = hist_all + (size_t)blockIdx.x * hist_cap;
 	const uint32_t hmask = hist_cap - 1;
 	const uint32_t tid = threadIdx.x;
@@ -216,56 +218,113 @@ __global__ void __launch_bounds__(128) k_rdo_rehint(uint4* blocks, const uint4* 
 	blocks[i] = v;
 }
 
-extern "C" int b200_uastc_rdo(b200_context* ctx, uint32_t num_blocks, void* pBlocks, const void* pBlock_pixels,
-	const b200_uastc_rdo_params* params, uint32_t flags, uint32_t total_jobs)
+// Shared by every entry point: blocks and source texels already on the device, `slice_blocks[s]` blocks per slice laid end
+// to end. Every slice is cut into chains exactly as uastc_rdo cuts it (uastc_enc.cpp:4116-4133, as if a job pool were supplied),
+// and ALL chains of ALL slices run in one launch, one CTA each; the deferred hint pass covers the whole array.
+static int rdo_run_device(b200_context* ctx, uint4* d_blocks, const uint4* d_pixels, uint32_t num_slices, const uint32_t* slice_blocks,
+	const b200_uastc_rdo_params* params, uint32_t flags, uint32_t total_jobs, int* h_failed_out)
 {
-	if (!ctx) return 0;
-	if (!ctx->activate()) return 0;
-	if (!num_blocks) return 1;
-	if (!pBlocks || !pBlock_pixels || !params) { ctx->fail("b200_uastc_rdo: null argument"); return 0; }
 	if (!(params->lambda > 0.0f) || !params->lz_dict_size) { ctx->fail("b200_uastc_rdo: lambda and lz_dict_size must be positive"); return 0; }
-
 	rdo_params p;
 	p.lz_dict_size = params->lz_dict_size; p.lambda = params->lambda; p.max_allowed_rms_increase_ratio = params->max_allowed_rms_increase_ratio;
 	p.skip_block_rms_thresh = params->skip_block_rms_thresh; p.endpoint_refinement = params->endpoint_refinement;
 	p.max_smooth_block_std_dev = params->max_smooth_block_std_dev; p.smooth_block_max_error_scale = params->smooth_block_max_error_scale;
 	p.lz_literal_cost = params->lz_literal_cost;
 
-	// chain split of uastc_rdo (uastc_enc.cpp:4116-4133), as if a job pool were supplied
-	uint32_t per_job = total_jobs ? num_blocks / total_jobs : 0;
-	uint32_t chains;
-	if (total_jobs <= 1 || per_job <= 8) { per_job = num_blocks; chains = 1; }
-	else chains = (num_blocks + per_job - 1) / per_job;
-
+	uint64_t total = 0;
+	uint32_t max_chain = 0, num_chains = 0;
+	for (uint32_t s = 0; s < num_slices; s++)
+	{
+		const uint32_t n = slice_blocks[s];
+		if (!n) continue;
+		uint32_t per_job = total_jobs ? n / total_jobs : 0;
+		if (total_jobs <= 1 || per_job <= 8) per_job = n;
+		num_chains += (n + per_job - 1) / per_job;
+		if (per_job > max_chain) max_chain = per_job;
+		total += n;
+	}
+	if (!total) return 1;
+	if (total > 0xFFFFFFFFull) { ctx->fail("b200_uastc_rdo: more than 2^32 blocks in one call"); return 0; }
+	const uint32_t num_blocks = (uint32_t)total;
+	uint2* h_chains = static_cast<uint2*>(malloc((size_t)num_chains * sizeof(uint2)));
+	if (!h_chains) { ctx->fail("b200_uastc_rdo: out of host memory"); return 0; }
+	{
+		uint32_t c = 0, base = 0;
+		for (uint32_t s = 0; s < num_slices; s++)
+		{
+			const uint32_t n = slice_blocks[s];
+			if (!n) continue;
+			uint32_t per_job = total_jobs ? n / total_jobs : 0;
+			if (total_jobs <= 1 || per_job <= 8) per_job = n;
+			for (uint32_t f = 0; f < n; f += per_job) { h_chains[c].x = base + f; h_chains[c].y = base + ((f + per_job < n) ? f + per_job : n); c++; }
+			base += n;
+		}
+	}
 	uint32_t cap = 64;
-	while (cap < 2 * per_job) cap <<= 1;
+	while (cap < 2 * max_chain) cap <<= 1;
 
-	if (!ctx->reserve(ctx->d_out, ctx->out_cap, (size_t)num_blocks * 16)) return 0;
-	if (!ctx->reserve(ctx->d_in, ctx->in_cap, (size_t)num_blocks * 64)) return 0;
-	if (!ctx->reserve(ctx->d_aux[4], ctx->aux_cap[4], (size_t)chains * cap * sizeof(hist_entry))) return 0;
-	if (!ctx->reserve(ctx->d_aux[5], ctx->aux_cap[5], (size_t)num_blocks + 16)) return 0;
+	const size_t hist_bytes = (size_t)num_chains * cap * sizeof(hist_entry);
+	const size_t flag_ofs = ((size_t)num_blocks + 15) & ~(size_t)15; // per-block "modified" bytes, then the failure flag, then the chain table
+	const size_t chains_ofs = flag_ofs + 16;
+	bool ok = ctx->reserve(ctx->d_aux[4], ctx->aux_cap[4], hist_bytes) && ctx->reserve(ctx->d_aux[5], ctx->aux_cap[5], chains_ofs + (size_t)num_chains * sizeof(uint2));
+	if (!ok) { free(h_chains); return 0; }
 	uint8_t* modified = static_cast<uint8_t*>(ctx->d_aux[5]);
-	int* failed = reinterpret_cast<int*>(modified + ((num_blocks + 3) & ~3u)); // the flag sits behind the per-block bytes (reserve adds 16)
-
-	B200_CUDA_OK(ctx, cudaMemcpyAsync(ctx->d_out, pBlocks, (size_t)num_blocks * 16, cudaMemcpyHostToDevice, ctx->stream));
-	B200_CUDA_OK(ctx, cudaMemcpyAsync(ctx->d_in, pBlock_pixels, (size_t)num_blocks * 64, cudaMemcpyHostToDevice, ctx->stream));
-	B200_CUDA_OK(ctx, cudaMemsetAsync(ctx->d_aux[4], 0, (size_t)chains * cap * sizeof(hist_entry), ctx->stream));
-	B200_CUDA_OK(ctx, cudaMemsetAsync(ctx->d_aux[5], 0, (size_t)num_blocks + 16, ctx->stream));
+	int* failed = reinterpret_cast<int*>(modified + flag_ofs);
+	uint2* d_chains = reinterpret_cast<uint2*>(modified + chains_ofs);
+	cudaError_t e = cudaMemsetAsync(ctx->d_aux[4], 0, hist_bytes, ctx->stream);
+	if (e == cudaSuccess) e = cudaMemsetAsync(ctx->d_aux[5], 0, chains_ofs, ctx->stream);
+	if (e == cudaSuccess) e = cudaMemcpyAsync(d_chains, h_chains, (size_t)num_chains * sizeof(uint2), cudaMemcpyHostToDevice, ctx->stream);
+	if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream); // h_chains is pageable and freed next
+	free(h_chains);
+	if (e != cudaSuccess) { ctx->fail_cuda("b200_uastc_rdo: setup", e); return 0; }
 	B200_CUDA_OK(ctx, cudaEventRecord(ctx->ev0, ctx->stream));
-
-	k_rdo_chain<<<chains, RDO_THREADS, 0, ctx->stream>>>(static_cast<uint4*>(ctx->d_out), static_cast<const uint4*>(ctx->d_in), num_blocks, per_job,
-		static_cast<hist_entry*>(ctx->d_aux[4]), cap, modified, p, failed);
+	k_rdo_chain<<<num_chains, RDO_THREADS, 0, ctx->stream>>>(d_blocks, d_pixels, d_chains, static_cast<hist_entry*>(ctx->d_aux[4]), cap, modified, p, failed);
 	const int lvl = (int)(flags & 0xF);
-	k_rdo_rehint<<<(num_blocks + 127) / 128, 128, 0, ctx->stream>>>(static_cast<uint4*>(ctx->d_out), static_cast<const uint4*>(ctx->d_in), num_blocks, modified,
-		make_level_opts(lvl), lvl, flags, failed);
+	k_rdo_rehint<<<(num_blocks + 127) / 128, 128, 0, ctx->stream>>>(d_blocks, d_pixels, num_blocks, modified, make_level_opts(lvl), lvl, flags, failed);
 	ctx->launches = 2; __atomic_add_fetch(&g_b200_total_launches, 2, __ATOMIC_RELAXED);
 	B200_CUDA_OK(ctx, cudaGetLastError());
 	B200_CUDA_OK(ctx, cudaEventRecord(ctx->ev1, ctx->stream));
-	int h_failed = 0;
-	B200_CUDA_OK(ctx, cudaMemcpyAsync(&h_failed, failed, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
-	B200_CUDA_OK(ctx, cudaMemcpyAsync(pBlocks, ctx->d_out, (size_t)num_blocks * 16, cudaMemcpyDeviceToHost, ctx->stream));
+	B200_CUDA_OK(ctx, cudaMemcpyAsync(h_failed_out, failed, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
 	B200_CUDA_OK(ctx, cudaStreamSynchronize(ctx->stream));
 	B200_CUDA_OK(ctx, cudaEventElapsedTime(&ctx->last_ms, ctx->ev0, ctx->ev1));
-	if (h_failed) { ctx->fail("b200_uastc_rdo: a block failed to unpack (invalid UASTC input)"); return 0; } // reference: cECFailedUASTCRDOPostProcess
+	if (*h_failed_out) { ctx->fail("b200_uastc_rdo: a block failed to unpack (invalid UASTC input)"); return 0; } // reference: cECFailedUASTCRDOPostProcess
 	return 1;
+}
+
+extern "C" int b200_uastc_rdo_batch_device(b200_context* ctx, uint32_t num_slices, const uint32_t* pSlice_num_blocks, void* dBlocks, const void* dBlock_pixels,
+	const b200_uastc_rdo_params* params, uint32_t flags, uint32_t total_jobs)
+{
+	if (!ctx) return 0;
+	if (!ctx->activate()) return 0;
+	if (!num_slices) return 1;
+	if (!pSlice_num_blocks || !dBlocks || !dBlock_pixels || !params) { ctx->fail("b200_uastc_rdo_batch_device: null argument"); return 0; }
+	int h_failed = 0;
+	return rdo_run_device(ctx, static_cast<uint4*>(dBlocks), static_cast<const uint4*>(dBlock_pixels), num_slices, pSlice_num_blocks, params, flags, total_jobs, &h_failed);
+}
+
+extern "C" int b200_uastc_rdo_batch(b200_context* ctx, uint32_t num_slices, const uint32_t* pSlice_num_blocks, void* pBlocks, const void* pBlock_pixels,
+	const b200_uastc_rdo_params* params, uint32_t flags, uint32_t total_jobs)
+{
+	if (!ctx) return 0;
+	if (!ctx->activate()) return 0;
+	if (!num_slices) return 1;
+	if (!pSlice_num_blocks || !pBlocks || !pBlock_pixels || !params) { ctx->fail("b200_uastc_rdo: null argument"); return 0; }
+	uint64_t total = 0;
+	for (uint32_t s = 0; s < num_slices; s++) total += pSlice_num_blocks[s];
+	if (!total) return 1;
+	if (!ctx->reserve(ctx->d_out, ctx->out_cap, (size_t)total * 16)) return 0;
+	if (!ctx->reserve(ctx->d_in, ctx->in_cap, (size_t)total * 64)) return 0;
+	B200_CUDA_OK(ctx, cudaMemcpyAsync(ctx->d_out, pBlocks, (size_t)total * 16, cudaMemcpyHostToDevice, ctx->stream));
+	B200_CUDA_OK(ctx, cudaMemcpyAsync(ctx->d_in, pBlock_pixels, (size_t)total * 64, cudaMemcpyHostToDevice, ctx->stream));
+	int h_failed = 0;
+	if (!rdo_run_device(ctx, static_cast<uint4*>(ctx->d_out), static_cast<const uint4*>(ctx->d_in), num_slices, pSlice_num_blocks, params, flags, total_jobs, &h_failed))
+		return 0; // pBlocks is left untouched on failure, so a caller may still run its own CPU pass on the encoder's output
+	B200_CUDA_OK(ctx, cudaMemcpy(pBlocks, ctx->d_out, (size_t)total * 16, cudaMemcpyDeviceToHost));
+	return 1;
+}
+
+extern "C" int b200_uastc_rdo(b200_context* ctx, uint32_t num_blocks, void* pBlocks, const void* pBlock_pixels,
+	const b200_uastc_rdo_params* params, uint32_t flags, uint32_t total_jobs)
+{
+	return b200_uastc_rdo_batch(ctx, 1, &num_blocks, pBlocks, pBlock_pixels, params, flags, total_jobs);
 }

@@ -20,9 +20,11 @@
 //   k_tsvq_split<D, NT>                  split_node (enc.h:1723): covariance -> power-iteration PCA (compute_pca_from_covar,
 //                                        enc.h:606) -> prep_split (enc.h:1848) -> refine_split (enc.h:1962) -> stable partition
 //
-// Sums over members are per-thread partial sums combined by a fixed shuffle/shared-memory tree: deterministic for a given input,
-// but not the reference's serial float order, so clusterings agree with the CPU up to float rounding (the ETC1S gate is
-// +-0.02 dB PSNR). Per-member arithmetic (projections, distances, side tests) repeats the reference's operations one for one.
+// Float sums are order-dependent, and node variances (a difference of nearly equal sums) decide which nodes get split, so every
+// sum is accumulated by one thread in the reference's member order (see "serial sums" below): the clusterer reproduces the CPU's
+// codebooks exactly; per-member arithmetic (projections, distances, side tests) repeats the reference's operations one for one
+// on all threads. Parallelism: across accumulators within a node, across the nodes of a round, and across members for the
+// per-member work. Built with --fmad=false like the rest of the library (the reference is compiled without FMA contraction).
 #include "b200_internal.h"
 #include <cub/cub.cuh>
 #include <algorithm>
@@ -48,11 +50,11 @@ namespace
 
 	struct tsvq_state
 	{
-		dev_buf raw, tv, tw, perm[2], keys[2], cub_tmp, heads, gid, gstart, uvec, uw64, uwf, members, tmp_members, side, nodes, frontier, results;
+		dev_buf raw, tv, tw, perm[2], keys[2], cub_tmp, heads, gid, gstart, uvec, uw64, uwf, members, tmp_members, side, tval, nodes, frontier, results;
 		std::vector<uint32_t> cl_off, cl_idx, pa_off, pa_idx;
 		void release()
 		{
-			dev_buf* all[] = { &raw, &tv, &tw, &perm[0], &perm[1], &keys[0], &keys[1], &cub_tmp, &heads, &gid, &gstart, &uvec, &uw64, &uwf, &members, &tmp_members, &side, &nodes, &frontier, &results };
+			dev_buf* all[] = { &raw, &tv, &tw, &perm[0], &perm[1], &keys[0], &keys[1], &cub_tmp, &heads, &gid, &gstart, &uvec, &uw64, &uwf, &members, &tmp_members, &side, &tval, &nodes, &frontier, &results };
 			for (dev_buf* b : all) b->release();
 		}
 	};
@@ -173,37 +175,86 @@ namespace
 		return r;
 	}
 
+	// ---- serial sums in the reference's order -------------------------------------------------------------------------------------
+	// The reference accumulates a node's sums in float, one member after the other. A float sum's value depends on that order, and the
+	// node variances computed from those sums (a difference of two nearly equal numbers) decide which nodes the priority queue splits.
+	// So every sum that feeds a stored value or a decision is accumulated by ONE thread in member order, exactly as the CPU does it;
+	// the parallelism is across the accumulators of a node (one thread per vector component / matrix entry, up to 136) and across the
+	// nodes of a round, while everything that is per-member (projections, distances, side tests) runs on all threads of the CTA.
+
+	// sum over the listed members with side[i] == want of vecs[m][c] * wf[m], in list order
+	template<int D> __device__ float serial_comp_sum(const float* __restrict__ vecs, const float* __restrict__ wf, const uint32_t* mem, const uint8_t* side, uint32_t count, int c, uint32_t want)
+	{
+		float acc = 0.0f;
+		uint32_t i = 0;
+		for (; i + 4 <= count; i += 4)
+		{
+			const uint32_t m0 = mem[i], m1 = mem[i + 1], m2 = mem[i + 2], m3 = mem[i + 3];
+			const uint32_t s0 = side[i], s1 = side[i + 1], s2 = side[i + 2], s3 = side[i + 3];
+			const float p0 = __ldg(vecs + (size_t)m0 * D + c) * __ldg(wf + m0), p1 = __ldg(vecs + (size_t)m1 * D + c) * __ldg(wf + m1);
+			const float p2 = __ldg(vecs + (size_t)m2 * D + c) * __ldg(wf + m2), p3 = __ldg(vecs + (size_t)m3 * D + c) * __ldg(wf + m3);
+			if (s0 == want) acc += p0;
+			if (s1 == want) acc += p1;
+			if (s2 == want) acc += p2;
+			if (s3 == want) acc += p3;
+		}
+		for (; i < count; i++)
+		{
+			const uint32_t m = mem[i];
+			if (side[i] == want) acc += __ldg(vecs + (size_t)m * D + c) * __ldg(wf + m);
+		}
+		return acc;
+	}
+
+	// double sum over the listed positions with side[i] == want of the float terms tval[i], in list order
+	__device__ double serial_term_sum(const float* tval, const uint8_t* side, uint32_t count, uint32_t want)
+	{
+		double acc = 0.0;
+		uint32_t i = 0;
+		for (; i + 4 <= count; i += 4)
+		{
+			const float t0 = tval[i], t1 = tval[i + 1], t2 = tval[i + 2], t3 = tval[i + 3];
+			const uint32_t s0 = side[i], s1 = side[i + 1], s2 = side[i + 2], s3 = side[i + 3];
+			if (s0 == want) acc += (double)t0;
+			if (s1 == want) acc += (double)t1;
+			if (s2 == want) acc += (double)t2;
+			if (s3 == want) acc += (double)t3;
+		}
+		for (; i < count; i++) if (side[i] == want) acc += (double)tval[i];
+		return acc;
+	}
+
 	// ---- prepare_root (enc.h:1696-1721) -------------------------------------------------------------------------------------
 
 	template<int D, int NT> __global__ void __launch_bounds__(NT) k_tsvq_root(const float* __restrict__ vecs, const float* __restrict__ wf, const unsigned long long* __restrict__ w64,
-		const uint32_t* __restrict__ members, node_rec<D>* nodes, const uint32_t* __restrict__ root_ids, root_out* out)
+		const uint32_t* __restrict__ members, uint8_t* side, float* tval, node_rec<D>* nodes, const uint32_t* __restrict__ root_ids, root_out* out)
 	{
-		__shared__ double s_part[(NT / 32) * (D + 2)];
-		__shared__ double s_out[D + 2];
+		__shared__ double s_part[(NT / 32) * 1];
+		__shared__ double s_out[1];
+		__shared__ float s_sum[D];
+		__shared__ double s_tt;
 		node_rec<D>& nd = nodes[root_ids[blockIdx.x]];
 		const uint32_t start = nd.start, count = nd.count;
-		float acc[D];
-#pragma unroll
-		for (int c = 0; c < D; c++) acc[c] = 0.0f;
-		double tt = 0, wsum = 0;
+		double wsum = 0;
 		for (uint32_t i = threadIdx.x; i < count; i += NT)
 		{
 			const uint32_t m = members[start + i];
 			float v[D];
 			load_vec<D>(vecs, m, v);
-			const float w = wf[m];
-#pragma unroll
-			for (int c = 0; c < D; c++) acc[c] += v[c] * w;
-			tt += (double)(dot_f<D>(v, v) * w);
-			wsum += (double)w64[m];
+			tval[start + i] = dot_f<D>(v, v) * wf[m]; // ttsum += v.dot(v) * weight
+			side[start + i] = 0;
+			wsum += (double)w64[m]; // integers: exact in any order
 		}
-		block_sum<D + 2, NT>([&](int k) -> double { return k < D ? (double)acc[k] : (k == D ? tt : wsum); }, s_part, s_out);
+		block_sum<1, NT>([&](int) -> double { return wsum; }, s_part, s_out);
+		if (threadIdx.x < D) s_sum[threadIdx.x] = serial_comp_sum<D>(vecs, wf, members + start, side + start, count, (int)threadIdx.x, 0);
+		else if (threadIdx.x == D) s_tt = serial_term_sum(tval + start, side + start, count, 0);
+		__syncthreads();
 		if (!threadIdx.x)
 		{
 			float org[D];
-			for (int c = 0; c < D; c++) org[c] = (float)s_out[c];
-			const unsigned long long weight = (unsigned long long)s_out[D + 1];
-			const float var = (float)(s_out[D] - (double)(dot_f<D>(org, org) / (float)weight));
+			for (int c = 0; c < D; c++) org[c] = s_sum[c];
+			const unsigned long long weight = (unsigned long long)s_out[0];
+			const float var = (float)(s_tt - (double)(dot_f<D>(org, org) / (float)weight));
 			const float inv = 1.0f / (float)weight;
 			for (int c = 0; c < D; c++) nd.origin[c] = org[c] * inv;
 			nd.weight = weight;
@@ -212,41 +263,6 @@ namespace
 	}
 
 	// ---- split_node ----------------------------------------------------------------------------------------------------------
-
-	template<int D, int X0, int X1> struct cov_count { enum { value = (X1 - X0) * D - (X1 * (X1 - 1) / 2 - X0 * (X0 - 1) / 2) }; };
-
-	// Rows X0..X1-1 of the upper triangle of sum_i (v_i - o)[x] * (w_i * (v_i - o))[y]   (compute_split_axis, enc.h:1811-1822)
-	template<int D, int NT, int X0, int X1> __device__ void cov_pass(const float* __restrict__ vecs, const float* __restrict__ wf, const uint32_t* members, uint32_t start, uint32_t count,
-		const float* s_origin, float* s_cov, double* s_part, double* s_out)
-	{
-		constexpr int K = cov_count<D, X0, X1>::value;
-		float acc[K];
-#pragma unroll
-		for (int k = 0; k < K; k++) acc[k] = 0.0f;
-		for (uint32_t i = threadIdx.x; i < count; i += NT)
-		{
-			const uint32_t m = members[start + i];
-			float v[D];
-			load_vec<D>(vecs, m, v);
-			const float w = wf[m];
-#pragma unroll
-			for (int c = 0; c < D; c++) v[c] -= s_origin[c];
-			int k = 0;
-#pragma unroll
-			for (int x = X0; x < X1; x++)
-#pragma unroll
-				for (int y = x; y < D; y++) acc[k++] += v[x] * (w * v[y]);
-		}
-		block_sum<K, NT>([&](int k) -> double { return (double)acc[k]; }, s_part, s_out);
-		if (threadIdx.x < K)
-		{
-			// k -> (x, y)
-			int k = threadIdx.x, x = X0;
-			while (k >= D - x) { k -= D - x; x++; }
-			s_cov[x * D + x + k] = (float)s_out[threadIdx.x];
-		}
-		__syncthreads();
-	}
 
 	template<int D> __device__ void pca_axis(float* cm, float renorm, float* axis_out) // compute_split_axis tail + compute_pca_from_covar (enc.h:1831-1845, 606-649)
 	{
@@ -277,67 +293,75 @@ namespace
 	}
 
 	template<int D, int NT> __global__ void __launch_bounds__(NT) k_tsvq_split(const float* __restrict__ vecs, const float* __restrict__ wf, const unsigned long long* __restrict__ w64,
-		uint32_t* members, uint32_t* tmp, uint8_t* side, node_rec<D>* nodes, const uint32_t* __restrict__ frontier, uint32_t child_base, split_out* out)
+		uint32_t* members, uint32_t* tmp, uint8_t* side, float* tval, node_rec<D>* nodes, const uint32_t* __restrict__ frontier, uint32_t child_base, split_out* out)
 	{
-		constexpr int KMAX = 2 * D + 5 > 36 ? 2 * D + 5 : 36;
-		__shared__ double s_part[(NT / 32) * KMAX];
-		__shared__ double s_out[KMAX];
-		__shared__ float s_origin[D], s_axis[D], s_l[D], s_r[D], s_cov[D * D];
+		constexpr int NE = D * (D + 1) / 2; // upper-triangle entries of the covariance matrix, one thread each
+		static_assert(NT >= NE && NT >= 2 * D + 2, "one thread per accumulator");
+		__shared__ double s_part[(NT / 32) * 3];
+		__shared__ double s_out[3];
+		__shared__ float s_origin[D], s_axis[D], s_l[D], s_r[D], s_cov[D * D], s_sum[2 * D];
+		__shared__ double s_tt[2];
 		__shared__ uint32_t s_warp[NT / 32];
 
 		const uint32_t tid = threadIdx.x;
 		const node_rec<D> nd = nodes[frontier[blockIdx.x]];
 		const uint32_t start = nd.start, count = nd.count;
+		const uint32_t* mem = members + start;
+		uint8_t* sd = side + start;
+		float* tv = tval + start;
 		if (tid < D) s_origin[tid] = nd.origin[tid];
 		__syncthreads();
 
 		// ---- prep_split (enc.h:1848-1960)
 		if (count == 2)
 		{
-			if (tid < D) { s_l[tid] = vecs[(size_t)members[start] * D + tid]; s_r[tid] = vecs[(size_t)members[start + 1] * D + tid]; }
+			if (tid < D) { s_l[tid] = vecs[(size_t)mem[0] * D + tid]; s_r[tid] = vecs[(size_t)mem[1] * D + tid]; }
 			__syncthreads();
 		}
 		else
 		{
-			if constexpr (D == 6) cov_pass<D, NT, 0, D>(vecs, wf, members, start, count, s_origin, s_cov, s_part, s_out);
-			else
+			// covariance (compute_split_axis, enc.h:1811-1822; the SSE4.1 16x16 kernel computes the same per-entry sums): entry (x, y >= x)
+			if (tid < NE)
 			{
-				// 136 upper-triangle entries in five passes of <= 33 register accumulators each
-				cov_pass<D, NT, 0, 2>(vecs, wf, members, start, count, s_origin, s_cov, s_part, s_out);
-				cov_pass<D, NT, 2, 4>(vecs, wf, members, start, count, s_origin, s_cov, s_part, s_out);
-				cov_pass<D, NT, 4, 7>(vecs, wf, members, start, count, s_origin, s_cov, s_part, s_out);
-				cov_pass<D, NT, 7, 11>(vecs, wf, members, start, count, s_origin, s_cov, s_part, s_out);
-				cov_pass<D, NT, 11, D>(vecs, wf, members, start, count, s_origin, s_cov, s_part, s_out);
+				int k = (int)tid, x = 0;
+				while (k >= D - x) { k -= D - x; x++; }
+				const int y = x + k;
+				const float ox = s_origin[x], oy = s_origin[y];
+				float acc = 0.0f;
+				for (uint32_t i = 0; i < count; i++)
+				{
+					const uint32_t m = mem[i];
+					const float vx = __ldg(vecs + (size_t)m * D + x) - ox, vy = __ldg(vecs + (size_t)m * D + y) - oy;
+					acc = acc + vx * (__ldg(wf + m) * vy);
+				}
+				s_cov[x * D + y] = acc;
 			}
+			__syncthreads();
 			if (!tid) pca_axis<D>(s_cov, 1.0f / (float)nd.weight, s_axis);
 			__syncthreads();
 
 			for (int mode = 0; mode < 2; mode++) // 0: side of the principal axis; 1: the reference's fallback (first half / second half of the member list)
 			{
-				float la[D], ra[D];
-#pragma unroll
-				for (int c = 0; c < D; c++) la[c] = ra[c] = 0.0f;
 				double lw = 0, rw = 0;
 				const uint32_t half = count / 2;
 				for (uint32_t i = tid; i < count; i += NT)
 				{
-					const uint32_t m = members[start + i];
-					float v[D], dv[D];
+					const uint32_t m = mem[i];
+					float v[D];
 					load_vec<D>(vecs, m, v);
-					const float w = wf[m];
 #pragma unroll
-					for (int c = 0; c < D; c++) dv[c] = v[c] - s_origin[c];
-					const bool right = mode ? (i >= half) : (dot_f<D>(dv, s_axis) >= 0.0f);
-					if (right) { for (int c = 0; c < D; c++) ra[c] += v[c] * w; rw += (double)w; }
-					else { for (int c = 0; c < D; c++) la[c] += v[c] * w; lw += (double)w; }
+					for (int c = 0; c < D; c++) v[c] -= s_origin[c];
+					const bool right = mode ? (i >= half) : (dot_f<D>(v, s_axis) >= 0.0f);
+					sd[i] = right ? 1 : 0;
+					if (right) rw += (double)wf[m]; else lw += (double)wf[m]; // double sums of float-valued integers: exact in any order
 				}
-				block_sum<2 * D + 2, NT>([&](int k) -> double { return k < D ? (double)la[k] : (k < 2 * D ? (double)ra[k - D] : (k == 2 * D ? lw : rw)); }, s_part, s_out);
-				const double l_weight = s_out[2 * D], r_weight = s_out[2 * D + 1];
-				if (l_weight > 0.0 && r_weight > 0.0)
-				{
-					if (tid < D) { s_l[tid] = (float)s_out[tid] * (float)(1.0f / l_weight); s_r[tid] = (float)s_out[D + tid] * (float)(1.0f / r_weight); }
-					break;
-				}
+				block_sum<2, NT>([&](int k) -> double { return k ? rw : lw; }, s_part, s_out);
+				const double l_weight = s_out[0], r_weight = s_out[1];
+				if (!(l_weight > 0.0 && r_weight > 0.0)) continue;
+				if (tid < 2 * D) s_sum[tid] = serial_comp_sum<D>(vecs, wf, mem, sd, count, (int)(tid % D), tid / D);
+				__syncthreads();
+				if (tid < D) { s_l[tid] = s_sum[tid] * (float)(1.0f / l_weight); s_r[tid] = s_sum[D + tid] * (float)(1.0f / r_weight); }
+				break;
 			}
 			__syncthreads();
 		}
@@ -352,16 +376,12 @@ namespace
 		{
 			for (int degenerate = 0; degenerate < 2; degenerate++)
 			{
-				float la[D], ra[D];
-#pragma unroll
-				for (int c = 0; c < D; c++) la[c] = ra[c] = 0.0f;
-				double ltt = 0, rtt = 0, lw = 0, rw = 0, lc = 0;
+				double lw = 0, rw = 0, lc = 0;
 				for (uint32_t i = tid; i < count; i += NT)
 				{
-					const uint32_t m = members[start + i];
+					const uint32_t m = mem[i];
 					float v[D];
 					load_vec<D>(vecs, m, v);
-					const float w = wf[m];
 					bool right;
 					if (!degenerate)
 					{
@@ -371,25 +391,26 @@ namespace
 						right = ld >= rd;
 					}
 					else right = (i == 0); // members are unique vectors, so only the first one equals "firstVec" (enc.h:2037-2061)
-					const double tt = (double)((float)w64[m] * dot_f<D>(v, v));
-					if (right) { for (int c = 0; c < D; c++) ra[c] += v[c] * w; rw += (double)w64[m]; rtt += tt; }
-					else { for (int c = 0; c < D; c++) la[c] += v[c] * w; lw += (double)w64[m]; ltt += tt; lc += 1.0; }
-					side[start + i] = right ? 1 : 0;
+					tv[i] = (float)w64[m] * dot_f<D>(v, v); // weight * v.dot(v)
+					sd[i] = right ? 1 : 0;
+					if (right) rw += (double)w64[m]; else { lw += (double)w64[m]; lc += 1.0; }
 				}
-				block_sum<2 * D + 5, NT>([&](int k) -> double {
-					return k < D ? (double)la[k] : (k < 2 * D ? (double)ra[k - D] : (k == 2 * D ? ltt : (k == 2 * D + 1 ? rtt : (k == 2 * D + 2 ? lw : (k == 2 * D + 3 ? rw : lc))))); }, s_part, s_out);
-				l_weight = (unsigned long long)s_out[2 * D + 2]; r_weight = (unsigned long long)s_out[2 * D + 3];
-				l_count = (uint32_t)s_out[2 * D + 4];
+				block_sum<3, NT>([&](int k) -> double { return k == 0 ? lw : (k == 1 ? rw : lc); }, s_part, s_out);
+				l_weight = (unsigned long long)s_out[0]; r_weight = (unsigned long long)s_out[1];
+				l_count = (uint32_t)s_out[2];
 				if (l_weight && r_weight) break;
 			}
 			if (!l_weight || !r_weight) { ok = false; break; }
+			if (tid < 2 * D) s_sum[tid] = serial_comp_sum<D>(vecs, wf, mem, sd, count, (int)(tid % D), tid / D);
+			else if (tid < 2 * D + 2) s_tt[tid - 2 * D] = serial_term_sum(tv, sd, count, tid - 2 * D);
+			__syncthreads();
 			float nl[D], nr[D];
 #pragma unroll
-			for (int c = 0; c < D; c++) { nl[c] = (float)s_out[c]; nr[c] = (float)s_out[D + c]; }
-			l_var = (float)(s_out[2 * D] - (double)(dot_f<D>(nl, nl) / (float)l_weight));
-			r_var = (float)(s_out[2 * D + 1] - (double)(dot_f<D>(nr, nr) / (float)r_weight));
+			for (int c = 0; c < D; c++) { nl[c] = s_sum[c]; nr[c] = s_sum[D + c]; }
+			l_var = (float)(s_tt[0] - (double)(dot_f<D>(nl, nl) / (float)l_weight));
+			r_var = (float)(s_tt[1] - (double)(dot_f<D>(nr, nr) / (float)r_weight));
 			const float il = 1.0f / (float)l_weight, ir = 1.0f / (float)r_weight;
-			__syncthreads(); // every thread has read s_out and the old centroids
+			__syncthreads(); // every thread has read the sums and the old centroids
 			if (tid < D) { s_l[tid] = nl[tid] * il; s_r[tid] = nr[tid] * ir; }
 			__syncthreads();
 			const float total_var = l_var + r_var;
@@ -411,8 +432,8 @@ namespace
 		{
 			const uint32_t i = c0 + tid;
 			const bool valid = i < count;
-			const uint32_t m = valid ? members[start + i] : 0;
-			const bool left = valid && !side[start + i];
+			const uint32_t m = valid ? mem[i] : 0;
+			const bool left = valid && !sd[i];
 			const uint32_t mask = __ballot_sync(0xffffffffu, left);
 			const uint32_t lane = tid & 31, warp = tid >> 5;
 			if (!lane) s_warp[warp] = __popc(mask);
@@ -578,8 +599,8 @@ namespace
 			if (!st->frontier.reserve((size_t)n * 4) || !st->results.reserve((size_t)n * sizeof(root_out))) { ctx->fail("b200_tsvq_generate: out of device memory"); return false; }
 			if (cudaMemcpyAsync(st->nodes.as<node_rec<D>>() + base, recs.data(), (size_t)n * sizeof(node_rec<D>), cudaMemcpyHostToDevice, ctx->stream) != cudaSuccess) return false;
 			if (cudaMemcpyAsync(st->frontier.p, rid.data(), (size_t)n * 4, cudaMemcpyHostToDevice, ctx->stream) != cudaSuccess) return false;
-			k_tsvq_root<D, 512><<<n, 512, 0, ctx->stream>>>(st->uvec.as<float>(), st->uwf.as<float>(), st->uw64.as<unsigned long long>(), st->members.as<uint32_t>(),
-				st->nodes.as<node_rec<D>>(), st->frontier.as<uint32_t>(), st->results.as<root_out>());
+			k_tsvq_root<D, 256><<<n, 256, 0, ctx->stream>>>(st->uvec.as<float>(), st->uwf.as<float>(), st->uw64.as<unsigned long long>(), st->members.as<uint32_t>(),
+				st->side.as<uint8_t>(), st->tval.as<float>(), st->nodes.as<node_rec<D>>(), st->frontier.as<uint32_t>(), st->results.as<root_out>());
 			ctx->launches++; __atomic_add_fetch(&g_b200_total_launches, 1, __ATOMIC_RELAXED);
 			std::vector<root_out> ro(n);
 			if (cudaMemcpyAsync(ro.data(), st->results.p, (size_t)n * sizeof(root_out), cudaMemcpyDeviceToHost, ctx->stream) != cudaSuccess) return false;
@@ -602,16 +623,17 @@ namespace
 			if (!st->frontier.reserve((size_t)n * 4) || !st->results.reserve((size_t)n * sizeof(split_out))) { ctx->fail("b200_tsvq_generate: out of device memory"); return false; }
 			if (cudaMemcpyAsync(st->frontier.p, order.data(), (size_t)n * 4, cudaMemcpyHostToDevice, ctx->stream) != cudaSuccess) return false;
 			const float* vecs = st->uvec.as<float>(); const float* wf = st->uwf.as<float>(); const unsigned long long* w64 = st->uw64.as<unsigned long long>();
-			uint32_t* members = st->members.as<uint32_t>(); uint32_t* tmp = st->tmp_members.as<uint32_t>(); uint8_t* side = st->side.as<uint8_t>();
+			uint32_t* members = st->members.as<uint32_t>(); uint32_t* tmp = st->tmp_members.as<uint32_t>(); uint8_t* side = st->side.as<uint8_t>(); float* tval = st->tval.as<float>();
+			constexpr int NT_SMALL = (D == 6) ? 64 : 160; // >= D (D + 1) / 2 accumulator threads
 			node_rec<D>* nodes = st->nodes.as<node_rec<D>>();
 			if (n_big)
 			{
-				k_tsvq_split<D, 512><<<n_big, 512, 0, ctx->stream>>>(vecs, wf, w64, members, tmp, side, nodes, st->frontier.as<uint32_t>(), child_base, st->results.as<split_out>());
+				k_tsvq_split<D, 256><<<n_big, 256, 0, ctx->stream>>>(vecs, wf, w64, members, tmp, side, tval, nodes, st->frontier.as<uint32_t>(), child_base, st->results.as<split_out>());
 				ctx->launches++; __atomic_add_fetch(&g_b200_total_launches, 1, __ATOMIC_RELAXED);
 			}
 			if (n > n_big)
 			{
-				k_tsvq_split<D, 64><<<n - n_big, 64, 0, ctx->stream>>>(vecs, wf, w64, members, tmp, side, nodes, st->frontier.as<uint32_t>() + n_big, child_base + 2 * n_big, st->results.as<split_out>() + n_big);
+				k_tsvq_split<D, NT_SMALL><<<n - n_big, NT_SMALL, 0, ctx->stream>>>(vecs, wf, w64, members, tmp, side, tval, nodes, st->frontier.as<uint32_t>() + n_big, child_base + 2 * n_big, st->results.as<split_out>() + n_big);
 				ctx->launches++; __atomic_add_fetch(&g_b200_total_launches, 1, __ATOMIC_RELAXED);
 			}
 			std::vector<split_out> so(n);
@@ -765,7 +787,7 @@ extern "C" int b200_tsvq_generate(b200_context* ctx, uint32_t dim, uint32_t num_
 
 	if (!st->raw.reserve((size_t)n * stride_bytes) || !st->tv.reserve((size_t)n * dim * 4) || !st->tw.reserve((size_t)n * 8) || !st->perm[0].reserve((size_t)n * 4) || !st->perm[1].reserve((size_t)n * 4) ||
 		!st->keys[0].reserve((size_t)n * 4) || !st->keys[1].reserve((size_t)n * 4) || !st->heads.reserve((size_t)n * 4) || !st->gid.reserve((size_t)n * 4) || !st->gstart.reserve(((size_t)n + 1) * 4) ||
-		!st->uvec.reserve((size_t)n * dim * 4) || !st->uw64.reserve((size_t)n * 8) || !st->uwf.reserve((size_t)n * 4) || !st->members.reserve((size_t)n * 4) || !st->tmp_members.reserve((size_t)n * 4) || !st->side.reserve(n))
+		!st->uvec.reserve((size_t)n * dim * 4) || !st->uw64.reserve((size_t)n * 8) || !st->uwf.reserve((size_t)n * 4) || !st->members.reserve((size_t)n * 4) || !st->tmp_members.reserve((size_t)n * 4) || !st->side.reserve(n) || !st->tval.reserve((size_t)n * 4))
 	{ ctx->fail("b200_tsvq_generate: out of device memory"); return 0; }
 
 	TSVQ_OK(cudaEventRecord(ctx->ev0, ctx->stream));

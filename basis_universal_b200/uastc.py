@@ -121,6 +121,27 @@ class Encoder:
         self._check(ok, "b200_uastc_rdo")
         return blocks
 
+    def uastc_rdo_batch(self, uastc_blocks, source_blocks, slice_num_blocks, params=None, flags=cPackUASTCLevelDefault, total_jobs=4):
+        """uastc_rdo over several slices laid end to end (the per-slice loop of comp.cpp:1996-2089): every chain of every slice
+        runs concurrently. Same result as one uastc_rdo call per slice. Returns the modified (N, 16) array."""
+        blocks = np.ascontiguousarray(uastc_blocks, np.uint8).copy()
+        src = np.ascontiguousarray(source_blocks, np.uint8)
+        counts = np.ascontiguousarray(slice_num_blocks, np.uint32)
+        if blocks.shape[0] != src.shape[0] or blocks.shape[1] != 16 or src.shape[1] != 64 or int(counts.sum()) != blocks.shape[0]:
+            raise ValueError("uastc_blocks must be (N,16), source_blocks (N,64) and the slice sizes must add up to N")
+        p = params if params is not None else uastc_rdo_params()
+        ok = self._lib.b200_uastc_rdo_batch(self._ctx, counts.shape[0], counts.ctypes.data, blocks.ctypes.data, src.ctypes.data, ctypes.byref(p), int(flags), int(total_jobs))
+        self._check(ok, "b200_uastc_rdo_batch")
+        return blocks
+
+    def uastc_rdo_batch_device(self, d_uastc_ptr, d_source_ptr, slice_num_blocks, params=None, flags=cPackUASTCLevelDefault, total_jobs=4):
+        """Device-resident form of uastc_rdo_batch: the encoder's output is post-processed in place in HBM."""
+        counts = np.ascontiguousarray(slice_num_blocks, np.uint32)
+        p = params if params is not None else uastc_rdo_params()
+        ok = self._lib.b200_uastc_rdo_batch_device(self._ctx, counts.shape[0], counts.ctypes.data, ctypes.c_void_p(d_uastc_ptr), ctypes.c_void_p(d_source_ptr),
+                                                   ctypes.byref(p), int(flags), int(total_jobs))
+        self._check(ok, "b200_uastc_rdo_batch_device")
+
     def encode_uastc_device(self, d_blocks_ptr, num_blocks, d_out_ptr, flags=cPackUASTCLevelDefault):
         """Device-resident form: raw device pointers (e.g. torch tensor .data_ptr()) to (N,64) and (N,16) uint8 buffers."""
         ok = self._lib.b200_uastc_encode_blocks_device(self._ctx, ctypes.c_void_p(d_blocks_ptr), int(num_blocks), ctypes.c_void_p(d_out_ptr), int(flags))

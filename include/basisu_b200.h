@@ -73,6 +73,16 @@ typedef struct b200_uastc_rdo_params
 } b200_uastc_rdo_params;
 int b200_uastc_rdo(b200_context* ctx, uint32_t num_blocks, void* pBlocks, const void* pBlock_pixels,
 	const b200_uastc_rdo_params* params, uint32_t flags, uint32_t total_jobs);
+/* On failure (0) pBlocks is left untouched, so the caller may run its own CPU uastc_rdo on the encoder's output. */
+
+/* Many slices in one call: pSlice_num_blocks[s] blocks per slice, the slices' blocks (and source texels) laid end to end.
+ * Equivalent to calling uastc_rdo once per slice with the same parameters and total_jobs (the loop at comp.cpp:1996-2089 over
+ * slices), but every chain of every slice runs concurrently (a chain is sequential; chains and slices are independent).
+ * The _device form takes DEVICE pointers (e.g. the output of b200_uastc_encode_blocks_device) and leaves the result there. */
+int b200_uastc_rdo_batch(b200_context* ctx, uint32_t num_slices, const uint32_t* pSlice_num_blocks, void* pBlocks, const void* pBlock_pixels,
+	const b200_uastc_rdo_params* params, uint32_t flags, uint32_t total_jobs);
+int b200_uastc_rdo_batch_device(b200_context* ctx, uint32_t num_slices, const uint32_t* pSlice_num_blocks, void* dBlocks, const void* dBlock_pixels,
+	const b200_uastc_rdo_params* params, uint32_t flags, uint32_t total_jobs);
 
 /* ---- ETC1S frontend per-block stages: the reference's existing GPU seam, symbol for symbol ------------------------------ */
 /* Packed argument structs are the reference's (encoder/basisu_opencl.h:36-135), restated in C. */

@@ -46,6 +46,7 @@ namespace basisu
 	static bool report(opencl_context_ptr p, int ok, const char* what)
 	{
 		if (!ok) error_printf("%s (b200): %s\n", what, b200_last_error(p ? p->m_ctx : nullptr));
+		else if (p) debug_printf("[b200] %s: %3.3f ms of kernels, %u launches\n", what, b200_last_kernel_ms(p->m_ctx), b200_last_launch_count(p->m_ctx));
 		return ok != 0;
 	}
 

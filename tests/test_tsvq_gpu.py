@@ -2,8 +2,8 @@
   b200_tsvq_generate                     vs generate_hierarchical_codebook_threaded (enc.h:2219) in the compiled reference
   b200_etc1s_encode_endpoint_clusters    vs the CPU path of generate_endpoint_codebook (frontend.cpp:1493-1549)
   b200_etc1s_optimize_selector_codebook  vs create_optimized_selector_codebook (frontend.cpp:2259-2345)
-The last two are integer stages: bit-exact. The clusterer's sums are parallel reductions instead of the reference's serial float
-sums, so its bar is the codebook itself: same cluster count, (nearly) the same partition, distortion within 0.1 %."""
+All bit-exact: the last two are integer stages, and the clusterer accumulates every float sum in the reference's member order
+(b200_tsvq.cu, "serial sums"), so clusters, their order and the order of their members equal the CPU's."""
 import ctypes
 
 import numpy as np
@@ -52,6 +52,18 @@ def labels(n, clusters):
     return lab
 
 
+def same_clusters(got, want):
+    w = {c.tobytes() for c in want}
+    return sum(1 for c in got if c.tobytes() in w)
+
+
+def assert_same_codebook(got, want):
+    """same clusters, in the same order, each listing its training vectors in the same order"""
+    assert len(got) == len(want)
+    for i, (a, b) in enumerate(zip(got, want)):
+        assert np.array_equal(a, b), f"cluster {i} differs"
+
+
 def check_partition(n, clusters):
     allidx = np.concatenate(clusters)
     assert allidx.shape[0] == n and np.array_equal(np.sort(allidx), np.arange(n)), "clusters must partition the training set"
@@ -80,15 +92,11 @@ def test_tsvq_endpoints_matches_reference(ctx, ref, max_codebook, max_parent):
     got, got_par, info = ctx.tsvq_generate(vecs, weights, max_codebook, max_parent, 1, True)
     n = vecs.shape[0]
     check_partition(n, got)
-    assert len(got) == len(want) and len(got_par) == len(want_par)
-    if got_par:
-        check_partition(n, got_par)
     d_ref, d_gpu = distortion(vecs, weights, want), distortion(vecs, weights, got)
-    same = float(np.mean(labels(n, got) == labels(n, want)))
     print(f"endpoints {max_codebook}/{max_parent}: {info['num_unique']} unique of {n}, {len(got)} clusters, {info['rounds']} rounds, {info['nodes_split']} splits, "
-          f"{info['device_ms']:.2f} ms; distortion ref {d_ref:.6f} gpu {d_gpu:.6f}; identical labels {same:.4f}")
-    assert abs(d_gpu - d_ref) <= 1e-3 * d_ref
-    assert same >= 0.98
+          f"{info['device_ms']:.2f} ms; distortion ref {d_ref:.6f} gpu {d_gpu:.6f}; identical clusters {same_clusters(got, want)} of {len(want)}")
+    assert_same_codebook(got, want)
+    assert_same_codebook(got_par, want_par)
     # every child cluster lies inside one parent cluster (frontend.cpp:918-940 verifies this and aborts otherwise)
     if got_par:
         plab = labels(n, got_par)
@@ -116,13 +124,11 @@ def test_tsvq_selectors_matches_reference(ctx, ref, max_codebook, max_parent):
     got, got_par, info = ctx.tsvq_generate(vecs, weights, max_codebook, max_parent, 1, False)
     n = vecs.shape[0]
     check_partition(n, got)
-    assert len(got) == len(want) and len(got_par) == len(want_par)
     d_ref, d_gpu = distortion(vecs, weights, want), distortion(vecs, weights, got)
-    same = float(np.mean(labels(n, got) == labels(n, want)))
     print(f"selectors {max_codebook}/{max_parent}: {info['num_unique']} unique of {n}, {len(got)} clusters, {info['rounds']} rounds, {info['nodes_split']} splits, "
-          f"{info['device_ms']:.2f} ms; distortion ref {d_ref:.4f} gpu {d_gpu:.4f}; identical labels {same:.4f}")
-    assert abs(d_gpu - d_ref) <= 1e-3 * d_ref
-    assert same >= 0.98
+          f"{info['device_ms']:.2f} ms; distortion ref {d_ref:.4f} gpu {d_gpu:.4f}; identical clusters {same_clusters(got, want)} of {len(want)}")
+    assert_same_codebook(got, want)
+    assert_same_codebook(got_par, want_par)
 
 
 def test_tsvq_small_and_degenerate_sets(ctx, ref):
@@ -134,8 +140,7 @@ def test_tsvq_small_and_degenerate_sets(ctx, ref):
         want, _ = ref_tsvq(ref, vecs, weights, cb, 0)
         got, _, _ = ctx.tsvq_generate(vecs, weights, cb, 0)
         check_partition(n, got)
-        assert len(got) == len(want), (n, dim, cb)
-        assert abs(distortion(vecs, weights, got) - distortion(vecs, weights, want)) <= 1e-3 * max(distortion(vecs, weights, want), 1e-9) + 1e-9
+        assert_same_codebook(got, want)
 
 
 def test_tsvq_two_level_path(ctx, ref):
@@ -150,9 +155,9 @@ def test_tsvq_two_level_path(ctx, ref):
     check_partition(n, got_par)
     want, want_par = ref_tsvq(ref, vecs, weights, 1024, 32, 8, False)
     print(f"two-level: {len(got)} clusters / {len(got_par)} parents (reference {len(want)} / {len(want_par)}), {info['rounds']} rounds, {info['device_ms']:.1f} ms")
-    assert len(got) == len(want) and len(got_par) == len(want_par)
-    d_ref, d_gpu = distortion(vecs, weights, want), distortion(vecs, weights, got)
-    assert abs(d_gpu - d_ref) <= 2e-3 * d_ref
+    print(f"identical clusters {same_clusters(got, want)} of {len(want)}")
+    assert_same_codebook(got, want)
+    assert_same_codebook(got_par, want_par)
 
 
 @pytest.mark.parametrize("perceptual", [0, 1])
