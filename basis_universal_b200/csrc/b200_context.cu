@@ -28,6 +28,7 @@ extern "C" b200_context* b200_create_context(int device_index)
 	memset(ctx, 0, sizeof(*ctx));
 	ctx->device = device_index;
 	ctx->etc_flavour = B200_ETC1S_FLAVOUR_CPU_OPTIMIZER;
+	ctx->world = 1;
 	if ((e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking)) != cudaSuccess ||
 		(e = cudaEventCreate(&ctx->ev0)) != cudaSuccess || (e = cudaEventCreate(&ctx->ev1)) != cudaSuccess ||
 		(e = cudaEventCreate(&ctx->ev_t0)) != cudaSuccess || (e = cudaEventCreate(&ctx->ev_t1)) != cudaSuccess)
@@ -47,6 +48,7 @@ extern "C" void b200_destroy_context(b200_context* ctx)
 	cudaSetDevice(ctx->device);
 	cudaStreamSynchronize(ctx->stream);
 	b200_tsvq_release(ctx);
+	b200_comm_release(ctx);
 	void* bufs[] = { ctx->d_in, ctx->d_out, ctx->d_meta, ctx->d_cands, ctx->d_slots, ctx->d_lists, ctx->d_etc_blocks };
 	for (void* p : bufs) if (p) cudaFree(p);
 	for (void* p : ctx->d_aux) if (p) cudaFree(p);
@@ -83,3 +85,40 @@ extern "C" float b200_timer_stop_ms(b200_context* ctx)
 }
 
 extern "C" uint64_t b200_global_launch_count(void) { return g_b200_total_launches; }
+
+#include <mutex>
+static std::mutex g_stat_mutex;
+static float g_stat_ms[B200_STAT_COUNT];
+static uint32_t g_stat_launches[B200_STAT_COUNT], g_stat_calls[B200_STAT_COUNT];
+void g_b200_stat_add(int stat_id, float ms, uint32_t launches)
+{
+	std::lock_guard<std::mutex> lk(g_stat_mutex);
+	g_stat_ms[stat_id] += ms; g_stat_launches[stat_id] += launches; g_stat_calls[stat_id]++;
+}
+extern "C" int b200_stats_get(const b200_context* ctx, uint32_t id, float* pMs, uint32_t* pLaunches, uint32_t* pCalls)
+{
+	if (!ctx || id >= B200_STAT_COUNT) return 0;
+	if (pMs) *pMs = ctx->stat_ms[id];
+	if (pLaunches) *pLaunches = ctx->stat_launches[id];
+	if (pCalls) *pCalls = ctx->stat_calls[id];
+	return 1;
+}
+extern "C" void b200_stats_reset(b200_context* ctx)
+{
+	if (!ctx) return;
+	for (int i = 0; i < B200_STAT_COUNT; i++) { ctx->stat_ms[i] = 0; ctx->stat_launches[i] = 0; ctx->stat_calls[i] = 0; }
+}
+extern "C" int b200_global_stats_get(uint32_t id, float* pMs, uint32_t* pLaunches, uint32_t* pCalls)
+{
+	if (id >= B200_STAT_COUNT) return 0;
+	std::lock_guard<std::mutex> lk(g_stat_mutex);
+	if (pMs) *pMs = g_stat_ms[id];
+	if (pLaunches) *pLaunches = g_stat_launches[id];
+	if (pCalls) *pCalls = g_stat_calls[id];
+	return 1;
+}
+extern "C" void b200_global_stats_reset(void)
+{
+	std::lock_guard<std::mutex> lk(g_stat_mutex);
+	for (int i = 0; i < B200_STAT_COUNT; i++) { g_stat_ms[i] = 0; g_stat_launches[i] = 0; g_stat_calls[i] = 0; }
+}

@@ -28,18 +28,18 @@ __device__ __forceinline__ void load_block16(const uint4* __restrict__ blocks, u
 	}
 }
 
-__global__ void __launch_bounds__(128) k_etc1s_encode_blocks(const uint4* __restrict__ blocks, uint32_t n, uint64_t* __restrict__ out, int perceptual, uint32_t total_perms, int flavour)
+__global__ void __launch_bounds__(128) k_etc1s_encode_blocks(const uint4* __restrict__ blocks, uint32_t first, uint32_t n, uint64_t* __restrict__ out, int perceptual, uint32_t total_perms, int flavour)
 {
-	const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+	const uint32_t i = first + blockIdx.x * blockDim.x + threadIdx.x; // [first, n): this rank's block range
 	if (i >= n) return;
 	uint32_t px[16];
 	load_block16(blocks, i, px);
 	out[i] = etc1s_encode_block(&d_tables, perceptual != 0, total_perms, px, flavour);
 }
 
-__global__ void __launch_bounds__(128) k_etc1s_determine_selectors(const uint4* __restrict__ blocks, uint32_t n, const uint32_t* __restrict__ color5_inten, uint64_t* __restrict__ out, int perceptual)
+__global__ void __launch_bounds__(128) k_etc1s_determine_selectors(const uint4* __restrict__ blocks, uint32_t first, uint32_t n, const uint32_t* __restrict__ color5_inten, uint64_t* __restrict__ out, int perceptual)
 {
-	const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+	const uint32_t i = first + blockIdx.x * blockDim.x + threadIdx.x;
 	if (i >= n) return;
 	uint32_t px[16];
 	load_block16(blocks, i, px);
@@ -185,9 +185,9 @@ __global__ void __launch_bounds__(128) k_etc1s_pixel_clusters(const b200_pixel_c
 // Endpoint clusters as CSR lists of block indices into the resident source blocks; `order` lists the clusters largest first
 // so that the long ones start early (a cluster is one warp's serial work).
 __global__ void __launch_bounds__(128) k_etc1s_endpoint_clusters(const uint32_t* __restrict__ blocks, const uint32_t* __restrict__ offsets, const uint32_t* __restrict__ bidx,
-	const uint32_t* __restrict__ order, uint32_t total_clusters, uint64_t* __restrict__ out, int perceptual_i, uint32_t total_perms, int flavour)
+	const uint32_t* __restrict__ order, uint32_t total_clusters, uint64_t* __restrict__ out, int perceptual_i, uint32_t total_perms, int flavour, uint32_t rank, uint32_t world)
 {
-	const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+	const uint32_t warp = ((blockIdx.x * blockDim.x + threadIdx.x) >> 5) * world + rank, lane = threadIdx.x & 31; // every world-th cluster of the size-sorted order
 	if (warp >= total_clusters) return;
 	const uint32_t c = order[warp];
 	px_blocks_src src;
@@ -201,9 +201,9 @@ __global__ void __launch_bounds__(128) k_etc1s_endpoint_clusters(const uint32_t*
 // Lane = (half, texel): the two half-warps take alternate member blocks; each lane accumulates, for its texel, the error of the
 // four block colours of every member block (decoded from the block's own endpoint) against the source texel.
 __global__ void __launch_bounds__(128) k_etc1s_selector_codebook(const uint32_t* __restrict__ blocks, const uint2* __restrict__ etc_blocks, const uint32_t* __restrict__ offsets,
-	const uint32_t* __restrict__ bidx, uint32_t total_clusters, uint32_t* __restrict__ out, int perceptual_i)
+	const uint32_t* __restrict__ bidx, uint32_t total_clusters, uint32_t* __restrict__ out, int perceptual_i, uint32_t rank, uint32_t world)
 {
-	const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+	const uint32_t warp = ((blockIdx.x * blockDim.x + threadIdx.x) >> 5) * world + rank, lane = threadIdx.x & 31;
 	if (warp >= total_clusters) return;
 	const bool perceptual = perceptual_i != 0;
 	const uint32_t first = offsets[warp], last = offsets[warp + 1];
@@ -237,10 +237,10 @@ __global__ void __launch_bounds__(128) k_etc1s_selector_codebook(const uint32_t*
 
 // ---- refine_endpoint_clusterization ------------------------------------------------------------------------------------------
 
-__global__ void __launch_bounds__(128) k_etc1s_refine(const uint4* __restrict__ blocks, uint32_t n, const b200_block_info* __restrict__ info,
+__global__ void __launch_bounds__(128) k_etc1s_refine(const uint4* __restrict__ blocks, uint32_t first, uint32_t n, const b200_block_info* __restrict__ info,
 	const b200_endpoint_cluster* __restrict__ clusters, const uint32_t* __restrict__ sorted, uint32_t* __restrict__ out, int perceptual_i)
 {
-	const uint32_t gid = blockIdx.x * blockDim.x + threadIdx.x;
+	const uint32_t gid = first + blockIdx.x * blockDim.x + threadIdx.x; // position in the cluster-sorted order
 	if (gid >= n) return;
 	const uint32_t bi = sorted[gid];
 	const bool perceptual = perceptual_i != 0;
@@ -266,12 +266,12 @@ __global__ void __launch_bounds__(128) k_etc1s_refine(const uint4* __restrict__ 
 
 // ---- find_optimal_selector_clusters_for_each_block: one warp per block -------------------------------------------------------
 
-__global__ void __launch_bounds__(128) k_etc1s_fosc(const uint4* __restrict__ blocks, uint32_t n, const b200_fosc_block* __restrict__ info,
+__global__ void __launch_bounds__(128) k_etc1s_fosc(const uint4* __restrict__ blocks, uint32_t first, uint32_t n, const b200_fosc_block* __restrict__ info,
 	const uint32_t* __restrict__ selectors, const uint32_t* __restrict__ cluster_indices, uint32_t* __restrict__ out, int perceptual_i)
 {
 	__shared__ uint32_t s_err[4][64]; // per warp: [selector 0..3][texel] errors
 	const uint32_t warp_in_cta = threadIdx.x >> 5, lane = threadIdx.x & 31;
-	const uint32_t bi = blockIdx.x * (blockDim.x >> 5) + warp_in_cta;
+	const uint32_t bi = first + blockIdx.x * (blockDim.x >> 5) + warp_in_cta;
 	if (bi >= n) return;
 	const bool perceptual = perceptual_i != 0;
 	const b200_fosc_block in = info[bi];
@@ -379,13 +379,32 @@ static bool upload(b200_context* ctx, int slot, const void* host, size_t bytes)
 	return true;
 }
 
-static int finish(b200_context* ctx, void* host_out, int slot, size_t bytes)
+// This rank's share [first, last) of n per-block units: contiguous ranges, i.e. block rows.
+static void shard_range(const b200_context* ctx, uint32_t n, uint32_t& first, uint32_t& last)
+{
+	if (ctx->world <= 1) { first = 0; last = n; return; }
+	const uint32_t per = (n + (uint32_t)ctx->world - 1) / (uint32_t)ctx->world;
+	first = (uint32_t)ctx->rank * per; if (first > n) first = n;
+	last = (first + per < n) ? first + per : n;
+}
+// With several ranks the output buffer is zeroed before the kernel so that the all-reduce in finish() is a merge.
+static bool shard_prepare_output(b200_context* ctx, int slot, size_t bytes)
+{
+	if (ctx->world <= 1) return true;
+	const cudaError_t e = cudaMemsetAsync(ctx->d_aux[slot], 0, bytes, ctx->stream);
+	if (e != cudaSuccess) { ctx->fail_cuda("cudaMemsetAsync", e); return false; }
+	return true;
+}
+
+static int finish(b200_context* ctx, void* host_out, int slot, size_t bytes, int stat_id)
 {
 	B200_CUDA_OK(ctx, cudaGetLastError());
 	B200_CUDA_OK(ctx, cudaEventRecord(ctx->ev1, ctx->stream));
+	if (!b200_merge_u32(ctx, ctx->d_aux[slot], bytes / 4)) return 0; // every output element is 4 or 8 bytes
 	B200_CUDA_OK(ctx, cudaMemcpyAsync(host_out, ctx->d_aux[slot], bytes, cudaMemcpyDeviceToHost, ctx->stream));
 	B200_CUDA_OK(ctx, cudaStreamSynchronize(ctx->stream));
 	B200_CUDA_OK(ctx, cudaEventElapsedTime(&ctx->last_ms, ctx->ev0, ctx->ev1));
+	ctx->account(stat_id);
 	return 1;
 }
 
@@ -416,9 +435,13 @@ extern "C" int b200_etc1s_encode_blocks(b200_context* ctx, void* pOutput_blocks,
 	const uint32_t n = ctx->etc_total_blocks;
 	if (!ctx->reserve(ctx->d_aux[0], ctx->aux_cap[0], (size_t)n * 8)) return 0;
 	ctx->launches = 1; __atomic_add_fetch(&g_b200_total_launches, 1, __ATOMIC_RELAXED);
+	uint32_t first, last;
+	shard_range(ctx, n, first, last);
+	if (!shard_prepare_output(ctx, 0, (size_t)n * 8)) return 0;
 	B200_CUDA_OK(ctx, cudaEventRecord(ctx->ev0, ctx->stream));
-	k_etc1s_encode_blocks<<<(n + 127) / 128, 128, 0, ctx->stream>>>(static_cast<const uint4*>(ctx->d_etc_blocks), n, static_cast<uint64_t*>(ctx->d_aux[0]), perceptual, total_perms, ctx->etc_flavour);
-	return finish(ctx, pOutput_blocks, 0, (size_t)n * 8);
+	if (last > first)
+		k_etc1s_encode_blocks<<<(last - first + 127) / 128, 128, 0, ctx->stream>>>(static_cast<const uint4*>(ctx->d_etc_blocks), first, last, static_cast<uint64_t*>(ctx->d_aux[0]), perceptual, total_perms, ctx->etc_flavour);
+	return finish(ctx, pOutput_blocks, 0, (size_t)n * 8, B200_STAT_ETC1S_ENCODE_BLOCKS);
 }
 
 extern "C" int b200_etc1s_encode_pixel_clusters(b200_context* ctx, void* pOutput_blocks, uint32_t total_clusters, const b200_pixel_cluster* pClusters,
@@ -438,7 +461,7 @@ extern "C" int b200_etc1s_encode_pixel_clusters(b200_context* ctx, void* pOutput
 	k_etc1s_pixel_clusters<<<(total_clusters + warps_per_cta - 1) / warps_per_cta, warps_per_cta * 32, 0, ctx->stream>>>(
 		static_cast<const b200_pixel_cluster*>(ctx->d_aux[1]), total_clusters, static_cast<const uint32_t*>(ctx->d_aux[2]),
 		static_cast<const uint32_t*>(ctx->d_aux[3]), static_cast<uint64_t*>(ctx->d_aux[0]), perceptual, total_perms, ctx->etc_flavour);
-	return finish(ctx, pOutput_blocks, 0, (size_t)total_clusters * 8);
+	return finish(ctx, pOutput_blocks, 0, (size_t)total_clusters * 8, B200_STAT_ETC1S_ENDPOINT_CLUSTERS);
 }
 
 extern "C" int b200_etc1s_refine_endpoint_clusterization(b200_context* ctx, const b200_block_info* pPixel_block_info, uint32_t total_clusters,
@@ -451,10 +474,14 @@ extern "C" int b200_etc1s_refine_endpoint_clusterization(b200_context* ctx, cons
 	if (!upload(ctx, 3, pSorted_block_indices, (size_t)n * 4)) return 0;
 	if (!ctx->reserve(ctx->d_aux[0], ctx->aux_cap[0], (size_t)n * 4)) return 0;
 	ctx->launches = 1; __atomic_add_fetch(&g_b200_total_launches, 1, __ATOMIC_RELAXED);
+	uint32_t first, last;
+	shard_range(ctx, n, first, last);
+	if (!shard_prepare_output(ctx, 0, (size_t)n * 4)) return 0;
 	B200_CUDA_OK(ctx, cudaEventRecord(ctx->ev0, ctx->stream));
-	k_etc1s_refine<<<(n + 127) / 128, 128, 0, ctx->stream>>>(static_cast<const uint4*>(ctx->d_etc_blocks), n, static_cast<const b200_block_info*>(ctx->d_aux[1]),
+	if (last > first)
+	k_etc1s_refine<<<(last - first + 127) / 128, 128, 0, ctx->stream>>>(static_cast<const uint4*>(ctx->d_etc_blocks), first, last, static_cast<const b200_block_info*>(ctx->d_aux[1]),
 		static_cast<const b200_endpoint_cluster*>(ctx->d_aux[2]), static_cast<const uint32_t*>(ctx->d_aux[3]), static_cast<uint32_t*>(ctx->d_aux[0]), perceptual);
-	return finish(ctx, pOutput_cluster_indices, 0, (size_t)n * 4);
+	return finish(ctx, pOutput_cluster_indices, 0, (size_t)n * 4, B200_STAT_ETC1S_REFINE);
 }
 
 extern "C" int b200_etc1s_find_optimal_selector_clusters_for_each_block(b200_context* ctx, const b200_fosc_block* pInput_block_info, uint32_t total_input_selectors,
@@ -467,12 +494,16 @@ extern "C" int b200_etc1s_find_optimal_selector_clusters_for_each_block(b200_con
 	if (!upload(ctx, 3, pSelector_cluster_indices, (size_t)total_input_selectors * 4)) return 0;
 	if (!ctx->reserve(ctx->d_aux[0], ctx->aux_cap[0], (size_t)n * 4)) return 0;
 	ctx->launches = 1; __atomic_add_fetch(&g_b200_total_launches, 1, __ATOMIC_RELAXED);
+	uint32_t first, last;
+	shard_range(ctx, n, first, last);
+	if (!shard_prepare_output(ctx, 0, (size_t)n * 4)) return 0;
 	B200_CUDA_OK(ctx, cudaEventRecord(ctx->ev0, ctx->stream));
 	const uint32_t warps_per_cta = 4;
-	k_etc1s_fosc<<<(n + warps_per_cta - 1) / warps_per_cta, warps_per_cta * 32, 0, ctx->stream>>>(static_cast<const uint4*>(ctx->d_etc_blocks), n,
+	if (last > first)
+	k_etc1s_fosc<<<(last - first + warps_per_cta - 1) / warps_per_cta, warps_per_cta * 32, 0, ctx->stream>>>(static_cast<const uint4*>(ctx->d_etc_blocks), first, last,
 		static_cast<const b200_fosc_block*>(ctx->d_aux[1]), static_cast<const uint32_t*>(ctx->d_aux[2]), static_cast<const uint32_t*>(ctx->d_aux[3]),
 		static_cast<uint32_t*>(ctx->d_aux[0]), perceptual);
-	return finish(ctx, pOutput_selector_cluster_indices, 0, (size_t)n * 4);
+	return finish(ctx, pOutput_selector_cluster_indices, 0, (size_t)n * 4, B200_STAT_ETC1S_FIND_SELECTOR_CLUSTERS);
 }
 
 extern "C" int b200_etc1s_determine_selectors(b200_context* ctx, const void* pInput_etc_color5_and_inten, void* pOutput_blocks, int perceptual)
@@ -482,10 +513,14 @@ extern "C" int b200_etc1s_determine_selectors(b200_context* ctx, const void* pIn
 	if (!upload(ctx, 1, pInput_etc_color5_and_inten, (size_t)n * 4)) return 0;
 	if (!ctx->reserve(ctx->d_aux[0], ctx->aux_cap[0], (size_t)n * 8)) return 0;
 	ctx->launches = 1; __atomic_add_fetch(&g_b200_total_launches, 1, __ATOMIC_RELAXED);
+	uint32_t first, last;
+	shard_range(ctx, n, first, last);
+	if (!shard_prepare_output(ctx, 0, (size_t)n * 8)) return 0;
 	B200_CUDA_OK(ctx, cudaEventRecord(ctx->ev0, ctx->stream));
-	k_etc1s_determine_selectors<<<(n + 127) / 128, 128, 0, ctx->stream>>>(static_cast<const uint4*>(ctx->d_etc_blocks), n, static_cast<const uint32_t*>(ctx->d_aux[1]),
+	if (last > first)
+	k_etc1s_determine_selectors<<<(last - first + 127) / 128, 128, 0, ctx->stream>>>(static_cast<const uint4*>(ctx->d_etc_blocks), first, last, static_cast<const uint32_t*>(ctx->d_aux[1]),
 		static_cast<uint64_t*>(ctx->d_aux[0]), perceptual);
-	return finish(ctx, pOutput_blocks, 0, (size_t)n * 8);
+	return finish(ctx, pOutput_blocks, 0, (size_t)n * 8, B200_STAT_ETC1S_DETERMINE_SELECTORS);
 }
 
 extern "C" int b200_etc1s_endpoint_histogram_device(b200_context* ctx, const void* dEtc_blocks, uint32_t num_blocks, uint32_t* dHist)
@@ -575,12 +610,14 @@ extern "C" int b200_etc1s_encode_endpoint_clusters(b200_context* ctx, void* pOut
 	free(order);
 	if (!ok) return 0;
 	ctx->launches = 1; __atomic_add_fetch(&g_b200_total_launches, 1, __ATOMIC_RELAXED);
+	if (!shard_prepare_output(ctx, 0, (size_t)total_clusters * 8)) return 0;
 	B200_CUDA_OK(ctx, cudaEventRecord(ctx->ev0, ctx->stream));
-	const uint32_t warps_per_cta = 4;
-	k_etc1s_endpoint_clusters<<<(total_clusters + warps_per_cta - 1) / warps_per_cta, warps_per_cta * 32, 0, ctx->stream>>>(static_cast<const uint32_t*>(ctx->d_etc_blocks),
+	const uint32_t warps_per_cta = 4, world = (uint32_t)(ctx->world > 1 ? ctx->world : 1);
+	const uint32_t my_clusters = (total_clusters + world - 1) / world;
+	k_etc1s_endpoint_clusters<<<(my_clusters + warps_per_cta - 1) / warps_per_cta, warps_per_cta * 32, 0, ctx->stream>>>(static_cast<const uint32_t*>(ctx->d_etc_blocks),
 		static_cast<const uint32_t*>(ctx->d_aux[1]), static_cast<const uint32_t*>(ctx->d_aux[2]), static_cast<const uint32_t*>(ctx->d_aux[3]), total_clusters,
-		static_cast<uint64_t*>(ctx->d_aux[0]), perceptual, total_perms, ctx->etc_flavour);
-	return finish(ctx, pOutput_blocks, 0, (size_t)total_clusters * 8);
+		static_cast<uint64_t*>(ctx->d_aux[0]), perceptual, total_perms, ctx->etc_flavour, (uint32_t)ctx->rank, world);
+	return finish(ctx, pOutput_blocks, 0, (size_t)total_clusters * 8, B200_STAT_ETC1S_ENDPOINT_CLUSTERS);
 }
 
 extern "C" int b200_etc1s_optimize_selector_codebook(b200_context* ctx, const void* pEtc_blocks, uint32_t total_clusters, const uint32_t* pCluster_offsets,
@@ -597,10 +634,12 @@ extern "C" int b200_etc1s_optimize_selector_codebook(b200_context* ctx, const vo
 	if (!upload(ctx, 3, pCluster_block_indices, (size_t)total_indices * 4)) return 0;
 	if (!ctx->reserve(ctx->d_aux[0], ctx->aux_cap[0], (size_t)total_clusters * 4)) return 0;
 	ctx->launches = 1; __atomic_add_fetch(&g_b200_total_launches, 1, __ATOMIC_RELAXED);
+	if (!shard_prepare_output(ctx, 0, (size_t)total_clusters * 4)) return 0;
 	B200_CUDA_OK(ctx, cudaEventRecord(ctx->ev0, ctx->stream));
-	const uint32_t warps_per_cta = 4;
-	k_etc1s_selector_codebook<<<(total_clusters + warps_per_cta - 1) / warps_per_cta, warps_per_cta * 32, 0, ctx->stream>>>(static_cast<const uint32_t*>(ctx->d_etc_blocks),
+	const uint32_t warps_per_cta = 4, world = (uint32_t)(ctx->world > 1 ? ctx->world : 1);
+	const uint32_t my_clusters = (total_clusters + world - 1) / world;
+	k_etc1s_selector_codebook<<<(my_clusters + warps_per_cta - 1) / warps_per_cta, warps_per_cta * 32, 0, ctx->stream>>>(static_cast<const uint32_t*>(ctx->d_etc_blocks),
 		static_cast<const uint2*>(ctx->d_aux[1]), static_cast<const uint32_t*>(ctx->d_aux[2]), static_cast<const uint32_t*>(ctx->d_aux[3]), total_clusters,
-		static_cast<uint32_t*>(ctx->d_aux[0]), perceptual);
-	return finish(ctx, pOutput_selectors, 0, (size_t)total_clusters * 4);
+		static_cast<uint32_t*>(ctx->d_aux[0]), perceptual, (uint32_t)ctx->rank, world);
+	return finish(ctx, pOutput_selectors, 0, (size_t)total_clusters * 4, B200_STAT_ETC1S_SELECTOR_CODEBOOK);
 }

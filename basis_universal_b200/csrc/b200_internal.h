@@ -7,6 +7,10 @@
 #include "../../include/basisu_b200.h"
 
 extern unsigned long long g_b200_total_launches;
+void g_b200_stat_add(int stat_id, float ms, uint32_t launches);
+struct b200_context;
+bool b200_merge_u32(b200_context* ctx, void* d_buf, size_t count); // b200_dist.cu: in-place SUM all-reduce over the ranks (no-op for one rank)
+void b200_comm_release(b200_context* ctx);
 
 struct b200_context
 {
@@ -31,8 +35,16 @@ struct b200_context
 	// ETC1S: source blocks of the current slice (b200_etc1s_set_pixel_blocks)
 	void* d_etc_blocks; size_t etc_blocks_cap; uint32_t etc_total_blocks;
 	int etc_flavour; // B200_ETC1S_FLAVOUR_*
+	float stat_ms[B200_STAT_COUNT]; uint32_t stat_launches[B200_STAT_COUNT], stat_calls[B200_STAT_COUNT];
 	void* tsvq; // b200_tsvq.cu: host-side result storage + device scratch of b200_tsvq_generate
+	void* comm; int rank, world; // b200_dist.cu: NCCL communicator (world <= 1: none)
+	float comm_ms; unsigned long long comm_bytes; uint32_t comm_calls;
 
+	void account(int stat_id) // adds the call that just succeeded (last_ms, launches) to the per-family totals
+	{
+		stat_ms[stat_id] += last_ms; stat_launches[stat_id] += launches; stat_calls[stat_id]++;
+		g_b200_stat_add(stat_id, last_ms, launches);
+	}
 	void fail(const char* msg) { snprintf(err, sizeof(err), "%s", msg); }
 	void fail_cuda(const char* what, cudaError_t e) { snprintf(err, sizeof(err), "%s: %s", what, cudaGetErrorString(e)); }
 	bool activate()

@@ -288,6 +288,7 @@ static int rdo_run_device(b200_context* ctx, uint4* d_blocks, const uint4* d_pix
 	B200_CUDA_OK(ctx, cudaStreamSynchronize(ctx->stream));
 	B200_CUDA_OK(ctx, cudaEventElapsedTime(&ctx->last_ms, ctx->ev0, ctx->ev1));
 	if (*h_failed_out) { ctx->fail("b200_uastc_rdo: a block failed to unpack (invalid UASTC input)"); return 0; } // reference: cECFailedUASTCRDOPostProcess
+	ctx->account(B200_STAT_UASTC_RDO);
 	return 1;
 }
 
@@ -320,6 +321,34 @@ extern "C" int b200_uastc_rdo_batch(b200_context* ctx, uint32_t num_slices, cons
 	if (!rdo_run_device(ctx, static_cast<uint4*>(ctx->d_out), static_cast<const uint4*>(ctx->d_in), num_slices, pSlice_num_blocks, params, flags, total_jobs, &h_failed))
 		return 0; // pBlocks is left untouched on failure, so a caller may still run its own CPU pass on the encoder's output
 	B200_CUDA_OK(ctx, cudaMemcpy(pBlocks, ctx->d_out, (size_t)total * 16, cudaMemcpyDeviceToHost));
+	return 1;
+}
+
+// The compressor's whole per-slice UASTC path (comp.cpp:1996-2089) for a list of slices in one call: encode, then (params != NULL)
+// the RDO post-pass, with the blocks staying in HBM between the two stages. Source blocks in, final UASTC blocks out (HOST pointers).
+extern "C" int b200_uastc_encode_rdo_blocks(b200_context* ctx, uint32_t num_slices, const uint32_t* pSlice_num_blocks, const void* pBlocks, void* pOut,
+	uint32_t flags, const b200_uastc_rdo_params* params, uint32_t total_jobs)
+{
+	if (!ctx) return 0;
+	if (!ctx->activate()) return 0;
+	if (!num_slices) return 1;
+	if (!pSlice_num_blocks || !pBlocks || !pOut) { ctx->fail("b200_uastc_encode_rdo_blocks: null argument"); return 0; }
+	uint64_t total = 0;
+	for (uint32_t s = 0; s < num_slices; s++) total += pSlice_num_blocks[s];
+	if (!total) return 1;
+	if (total > 0xFFFFFFFFull) { ctx->fail("b200_uastc_encode_rdo_blocks: more than 2^32 blocks in one call"); return 0; }
+	if (!ctx->reserve(ctx->d_in, ctx->in_cap, (size_t)total * 64)) return 0;
+	if (!ctx->reserve(ctx->d_out, ctx->out_cap, (size_t)total * 16)) return 0;
+	B200_CUDA_OK(ctx, cudaMemcpyAsync(ctx->d_in, pBlocks, (size_t)total * 64, cudaMemcpyHostToDevice, ctx->stream));
+	if (!b200_uastc_encode_blocks_device(ctx, ctx->d_in, (uint32_t)total, ctx->d_out, flags)) return 0;
+	const float enc_ms = ctx->last_ms; const uint32_t enc_launches = ctx->launches;
+	if (params)
+	{
+		int h_failed = 0;
+		if (!rdo_run_device(ctx, static_cast<uint4*>(ctx->d_out), static_cast<const uint4*>(ctx->d_in), num_slices, pSlice_num_blocks, params, flags, total_jobs, &h_failed)) return 0;
+		ctx->last_ms += enc_ms; ctx->launches += enc_launches;
+	}
+	B200_CUDA_OK(ctx, cudaMemcpy(pOut, ctx->d_out, (size_t)total * 16, cudaMemcpyDeviceToHost));
 	return 1;
 }
 

@@ -50,11 +50,11 @@ namespace
 
 	struct tsvq_state
 	{
-		dev_buf raw, tv, tw, perm[2], keys[2], cub_tmp, heads, gid, gstart, uvec, uw64, uwf, members, tmp_members, side, tval, nodes, frontier, results;
+		dev_buf raw, tv, tw, perm[2], keys[2], cub_tmp, heads, gid, gstart, uvec, uw64, uwf, members, tmp_members, side, nodes, frontier, results;
 		std::vector<uint32_t> cl_off, cl_idx, pa_off, pa_idx;
 		void release()
 		{
-			dev_buf* all[] = { &raw, &tv, &tw, &perm[0], &perm[1], &keys[0], &keys[1], &cub_tmp, &heads, &gid, &gstart, &uvec, &uw64, &uwf, &members, &tmp_members, &side, &tval, &nodes, &frontier, &results };
+			dev_buf* all[] = { &raw, &tv, &tw, &perm[0], &perm[1], &keys[0], &keys[1], &cub_tmp, &heads, &gid, &gstart, &uvec, &uw64, &uwf, &members, &tmp_members, &side, &nodes, &frontier, &results };
 			for (dev_buf* b : all) b->release();
 		}
 	};
@@ -178,78 +178,58 @@ namespace
 	// ---- serial sums in the reference's order -------------------------------------------------------------------------------------
 	// The reference accumulates a node's sums in float, one member after the other. A float sum's value depends on that order, and the
 	// node variances computed from those sums (a difference of two nearly equal numbers) decide which nodes the priority queue splits.
-	// So every sum that feeds a stored value or a decision is accumulated by ONE thread in member order, exactly as the CPU does it;
-	// the parallelism is across the accumulators of a node (one thread per vector component / matrix entry, up to 136) and across the
-	// nodes of a round, while everything that is per-member (projections, distances, side tests) runs on all threads of the CTA.
+	// So every sum that feeds a stored value or a decision is accumulated by ONE thread in member order, exactly as the CPU does it.
+	// A pass over a node's members goes tile by tile (NT members): in the LOAD phase every thread takes one member, does the per-member
+	// arithmetic (difference to the origin, projection, distances, side test, products) and stages the terms in shared memory; in the
+	// ACCUMULATE phase one thread per accumulator (vector component / matrix entry: up to 136) adds the tile's terms in order, reading
+	// shared memory only (the add chain is the critical path, ~NT x 4 cycles per tile). Parallelism: across accumulators within a
+	// node, across the nodes of a round, across members for the per-member work.
 
-	// sum over the listed members with side[i] == want of vecs[m][c] * wf[m], in list order
-	template<int D> __device__ float serial_comp_sum(const float* __restrict__ vecs, const float* __restrict__ wf, const uint32_t* mem, const uint8_t* side, uint32_t count, int c, uint32_t want)
+	template<int D, int NT> struct tile_smem
 	{
-		float acc = 0.0f;
-		uint32_t i = 0;
-		for (; i + 4 <= count; i += 4)
-		{
-			const uint32_t m0 = mem[i], m1 = mem[i + 1], m2 = mem[i + 2], m3 = mem[i + 3];
-			const uint32_t s0 = side[i], s1 = side[i + 1], s2 = side[i + 2], s3 = side[i + 3];
-			const float p0 = __ldg(vecs + (size_t)m0 * D + c) * __ldg(wf + m0), p1 = __ldg(vecs + (size_t)m1 * D + c) * __ldg(wf + m1);
-			const float p2 = __ldg(vecs + (size_t)m2 * D + c) * __ldg(wf + m2), p3 = __ldg(vecs + (size_t)m3 * D + c) * __ldg(wf + m3);
-			if (s0 == want) acc += p0;
-			if (s1 == want) acc += p1;
-			if (s2 == want) acc += p2;
-			if (s3 == want) acc += p3;
-		}
-		for (; i < count; i++)
-		{
-			const uint32_t m = mem[i];
-			if (side[i] == want) acc += __ldg(vecs + (size_t)m * D + c) * __ldg(wf + m);
-		}
-		return acc;
-	}
-
-	// double sum over the listed positions with side[i] == want of the float terms tval[i], in list order
-	__device__ double serial_term_sum(const float* tval, const uint8_t* side, uint32_t count, uint32_t want)
-	{
-		double acc = 0.0;
-		uint32_t i = 0;
-		for (; i + 4 <= count; i += 4)
-		{
-			const float t0 = tval[i], t1 = tval[i + 1], t2 = tval[i + 2], t3 = tval[i + 3];
-			const uint32_t s0 = side[i], s1 = side[i + 1], s2 = side[i + 2], s3 = side[i + 3];
-			if (s0 == want) acc += (double)t0;
-			if (s1 == want) acc += (double)t1;
-			if (s2 == want) acc += (double)t2;
-			if (s3 == want) acc += (double)t3;
-		}
-		for (; i < count; i++) if (side[i] == want) acc += (double)tval[i];
-		return acc;
-	}
+		float p[NT][D + 1]; // per member: the D terms (row padded to D + 1 words: conflict-free column writes)
+		float t[NT];        // per member: a scalar term (weight, or the ttsum term)
+		uint8_t side[NT];
+	};
 
 	// ---- prepare_root (enc.h:1696-1721) -------------------------------------------------------------------------------------
 
 	template<int D, int NT> __global__ void __launch_bounds__(NT) k_tsvq_root(const float* __restrict__ vecs, const float* __restrict__ wf, const unsigned long long* __restrict__ w64,
-		const uint32_t* __restrict__ members, uint8_t* side, float* tval, node_rec<D>* nodes, const uint32_t* __restrict__ root_ids, root_out* out)
+		const uint32_t* __restrict__ members, node_rec<D>* nodes, const uint32_t* __restrict__ root_ids, root_out* out)
 	{
 		__shared__ double s_part[(NT / 32) * 1];
 		__shared__ double s_out[1];
+		__shared__ tile_smem<D, NT> S;
 		__shared__ float s_sum[D];
 		__shared__ double s_tt;
 		node_rec<D>& nd = nodes[root_ids[blockIdx.x]];
-		const uint32_t start = nd.start, count = nd.count;
+		const uint32_t start = nd.start, count = nd.count, tid = threadIdx.x;
 		double wsum = 0;
-		for (uint32_t i = threadIdx.x; i < count; i += NT)
+		float acc = 0.0f;
+		double acc_d = 0.0;
+		for (uint32_t base = 0; base < count; base += NT)
 		{
-			const uint32_t m = members[start + i];
-			float v[D];
-			load_vec<D>(vecs, m, v);
-			tval[start + i] = dot_f<D>(v, v) * wf[m]; // ttsum += v.dot(v) * weight
-			side[start + i] = 0;
-			wsum += (double)w64[m]; // integers: exact in any order
+			const uint32_t i = base + tid;
+			if (i < count)
+			{
+				const uint32_t m = members[start + i];
+				float v[D];
+				load_vec<D>(vecs, m, v);
+				const float w = wf[m];
+#pragma unroll
+				for (int c = 0; c < D; c++) S.p[tid][c] = v[c] * w;   // root.m_origin += v * (float)weight
+				S.t[tid] = dot_f<D>(v, v) * w;                          // ttsum += v.dot(v) * weight
+				wsum += (double)w64[m];                                  // integers: exact in any order
+			}
+			__syncthreads();
+			const uint32_t nt = (count - base < (uint32_t)NT) ? count - base : (uint32_t)NT;
+			if (tid < D) { for (uint32_t k = 0; k < nt; k++) acc += S.p[k][tid]; }
+			else if (tid == D) { for (uint32_t k = 0; k < nt; k++) acc_d += (double)S.t[k]; }
+			__syncthreads();
 		}
+		if (tid < D) s_sum[tid] = acc; else if (tid == D) s_tt = acc_d;
 		block_sum<1, NT>([&](int) -> double { return wsum; }, s_part, s_out);
-		if (threadIdx.x < D) s_sum[threadIdx.x] = serial_comp_sum<D>(vecs, wf, members + start, side + start, count, (int)threadIdx.x, 0);
-		else if (threadIdx.x == D) s_tt = serial_term_sum(tval + start, side + start, count, 0);
-		__syncthreads();
-		if (!threadIdx.x)
+		if (!tid)
 		{
 			float org[D];
 			for (int c = 0; c < D; c++) org[c] = s_sum[c];
@@ -293,12 +273,13 @@ namespace
 	}
 
 	template<int D, int NT> __global__ void __launch_bounds__(NT) k_tsvq_split(const float* __restrict__ vecs, const float* __restrict__ wf, const unsigned long long* __restrict__ w64,
-		uint32_t* members, uint32_t* tmp, uint8_t* side, float* tval, node_rec<D>* nodes, const uint32_t* __restrict__ frontier, uint32_t child_base, split_out* out)
+		uint32_t* members, uint32_t* tmp, uint8_t* side, node_rec<D>* nodes, const uint32_t* __restrict__ frontier, uint32_t child_base, split_out* out)
 	{
 		constexpr int NE = D * (D + 1) / 2; // upper-triangle entries of the covariance matrix, one thread each
 		static_assert(NT >= NE && NT >= 2 * D + 2, "one thread per accumulator");
 		__shared__ double s_part[(NT / 32) * 3];
 		__shared__ double s_out[3];
+		__shared__ tile_smem<D, NT> S;
 		__shared__ float s_origin[D], s_axis[D], s_l[D], s_r[D], s_cov[D * D], s_sum[2 * D];
 		__shared__ double s_tt[2];
 		__shared__ uint32_t s_warp[NT / 32];
@@ -308,7 +289,6 @@ namespace
 		const uint32_t start = nd.start, count = nd.count;
 		const uint32_t* mem = members + start;
 		uint8_t* sd = side + start;
-		float* tv = tval + start;
 		if (tid < D) s_origin[tid] = nd.origin[tid];
 		__syncthreads();
 
@@ -321,20 +301,29 @@ namespace
 		else
 		{
 			// covariance (compute_split_axis, enc.h:1811-1822; the SSE4.1 16x16 kernel computes the same per-entry sums): entry (x, y >= x)
-			if (tid < NE)
 			{
-				int k = (int)tid, x = 0;
-				while (k >= D - x) { k -= D - x; x++; }
-				const int y = x + k;
-				const float ox = s_origin[x], oy = s_origin[y];
+				int ex = 0, ey = 0;
+				if (tid < NE) { int k = (int)tid; while (k >= D - ex) { k -= D - ex; ex++; } ey = ex + k; }
 				float acc = 0.0f;
-				for (uint32_t i = 0; i < count; i++)
+				for (uint32_t base = 0; base < count; base += NT)
 				{
-					const uint32_t m = mem[i];
-					const float vx = __ldg(vecs + (size_t)m * D + x) - ox, vy = __ldg(vecs + (size_t)m * D + y) - oy;
-					acc = acc + vx * (__ldg(wf + m) * vy);
+					const uint32_t i = base + tid;
+					if (i < count)
+					{
+						const uint32_t m = mem[i];
+						float v[D];
+						load_vec<D>(vecs, m, v);
+#pragma unroll
+						for (int c = 0; c < D; c++) S.p[tid][c] = v[c] - s_origin[c];
+						S.t[tid] = wf[m];
+					}
+					__syncthreads();
+					const uint32_t nt = (count - base < (uint32_t)NT) ? count - base : (uint32_t)NT;
+					if (tid < NE)
+						for (uint32_t k = 0; k < nt; k++) acc = acc + S.p[k][ex] * (S.t[k] * S.p[k][ey]);
+					__syncthreads();
 				}
-				s_cov[x * D + y] = acc;
+				if (tid < NE) s_cov[ex * D + ey] = acc;
 			}
 			__syncthreads();
 			if (!tid) pca_axis<D>(s_cov, 1.0f / (float)nd.weight, s_axis);
@@ -344,22 +333,37 @@ namespace
 			{
 				double lw = 0, rw = 0;
 				const uint32_t half = count / 2;
-				for (uint32_t i = tid; i < count; i += NT)
+				float acc = 0.0f;
+				for (uint32_t base = 0; base < count; base += NT)
 				{
-					const uint32_t m = mem[i];
-					float v[D];
-					load_vec<D>(vecs, m, v);
+					const uint32_t i = base + tid;
+					if (i < count)
+					{
+						const uint32_t m = mem[i];
+						float v[D], dv[D];
+						load_vec<D>(vecs, m, v);
+						const float w = wf[m];
 #pragma unroll
-					for (int c = 0; c < D; c++) v[c] -= s_origin[c];
-					const bool right = mode ? (i >= half) : (dot_f<D>(v, s_axis) >= 0.0f);
-					sd[i] = right ? 1 : 0;
-					if (right) rw += (double)wf[m]; else lw += (double)wf[m]; // double sums of float-valued integers: exact in any order
+						for (int c = 0; c < D; c++) dv[c] = v[c] - s_origin[c];
+						const bool right = mode ? (i >= half) : (dot_f<D>(dv, s_axis) >= 0.0f);
+						S.side[tid] = right ? 1 : 0;
+#pragma unroll
+						for (int c = 0; c < D; c++) S.p[tid][c] = v[c] * w;
+						if (right) rw += (double)w; else lw += (double)w; // double sums of float-valued integers: exact in any order
+					}
+					__syncthreads();
+					const uint32_t nt = (count - base < (uint32_t)NT) ? count - base : (uint32_t)NT;
+					if (tid < 2 * D)
+					{
+						const uint32_t want = tid / D, c = tid % D;
+						for (uint32_t k = 0; k < nt; k++) if (S.side[k] == want) acc += S.p[k][c];
+					}
+					__syncthreads();
 				}
+				if (tid < 2 * D) s_sum[tid] = acc;
 				block_sum<2, NT>([&](int k) -> double { return k ? rw : lw; }, s_part, s_out);
 				const double l_weight = s_out[0], r_weight = s_out[1];
 				if (!(l_weight > 0.0 && r_weight > 0.0)) continue;
-				if (tid < 2 * D) s_sum[tid] = serial_comp_sum<D>(vecs, wf, mem, sd, count, (int)(tid % D), tid / D);
-				__syncthreads();
 				if (tid < D) { s_l[tid] = s_sum[tid] * (float)(1.0f / l_weight); s_r[tid] = s_sum[D + tid] * (float)(1.0f / r_weight); }
 				break;
 			}
@@ -377,33 +381,54 @@ namespace
 			for (int degenerate = 0; degenerate < 2; degenerate++)
 			{
 				double lw = 0, rw = 0, lc = 0;
-				for (uint32_t i = tid; i < count; i += NT)
+				float acc = 0.0f;
+				double acc_d = 0.0;
+				for (uint32_t base = 0; base < count; base += NT)
 				{
-					const uint32_t m = mem[i];
-					float v[D];
-					load_vec<D>(vecs, m, v);
-					bool right;
-					if (!degenerate)
+					const uint32_t i = base + tid;
+					if (i < count)
 					{
-						double ld = 0, rd = 0; // vec::squared_distance_d (enc.h:483)
+						const uint32_t m = mem[i];
+						float v[D];
+						load_vec<D>(vecs, m, v);
+						bool right;
+						if (!degenerate)
+						{
+							double ld = 0, rd = 0; // vec::squared_distance_d (enc.h:483)
 #pragma unroll
-						for (int c = 0; c < D; c++) { const double a = (double)s_l[c] - (double)v[c]; ld += a * a; const double b = (double)s_r[c] - (double)v[c]; rd += b * b; }
-						right = ld >= rd;
+							for (int c = 0; c < D; c++) { const double a = (double)s_l[c] - (double)v[c]; ld += a * a; const double b = (double)s_r[c] - (double)v[c]; rd += b * b; }
+							right = ld >= rd;
+						}
+						else right = (i == 0); // members are unique vectors, so only the first one equals "firstVec" (enc.h:2037-2061)
+						const float w = wf[m];
+#pragma unroll
+						for (int c = 0; c < D; c++) S.p[tid][c] = v[c] * w; // v * (float)weight
+						S.t[tid] = (float)w64[m] * dot_f<D>(v, v);            // weight * v.dot(v)
+						S.side[tid] = right ? 1 : 0;
+						sd[i] = right ? 1 : 0;
+						if (right) rw += (double)w64[m]; else { lw += (double)w64[m]; lc += 1.0; }
 					}
-					else right = (i == 0); // members are unique vectors, so only the first one equals "firstVec" (enc.h:2037-2061)
-					tv[i] = (float)w64[m] * dot_f<D>(v, v); // weight * v.dot(v)
-					sd[i] = right ? 1 : 0;
-					if (right) rw += (double)w64[m]; else { lw += (double)w64[m]; lc += 1.0; }
+					__syncthreads();
+					const uint32_t nt = (count - base < (uint32_t)NT) ? count - base : (uint32_t)NT;
+					if (tid < 2 * D)
+					{
+						const uint32_t want = tid / D, c = tid % D;
+						for (uint32_t k = 0; k < nt; k++) if (S.side[k] == want) acc += S.p[k][c];
+					}
+					else if (tid < 2 * D + 2)
+					{
+						const uint32_t want = tid - 2 * D;
+						for (uint32_t k = 0; k < nt; k++) if (S.side[k] == want) acc_d += (double)S.t[k];
+					}
+					__syncthreads();
 				}
+				if (tid < 2 * D) s_sum[tid] = acc; else if (tid < 2 * D + 2) s_tt[tid - 2 * D] = acc_d;
 				block_sum<3, NT>([&](int k) -> double { return k == 0 ? lw : (k == 1 ? rw : lc); }, s_part, s_out);
 				l_weight = (unsigned long long)s_out[0]; r_weight = (unsigned long long)s_out[1];
 				l_count = (uint32_t)s_out[2];
 				if (l_weight && r_weight) break;
 			}
 			if (!l_weight || !r_weight) { ok = false; break; }
-			if (tid < 2 * D) s_sum[tid] = serial_comp_sum<D>(vecs, wf, mem, sd, count, (int)(tid % D), tid / D);
-			else if (tid < 2 * D + 2) s_tt[tid - 2 * D] = serial_term_sum(tv, sd, count, tid - 2 * D);
-			__syncthreads();
 			float nl[D], nr[D];
 #pragma unroll
 			for (int c = 0; c < D; c++) { nl[c] = s_sum[c]; nr[c] = s_sum[D + c]; }
@@ -600,7 +625,7 @@ namespace
 			if (cudaMemcpyAsync(st->nodes.as<node_rec<D>>() + base, recs.data(), (size_t)n * sizeof(node_rec<D>), cudaMemcpyHostToDevice, ctx->stream) != cudaSuccess) return false;
 			if (cudaMemcpyAsync(st->frontier.p, rid.data(), (size_t)n * 4, cudaMemcpyHostToDevice, ctx->stream) != cudaSuccess) return false;
 			k_tsvq_root<D, 256><<<n, 256, 0, ctx->stream>>>(st->uvec.as<float>(), st->uwf.as<float>(), st->uw64.as<unsigned long long>(), st->members.as<uint32_t>(),
-				st->side.as<uint8_t>(), st->tval.as<float>(), st->nodes.as<node_rec<D>>(), st->frontier.as<uint32_t>(), st->results.as<root_out>());
+				st->nodes.as<node_rec<D>>(), st->frontier.as<uint32_t>(), st->results.as<root_out>());
 			ctx->launches++; __atomic_add_fetch(&g_b200_total_launches, 1, __ATOMIC_RELAXED);
 			std::vector<root_out> ro(n);
 			if (cudaMemcpyAsync(ro.data(), st->results.p, (size_t)n * sizeof(root_out), cudaMemcpyDeviceToHost, ctx->stream) != cudaSuccess) return false;
@@ -623,17 +648,17 @@ namespace
 			if (!st->frontier.reserve((size_t)n * 4) || !st->results.reserve((size_t)n * sizeof(split_out))) { ctx->fail("b200_tsvq_generate: out of device memory"); return false; }
 			if (cudaMemcpyAsync(st->frontier.p, order.data(), (size_t)n * 4, cudaMemcpyHostToDevice, ctx->stream) != cudaSuccess) return false;
 			const float* vecs = st->uvec.as<float>(); const float* wf = st->uwf.as<float>(); const unsigned long long* w64 = st->uw64.as<unsigned long long>();
-			uint32_t* members = st->members.as<uint32_t>(); uint32_t* tmp = st->tmp_members.as<uint32_t>(); uint8_t* side = st->side.as<uint8_t>(); float* tval = st->tval.as<float>();
+			uint32_t* members = st->members.as<uint32_t>(); uint32_t* tmp = st->tmp_members.as<uint32_t>(); uint8_t* side = st->side.as<uint8_t>();
 			constexpr int NT_SMALL = (D == 6) ? 64 : 160; // >= D (D + 1) / 2 accumulator threads
 			node_rec<D>* nodes = st->nodes.as<node_rec<D>>();
 			if (n_big)
 			{
-				k_tsvq_split<D, 256><<<n_big, 256, 0, ctx->stream>>>(vecs, wf, w64, members, tmp, side, tval, nodes, st->frontier.as<uint32_t>(), child_base, st->results.as<split_out>());
+				k_tsvq_split<D, 256><<<n_big, 256, 0, ctx->stream>>>(vecs, wf, w64, members, tmp, side, nodes, st->frontier.as<uint32_t>(), child_base, st->results.as<split_out>());
 				ctx->launches++; __atomic_add_fetch(&g_b200_total_launches, 1, __ATOMIC_RELAXED);
 			}
 			if (n > n_big)
 			{
-				k_tsvq_split<D, NT_SMALL><<<n - n_big, NT_SMALL, 0, ctx->stream>>>(vecs, wf, w64, members, tmp, side, tval, nodes, st->frontier.as<uint32_t>() + n_big, child_base + 2 * n_big, st->results.as<split_out>() + n_big);
+				k_tsvq_split<D, NT_SMALL><<<n - n_big, NT_SMALL, 0, ctx->stream>>>(vecs, wf, w64, members, tmp, side, nodes, st->frontier.as<uint32_t>() + n_big, child_base + 2 * n_big, st->results.as<split_out>() + n_big);
 				ctx->launches++; __atomic_add_fetch(&g_b200_total_launches, 1, __ATOMIC_RELAXED);
 			}
 			std::vector<split_out> so(n);
@@ -787,7 +812,7 @@ extern "C" int b200_tsvq_generate(b200_context* ctx, uint32_t dim, uint32_t num_
 
 	if (!st->raw.reserve((size_t)n * stride_bytes) || !st->tv.reserve((size_t)n * dim * 4) || !st->tw.reserve((size_t)n * 8) || !st->perm[0].reserve((size_t)n * 4) || !st->perm[1].reserve((size_t)n * 4) ||
 		!st->keys[0].reserve((size_t)n * 4) || !st->keys[1].reserve((size_t)n * 4) || !st->heads.reserve((size_t)n * 4) || !st->gid.reserve((size_t)n * 4) || !st->gstart.reserve(((size_t)n + 1) * 4) ||
-		!st->uvec.reserve((size_t)n * dim * 4) || !st->uw64.reserve((size_t)n * 8) || !st->uwf.reserve((size_t)n * 4) || !st->members.reserve((size_t)n * 4) || !st->tmp_members.reserve((size_t)n * 4) || !st->side.reserve(n) || !st->tval.reserve((size_t)n * 4))
+		!st->uvec.reserve((size_t)n * dim * 4) || !st->uw64.reserve((size_t)n * 8) || !st->uwf.reserve((size_t)n * 4) || !st->members.reserve((size_t)n * 4) || !st->tmp_members.reserve((size_t)n * 4) || !st->side.reserve(n))
 	{ ctx->fail("b200_tsvq_generate: out of device memory"); return 0; }
 
 	TSVQ_OK(cudaEventRecord(ctx->ev0, ctx->stream));
@@ -857,6 +882,10 @@ extern "C" int b200_tsvq_generate(b200_context* ctx, uint32_t dim, uint32_t num_
 		off.push_back(0);
 		for (const segment& s : segs)
 		{
+			// A node's member list is an ascending run of unique-vector ids in the reference (children are stable sub-lists of the root's
+			// 0..U-1). Here a speculative split that the replay did not take has already partitioned its node's segment in place, so the
+			// set is right but the order is [left | right]: restore it.
+			std::sort(h_members.begin() + s.start, h_members.begin() + s.start + s.count);
 			for (uint32_t i = 0; i < s.count; i++)
 			{
 				const uint32_t g = h_members[s.start + i];
@@ -873,5 +902,6 @@ extern "C" int b200_tsvq_generate(b200_context* ctx, uint32_t dim, uint32_t num_
 	pResult->num_parent_clusters = (uint32_t)parents.size();
 	pResult->parent_offsets = st->pa_off.data(); pResult->parent_indices = st->pa_idx.data();
 	pResult->rounds = rounds; pResult->nodes_split = splits;
+	ctx->account(B200_STAT_TSVQ);
 	return 1;
 }

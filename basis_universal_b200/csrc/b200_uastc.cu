@@ -236,6 +236,7 @@ extern "C" int b200_uastc_encode_blocks_device(b200_context* ctx, const void* dB
 	B200_CUDA_OK(ctx, cudaStreamSynchronize(ctx->stream));
 	B200_CUDA_OK(ctx, cudaEventElapsedTime(&ctx->last_ms, ctx->ev0, ctx->ev1));
 	ctx->collect_stage_times();
+	ctx->account(B200_STAT_UASTC_ENCODE);
 	return 1;
 }
 
@@ -266,5 +267,6 @@ extern "C" int b200_uastc_encode_blocks(b200_context* ctx, const void* pBlocks, 
 	B200_CUDA_OK(ctx, cudaEventElapsedTime(&total_ms, ctx->ev0, ctx->ev1));
 	ctx->last_ms = total_ms;
 	ctx->collect_stage_times();
+	ctx->account(B200_STAT_UASTC_ENCODE);
 	return 1;
 }

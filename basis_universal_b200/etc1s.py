@@ -181,6 +181,29 @@ def _optimize_selector_codebook(self, etc_blocks, clusters, perceptual):
     return out
 
 
+def comm_unique_id():
+    """128-byte NCCL id (rank 0 calls this, then broadcasts the bytes to the other ranks)."""
+    buf = np.zeros(128, np.uint8)
+    if not lib().b200_comm_unique_id(_p(buf)):
+        raise B200Error("b200_comm_unique_id failed: " + lib().b200_comm_last_error().decode())
+    return buf
+
+
+def _comm_init(self, rank, world, unique_id):
+    """Attaches the NCCL communicator: afterwards every stage call computes this rank's share and merges with the other ranks."""
+    uid = np.ascontiguousarray(unique_id, np.uint8)
+    assert uid.shape == (128,)
+    self._check(self._lib.b200_comm_init(self._ctx, int(rank), int(world), _p(uid)), "b200_comm_init")
+
+
+def _comm_stats(self):
+    ms, by, ca = ctypes.c_float(0), ctypes.c_uint64(0), ctypes.c_uint32(0)
+    self._lib.b200_comm_stats(self._ctx, ctypes.byref(ms), ctypes.byref(by), ctypes.byref(ca))
+    return {"ms": float(ms.value), "bytes": int(by.value), "calls": int(ca.value)}
+
+
+Etc1sContext.comm_init = _comm_init
+Etc1sContext.comm_stats = _comm_stats
 Etc1sContext.tsvq_generate = _tsvq_generate
 Etc1sContext.encode_endpoint_clusters = _encode_endpoint_clusters
 Etc1sContext.optimize_selector_codebook = _optimize_selector_codebook

@@ -142,6 +142,13 @@ class Encoder:
                                                    ctypes.byref(p), int(flags), int(total_jobs))
         self._check(ok, "b200_uastc_rdo_batch_device")
 
+    def encode_rdo_host_ptr(self, host_in_ptr, slice_num_blocks, host_out_ptr, params=None, flags=cPackUASTCLevelDefault, total_jobs=4):
+        """b200_uastc_encode_rdo_blocks: source blocks in, encoded (and, with params, RDO post-processed) UASTC blocks out; host pointers."""
+        counts = np.ascontiguousarray(slice_num_blocks, np.uint32)
+        ok = self._lib.b200_uastc_encode_rdo_blocks(self._ctx, counts.shape[0], counts.ctypes.data, ctypes.c_void_p(host_in_ptr), ctypes.c_void_p(host_out_ptr), int(flags),
+                                                    ctypes.byref(params) if params is not None else None, int(total_jobs))
+        self._check(ok, "b200_uastc_encode_rdo_blocks")
+
     def encode_uastc_device(self, d_blocks_ptr, num_blocks, d_out_ptr, flags=cPackUASTCLevelDefault):
         """Device-resident form: raw device pointers (e.g. torch tensor .data_ptr()) to (N,64) and (N,16) uint8 buffers."""
         ok = self._lib.b200_uastc_encode_blocks_device(self._ctx, ctypes.c_void_p(d_blocks_ptr), int(num_blocks), ctypes.c_void_p(d_out_ptr), int(flags))

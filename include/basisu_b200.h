@@ -84,6 +84,12 @@ int b200_uastc_rdo_batch(b200_context* ctx, uint32_t num_slices, const uint32_t*
 int b200_uastc_rdo_batch_device(b200_context* ctx, uint32_t num_slices, const uint32_t* pSlice_num_blocks, void* dBlocks, const void* dBlock_pixels,
 	const b200_uastc_rdo_params* params, uint32_t flags, uint32_t total_jobs);
 
+/* encode_slices_to_uastc_4x4_ldr's per-slice body (comp.cpp:1996-2089) for a list of slices: encode_uastc over every block, then,
+ * if params is not NULL, uastc_rdo per slice with the same total_jobs. HOST pointers: source blocks in (64 B each, the slices end
+ * to end), final UASTC blocks out; the encoded blocks stay in HBM between the two stages. */
+int b200_uastc_encode_rdo_blocks(b200_context* ctx, uint32_t num_slices, const uint32_t* pSlice_num_blocks, const void* pBlocks, void* pOut,
+	uint32_t flags, const b200_uastc_rdo_params* params, uint32_t total_jobs);
+
 /* ---- ETC1S frontend per-block stages: the reference's existing GPU seam, symbol for symbol ------------------------------ */
 /* Packed argument structs are the reference's (encoder/basisu_opencl.h:36-135), restated in C. */
 
@@ -188,6 +194,26 @@ int b200_etc1s_endpoint_histogram_device(b200_context* ctx, const void* dEtc_blo
 int b200_etc1s_selector_training(b200_context* ctx, const void* pEtc_blocks, uint32_t num_blocks, int perceptual, uint32_t* pKeys, uint32_t* pWeights);
 int b200_etc1s_selector_training_device(b200_context* ctx, const void* dEtc_blocks, uint32_t num_blocks, int perceptual, uint32_t* dKeys, uint32_t* dWeights);
 
+/* ---- multi-GPU: one process per GPU, NCCL over NVLink / NVSwitch ---------------------------------------------------------------- */
+
+/* With a communicator attached, every b200_etc1s_* stage call computes only this rank's share (per-block stages: a contiguous
+ * block range = block rows; per-cluster stages: every world-th cluster) and the ranks merge the stage's output array with one
+ * NCCL all-reduce, so each rank returns the COMPLETE output: the host logic above (the reference's frontend) runs replicated
+ * on identical data. b200_etc1s_set_pixel_blocks still takes the whole slice (268 MB at 8192^2: replicating the texels is what
+ * NVSwitch makes cheap; the work is what gets divided). b200_tsvq_generate runs replicated (deterministic, identical on every
+ * rank). UASTC needs no collective: shard the blocks by rows and call the encoder on each shard.
+ * Rank 0 obtains an id with b200_comm_unique_id and hands its 128 bytes to the other ranks by any means (torch.distributed
+ * broadcast, MPI, a file); every rank then calls b200_comm_init on its context. NCCL is loaded with dlopen on first use. */
+int b200_comm_unique_id(uint8_t* pId128);
+int b200_comm_init(b200_context* ctx, int rank, int world, const uint8_t* pId128);
+int b200_comm_rank(const b200_context* ctx);
+int b200_comm_world(const b200_context* ctx);
+/* In-place SUM all-reduce of `count` u32 in device memory over the context's communicator (e.g. the 2^18 endpoint histogram). */
+int b200_comm_allreduce_u32_device(b200_context* ctx, void* dBuf, size_t count);
+/* Device time, bytes and number of the stage-output merges issued through this context so far. */
+int b200_comm_stats(const b200_context* ctx, float* pMs, uint64_t* pBytes, uint32_t* pCalls);
+const char* b200_comm_last_error(void);
+
 /* ---- either side of the per-block path: ingest, decode, quality metric ---------------------------------------------------- */
 
 /* Raster RGBA8 image -> array of 64 B pixel_blocks in raster block order, edge texels clamped: one slice of
@@ -226,6 +252,21 @@ int b200_block_metrics_device(b200_context* ctx, const void* dBlocksA, const voi
  * context's stream), and the number of kernel launches it issued. */
 float b200_last_kernel_ms(const b200_context* ctx);
 uint32_t b200_last_launch_count(const b200_context* ctx);
+
+/* Accumulated per entry-point family since the context was created or b200_stats_reset: device milliseconds of the kernels
+ * (CUDA events on the context's stream), kernel launches and calls. Lets a host that drives the stages through the reference's
+ * own frontend attribute a whole compress() to kernels. Returns 0 for an unknown id. */
+enum
+{
+	B200_STAT_ETC1S_ENCODE_BLOCKS = 0, B200_STAT_ETC1S_ENDPOINT_CLUSTERS = 1, B200_STAT_ETC1S_REFINE = 2, B200_STAT_ETC1S_DETERMINE_SELECTORS = 3,
+	B200_STAT_ETC1S_FIND_SELECTOR_CLUSTERS = 4, B200_STAT_ETC1S_SELECTOR_CODEBOOK = 5, B200_STAT_TSVQ = 6, B200_STAT_UASTC_ENCODE = 7, B200_STAT_UASTC_RDO = 8,
+	B200_STAT_COUNT = 9
+};
+int b200_stats_get(const b200_context* ctx, uint32_t stat_id, float* pKernel_ms, uint32_t* pLaunches, uint32_t* pCalls);
+void b200_stats_reset(b200_context* ctx);
+/* Same, summed over every context this process has created (a host that never sees the contexts, e.g. basis_compress()). */
+int b200_global_stats_get(uint32_t stat_id, float* pKernel_ms, uint32_t* pLaunches, uint32_t* pCalls);
+void b200_global_stats_reset(void);
 
 /* Kernel launches issued by this process through any context since load (lets a host that only sees the reference's API,
  * e.g. the drop-in build of INTEGRATION.md section 1, confirm that the GPU path really ran). */

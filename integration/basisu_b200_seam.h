@@ -40,4 +40,8 @@ namespace basisu
 	// 2 * (x + 4 * y) of pOutput_selectors[cluster]; pEtc_blocks = m_encoded_blocks (all blocks of the slice).
 	bool opencl_b200_optimize_selector_codebook(opencl_context_ptr pContext, const etc_block* pEtc_blocks, uint32_t total_clusters,
 		const uint32_t* pCluster_offsets, const uint32_t* pCluster_block_indices, uint32_t* pOutput_selectors, bool perceptual);
+
+	// Stage clocks of the patched compressor (basis_compressor::process): name -> seconds of the last run, readable from outside
+	// through `extern "C" double b200_dropin_stage_secs(const char* name)` (benchmarks; no effect on the output).
+	void opencl_b200_note_stage_secs(const char* pName, double secs);
 } // namespace basisu

@@ -8,6 +8,12 @@
 // m_opencl_failed and recompute that stage on the CPU (encoder/basisu_frontend.cpp:757-762).
 #include "basisu_b200_seam.h"
 #include "basisu_b200.h"
+#include <map>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <mutex>
+#include <string>
 
 namespace basisu
 {
@@ -29,8 +35,24 @@ namespace basisu
 	opencl_context_ptr opencl_create_context()
 	{
 		if (!g_b200_available) return nullptr;
-		b200_context* c = b200_create_context(0);
+		// One process per GPU: B200_DEVICE selects the device (default 0); B200_COMM_WORLD / B200_COMM_RANK / B200_COMM_ID (the 128
+		// bytes of b200_comm_unique_id in hex, distributed by the launcher) attach the NCCL communicator that merges stage outputs.
+		const char* pDev = getenv("B200_DEVICE");
+		b200_context* c = b200_create_context(pDev ? atoi(pDev) : 0);
 		if (!c) { error_printf("opencl_create_context (b200): %s\n", b200_last_error(nullptr)); return nullptr; }
+		const char* pWorld = getenv("B200_COMM_WORLD"); const char* pRank = getenv("B200_COMM_RANK"); const char* pId = getenv("B200_COMM_ID");
+		if (pWorld && atoi(pWorld) > 1)
+		{
+			uint8_t id[128];
+			bool ok = pRank && pId && strlen(pId) == 256;
+			for (uint32_t i = 0; ok && i < 128; i++) { unsigned v = 0; ok = sscanf(pId + i * 2, "%2x", &v) == 1; id[i] = (uint8_t)v; }
+			if (!ok || !b200_comm_init(c, atoi(pRank), atoi(pWorld), id))
+			{
+				error_printf("opencl_create_context (b200): communicator setup failed: %s\n", ok ? b200_last_error(c) : "B200_COMM_RANK / B200_COMM_ID missing or malformed");
+				b200_destroy_context(c);
+				return nullptr;
+			}
+		}
 		opencl_context* p = new opencl_context;
 		p->m_ctx = c;
 		return p;
@@ -165,4 +187,21 @@ namespace basisu
 		return report(p, b200_etc1s_optimize_selector_codebook(p->m_ctx, pEtc_blocks, total_clusters, pCluster_offsets, pCluster_block_indices, pOutput_selectors, perceptual),
 			"opencl_b200_optimize_selector_codebook");
 	}
+
+	static std::mutex g_stage_mutex;
+	static std::map<std::string, double> g_stage_secs;
+
+	void opencl_b200_note_stage_secs(const char* pName, double secs)
+	{
+		debug_printf("[stage] %s: %3.3f secs\n", pName, secs);
+		std::lock_guard<std::mutex> lk(g_stage_mutex);
+		g_stage_secs[pName] = secs;
+	}
 } // namespace basisu
+
+extern "C" __attribute__((visibility("default"))) double b200_dropin_stage_secs(const char* pName)
+{
+	std::lock_guard<std::mutex> lk(basisu::g_stage_mutex);
+	auto it = basisu::g_stage_secs.find(pName);
+	return (it == basisu::g_stage_secs.end()) ? -1.0 : it->second;
+}
