@@ -93,6 +93,8 @@ def lib():
         L.b200_comm_unique_id.argtypes = [vp]
         L.b200_comm_init.restype = i32
         L.b200_comm_init.argtypes = [vp, i32, i32, vp]
+        L.b200_shard_range.restype = None
+        L.b200_shard_range.argtypes = [u32, u32, u32, vp, vp]
         L.b200_comm_rank.restype = i32
         L.b200_comm_rank.argtypes = [vp]
         L.b200_comm_world.restype = i32
@@ -141,6 +143,6 @@ EXPORTS = [
     "b200_etc1s_refine_endpoint_clusterization", "b200_etc1s_find_optimal_selector_clusters_for_each_block",
     "b200_etc1s_determine_selectors", "b200_last_kernel_ms", "b200_last_launch_count", "b200_last_stage_ms",
     "b200_timer_start", "b200_timer_stop_ms", "b200_global_launch_count",
-    "b200_comm_unique_id", "b200_comm_init", "b200_comm_rank", "b200_comm_world", "b200_comm_allreduce_u32_device", "b200_comm_stats", "b200_comm_last_error",
+    "b200_comm_unique_id", "b200_comm_init", "b200_shard_range", "b200_comm_rank", "b200_comm_world", "b200_comm_allreduce_u32_device", "b200_comm_stats", "b200_comm_last_error",
     "b200_stats_get", "b200_stats_reset", "b200_global_stats_get", "b200_global_stats_reset", "b200_tsvq_generate", "b200_etc1s_encode_endpoint_clusters", "b200_etc1s_optimize_selector_codebook",
 ]

@@ -24,6 +24,15 @@ extern "C" b200_context* b200_create_context(int device_index)
 	if (device_index < 0 || device_index >= n) { snprintf(g_create_err, sizeof(g_create_err), "device index %d out of range (0..%d)", device_index, n - 1); return nullptr; }
 	cudaError_t e = cudaSetDevice(device_index);
 	if (e != cudaSuccess) { snprintf(g_create_err, sizeof(g_create_err), "cudaSetDevice: %s", cudaGetErrorString(e)); return nullptr; }
+	{
+		// keep freed blocks in the default pool instead of returning them to the driver at every synchronisation
+		cudaMemPool_t pool;
+		if (cudaDeviceGetDefaultMemPool(&pool, device_index) == cudaSuccess)
+		{
+			unsigned long long threshold = ~0ull;
+			cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &threshold);
+		}
+	}
 	b200_context* ctx = new b200_context();
 	memset(ctx, 0, sizeof(*ctx));
 	ctx->device = device_index;
@@ -50,8 +59,9 @@ extern "C" void b200_destroy_context(b200_context* ctx)
 	b200_tsvq_release(ctx);
 	b200_comm_release(ctx);
 	void* bufs[] = { ctx->d_in, ctx->d_out, ctx->d_meta, ctx->d_cands, ctx->d_slots, ctx->d_lists, ctx->d_etc_blocks };
-	for (void* p : bufs) if (p) cudaFree(p);
-	for (void* p : ctx->d_aux) if (p) cudaFree(p);
+	for (void* p : bufs) if (p) cudaFreeAsync(p, ctx->stream);
+	for (void* p : ctx->d_aux) if (p) cudaFreeAsync(p, ctx->stream);
+	cudaStreamSynchronize(ctx->stream);
 	cudaEventDestroy(ctx->ev0);
 	cudaEventDestroy(ctx->ev1);
 	cudaEventDestroy(ctx->ev_t0);

@@ -77,6 +77,21 @@ void b200_comm_release(b200_context* ctx)
 	if (ctx && ctx->comm) { g_nccl.CommDestroy(static_cast<ncclComm_t>(ctx->comm)); ctx->comm = nullptr; ctx->world = 1; ctx->rank = 0; }
 }
 
+// [first, last) of `rank`'s share of n per-block units: equal contiguous ranges of ceil(n / world), the tail ranks short or empty.
+extern "C" void b200_shard_range(uint32_t n, uint32_t rank, uint32_t world, uint32_t* pFirst, uint32_t* pLast)
+{
+	uint32_t first = 0, last = n;
+	if (world > 1)
+	{
+		const uint32_t per = (n + world - 1) / world;
+		const uint64_t f = (uint64_t)rank * per;
+		first = (f > n) ? n : (uint32_t)f;
+		last = (n - first > per) ? first + per : n;
+	}
+	if (pFirst) *pFirst = first;
+	if (pLast) *pLast = last;
+}
+
 extern "C" int b200_comm_rank(const b200_context* ctx) { return ctx ? ctx->rank : 0; }
 extern "C" int b200_comm_world(const b200_context* ctx) { return (ctx && ctx->world > 1) ? ctx->world : 1; }
 

@@ -382,10 +382,7 @@ static bool upload(b200_context* ctx, int slot, const void* host, size_t bytes)
 // This rank's share [first, last) of n per-block units: contiguous ranges, i.e. block rows.
 static void shard_range(const b200_context* ctx, uint32_t n, uint32_t& first, uint32_t& last)
 {
-	if (ctx->world <= 1) { first = 0; last = n; return; }
-	const uint32_t per = (n + (uint32_t)ctx->world - 1) / (uint32_t)ctx->world;
-	first = (uint32_t)ctx->rank * per; if (first > n) first = n;
-	last = (first + per < n) ? first + per : n;
+	b200_shard_range(n, (uint32_t)ctx->rank, (uint32_t)(ctx->world > 1 ? ctx->world : 1), &first, &last);
 }
 // With several ranks the output buffer is zeroed before the kernel so that the all-reduce in finish() is a merge.
 static bool shard_prepare_output(b200_context* ctx, int slot, size_t bytes)

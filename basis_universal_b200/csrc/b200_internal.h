@@ -78,9 +78,12 @@ struct b200_context
 	bool reserve(void*& p, size_t& cap, size_t bytes)
 	{
 		if (bytes <= cap) return true;
-		if (p) { cudaFree(p); p = nullptr; cap = 0; }
-		cudaError_t e = cudaMalloc(&p, bytes);
-		if (e != cudaSuccess) { p = nullptr; fail_cuda("cudaMalloc", e); return false; }
+		// Stream-ordered allocation from the device's default pool (release threshold raised in b200_create_context): a compressor
+		// that creates one context per image (basis_compressor does) gets its buffers back from the pool instead of paying
+		// cudaMalloc / cudaFree (device-synchronising, milliseconds each) for every image.
+		if (p) { cudaFreeAsync(p, stream); p = nullptr; cap = 0; }
+		cudaError_t e = cudaMallocAsync(&p, bytes, stream);
+		if (e != cudaSuccess) { p = nullptr; fail_cuda("cudaMallocAsync", e); return false; }
 		cap = bytes;
 		return true;
 	}

@@ -32,19 +32,19 @@
 
 namespace
 {
-	struct dev_buf
+	struct dev_buf // grow-only device buffer from the stream-ordered pool (see b200_context::reserve)
 	{
 		void* p = nullptr; size_t cap = 0;
-		bool reserve(size_t bytes)
+		bool reserve(size_t bytes, cudaStream_t s)
 		{
 			if (bytes <= cap) return true;
-			if (p) { cudaFree(p); p = nullptr; cap = 0; }
+			if (p) { cudaFreeAsync(p, s); p = nullptr; cap = 0; }
 			const size_t want = bytes + bytes / 4 + 256;
-			if (cudaMalloc(&p, want) != cudaSuccess) { p = nullptr; return false; }
+			if (cudaMallocAsync(&p, want, s) != cudaSuccess) { p = nullptr; return false; }
 			cap = want;
 			return true;
 		}
-		void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+		void release(cudaStream_t s) { if (p) cudaFreeAsync(p, s); p = nullptr; cap = 0; }
 		template<typename T> T* as() { return static_cast<T*>(p); }
 	};
 
@@ -52,10 +52,10 @@ namespace
 	{
 		dev_buf raw, tv, tw, perm[2], keys[2], cub_tmp, heads, gid, gstart, uvec, uw64, uwf, members, tmp_members, side, nodes, frontier, results;
 		std::vector<uint32_t> cl_off, cl_idx, pa_off, pa_idx;
-		void release()
+		void release(cudaStream_t s)
 		{
 			dev_buf* all[] = { &raw, &tv, &tw, &perm[0], &perm[1], &keys[0], &keys[1], &cub_tmp, &heads, &gid, &gstart, &uvec, &uw64, &uwf, &members, &tmp_members, &side, &nodes, &frontier, &results };
-			for (dev_buf* b : all) b->release();
+			for (dev_buf* b : all) b->release(s);
 		}
 	};
 
@@ -605,10 +605,10 @@ namespace
 			const size_t bytes = n * sizeof(node_rec<D>);
 			if (bytes <= st->nodes.cap) return true;
 			dev_buf nb;
-			if (!nb.reserve(bytes * 2)) return false;
-			if (st->nodes.p && !spec.empty() && cudaMemcpyAsync(nb.p, st->nodes.p, spec.size() * sizeof(node_rec<D>), cudaMemcpyDeviceToDevice, ctx->stream) != cudaSuccess) { nb.release(); return false; }
-			if (cudaStreamSynchronize(ctx->stream) != cudaSuccess) { nb.release(); return false; }
-			st->nodes.release();
+			if (!nb.reserve(bytes * 2, ctx->stream)) return false;
+			if (st->nodes.p && !spec.empty() && cudaMemcpyAsync(nb.p, st->nodes.p, spec.size() * sizeof(node_rec<D>), cudaMemcpyDeviceToDevice, ctx->stream) != cudaSuccess) { nb.release(ctx->stream); return false; }
+			if (cudaStreamSynchronize(ctx->stream) != cudaSuccess) { nb.release(ctx->stream); return false; }
+			st->nodes.release(ctx->stream);
 			st->nodes = nb;
 			return true;
 		}
@@ -621,7 +621,7 @@ namespace
 			std::vector<node_rec<D>> recs(n);
 			std::vector<uint32_t> rid(n);
 			for (uint32_t i = 0; i < n; i++) { memset(&recs[i], 0, sizeof(recs[i])); recs[i].start = segs[i].start; recs[i].count = segs[i].count; rid[i] = base + i; }
-			if (!st->frontier.reserve((size_t)n * 4) || !st->results.reserve((size_t)n * sizeof(root_out))) { ctx->fail("b200_tsvq_generate: out of device memory"); return false; }
+			if (!st->frontier.reserve((size_t)n * 4, ctx->stream) || !st->results.reserve((size_t)n * sizeof(root_out), ctx->stream)) { ctx->fail("b200_tsvq_generate: out of device memory"); return false; }
 			if (cudaMemcpyAsync(st->nodes.as<node_rec<D>>() + base, recs.data(), (size_t)n * sizeof(node_rec<D>), cudaMemcpyHostToDevice, ctx->stream) != cudaSuccess) return false;
 			if (cudaMemcpyAsync(st->frontier.p, rid.data(), (size_t)n * 4, cudaMemcpyHostToDevice, ctx->stream) != cudaSuccess) return false;
 			k_tsvq_root<D, 256><<<n, 256, 0, ctx->stream>>>(st->uvec.as<float>(), st->uwf.as<float>(), st->uw64.as<unsigned long long>(), st->members.as<uint32_t>(),
@@ -645,7 +645,7 @@ namespace
 			while (n_big < n && spec[order[n_big]].count > 256) n_big++;
 			const uint32_t child_base = (uint32_t)spec.size();
 			if (!ensure_nodes((size_t)child_base + 2 * (size_t)n)) { ctx->fail("b200_tsvq_generate: out of device memory (nodes)"); return false; }
-			if (!st->frontier.reserve((size_t)n * 4) || !st->results.reserve((size_t)n * sizeof(split_out))) { ctx->fail("b200_tsvq_generate: out of device memory"); return false; }
+			if (!st->frontier.reserve((size_t)n * 4, ctx->stream) || !st->results.reserve((size_t)n * sizeof(split_out), ctx->stream)) { ctx->fail("b200_tsvq_generate: out of device memory"); return false; }
 			if (cudaMemcpyAsync(st->frontier.p, order.data(), (size_t)n * 4, cudaMemcpyHostToDevice, ctx->stream) != cudaSuccess) return false;
 			const float* vecs = st->uvec.as<float>(); const float* wf = st->uwf.as<float>(); const unsigned long long* w64 = st->uw64.as<unsigned long long>();
 			uint32_t* members = st->members.as<uint32_t>(); uint32_t* tmp = st->tmp_members.as<uint32_t>(); uint8_t* side = st->side.as<uint8_t>();
@@ -785,7 +785,8 @@ void b200_tsvq_release(b200_context* ctx)
 {
 	if (!ctx || !ctx->tsvq) return;
 	tsvq_state* st = static_cast<tsvq_state*>(ctx->tsvq);
-	st->release();
+	st->release(ctx->stream);
+	cudaStreamSynchronize(ctx->stream);
 	delete st;
 	ctx->tsvq = nullptr;
 }
@@ -810,9 +811,9 @@ extern "C" int b200_tsvq_generate(b200_context* ctx, uint32_t dim, uint32_t num_
 	const uint32_t n = num_training;
 	ctx->launches = 0;
 
-	if (!st->raw.reserve((size_t)n * stride_bytes) || !st->tv.reserve((size_t)n * dim * 4) || !st->tw.reserve((size_t)n * 8) || !st->perm[0].reserve((size_t)n * 4) || !st->perm[1].reserve((size_t)n * 4) ||
-		!st->keys[0].reserve((size_t)n * 4) || !st->keys[1].reserve((size_t)n * 4) || !st->heads.reserve((size_t)n * 4) || !st->gid.reserve((size_t)n * 4) || !st->gstart.reserve(((size_t)n + 1) * 4) ||
-		!st->uvec.reserve((size_t)n * dim * 4) || !st->uw64.reserve((size_t)n * 8) || !st->uwf.reserve((size_t)n * 4) || !st->members.reserve((size_t)n * 4) || !st->tmp_members.reserve((size_t)n * 4) || !st->side.reserve(n))
+	if (!st->raw.reserve((size_t)n * stride_bytes, ctx->stream) || !st->tv.reserve((size_t)n * dim * 4, ctx->stream) || !st->tw.reserve((size_t)n * 8, ctx->stream) || !st->perm[0].reserve((size_t)n * 4, ctx->stream) || !st->perm[1].reserve((size_t)n * 4, ctx->stream) ||
+		!st->keys[0].reserve((size_t)n * 4, ctx->stream) || !st->keys[1].reserve((size_t)n * 4, ctx->stream) || !st->heads.reserve((size_t)n * 4, ctx->stream) || !st->gid.reserve((size_t)n * 4, ctx->stream) || !st->gstart.reserve(((size_t)n + 1) * 4, ctx->stream) ||
+		!st->uvec.reserve((size_t)n * dim * 4, ctx->stream) || !st->uw64.reserve((size_t)n * 8, ctx->stream) || !st->uwf.reserve((size_t)n * 4, ctx->stream) || !st->members.reserve((size_t)n * 4, ctx->stream) || !st->tmp_members.reserve((size_t)n * 4, ctx->stream) || !st->side.reserve(n, ctx->stream))
 	{ ctx->fail("b200_tsvq_generate: out of device memory"); return 0; }
 
 	TSVQ_OK(cudaEventRecord(ctx->ev0, ctx->stream));
@@ -830,7 +831,7 @@ extern "C" int b200_tsvq_generate(b200_context* ctx, uint32_t dim, uint32_t num_
 		size_t scan_bytes = 0;
 		TSVQ_OK(cub::DeviceScan::InclusiveSum(nullptr, scan_bytes, st->heads.as<uint32_t>(), st->gid.as<uint32_t>(), (int)n, ctx->stream));
 		if (scan_bytes > tmp_bytes) tmp_bytes = scan_bytes;
-		if (!st->cub_tmp.reserve(tmp_bytes)) { ctx->fail("b200_tsvq_generate: out of device memory"); return 0; }
+		if (!st->cub_tmp.reserve(tmp_bytes, ctx->stream)) { ctx->fail("b200_tsvq_generate: out of device memory"); return 0; }
 	}
 	int cur = 0; // which perm buffer holds the current permutation
 	for (int c = (int)dim - 1; c >= 0; c--)

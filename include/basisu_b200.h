@@ -206,6 +206,8 @@ int b200_etc1s_selector_training_device(b200_context* ctx, const void* dEtc_bloc
  * broadcast, MPI, a file); every rank then calls b200_comm_init on its context. NCCL is loaded with dlopen on first use. */
 int b200_comm_unique_id(uint8_t* pId128);
 int b200_comm_init(b200_context* ctx, int rank, int world, const uint8_t* pId128);
+/* The share of `rank` of n per-block units (host arithmetic, usable without a GPU): [*pFirst, *pLast), contiguous, ceil(n / world) each. */
+void b200_shard_range(uint32_t n, uint32_t rank, uint32_t world, uint32_t* pFirst, uint32_t* pLast);
 int b200_comm_rank(const b200_context* ctx);
 int b200_comm_world(const b200_context* ctx);
 /* In-place SUM all-reduce of `count` u32 in device memory over the context's communicator (e.g. the 2^18 endpoint histogram). */

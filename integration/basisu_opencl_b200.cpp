@@ -32,9 +32,13 @@ namespace basisu
 	void opencl_deinit() { g_b200_available = false; }
 	bool opencl_is_available() { return g_b200_available; }
 
+	void opencl_b200_note_stage_secs(const char* pName, double secs);
+
 	opencl_context_ptr opencl_create_context()
 	{
 		if (!g_b200_available) return nullptr;
+		interval_timer tm; tm.start();
+		struct note { interval_timer& t; ~note() { opencl_b200_note_stage_secs("context_create", t.get_elapsed_secs()); } } n{ tm };
 		// One process per GPU: B200_DEVICE selects the device (default 0); B200_COMM_WORLD / B200_COMM_RANK / B200_COMM_ID (the 128
 		// bytes of b200_comm_unique_id in hex, distributed by the launcher) attach the NCCL communicator that merges stage outputs.
 		const char* pDev = getenv("B200_DEVICE");
@@ -61,8 +65,10 @@ namespace basisu
 	void opencl_destroy_context(opencl_context_ptr context)
 	{
 		if (!context) return;
+		interval_timer tm; tm.start();
 		b200_destroy_context(context->m_ctx);
 		delete context;
+		opencl_b200_note_stage_secs("context_destroy", tm.get_elapsed_secs());
 	}
 
 	static bool report(opencl_context_ptr p, int ok, const char* what)

@@ -120,3 +120,66 @@ def test_two_rank_selector_training_allgather_gloo():
         p.join(180)
         assert p.exitcode == 0
     assert q.get()
+
+
+def _merge_worker(rank, world, port, n_blocks, n_clusters, q):
+    """The multi-GPU ETC1S pattern of b200_dist.cu on the CPU: every rank fills ITS share of a stage's output array (per-block
+    stages: the contiguous range of b200_shard_range; per-cluster stages: every world-th entry) into a zeroed buffer, and one SUM
+    all-reduce over the array as u32 words is a merge, because each element is written by exactly one rank (no carries between the
+    two halves of a 64-bit etc_block either)."""
+    import ctypes
+    from basis_universal_b200 import lib
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    rng = np.random.default_rng(99)                              # same "full result" on every rank
+    full_blocks = rng.integers(0, 1 << 63, n_blocks, dtype=np.uint64)   # 8-byte per-block outputs (etc_blocks)
+    full_clusters = rng.integers(0, 1 << 32, n_clusters, dtype=np.uint64).astype(np.uint32)
+    first, last = ctypes.c_uint32(0), ctypes.c_uint32(0)
+    lib().b200_shard_range(n_blocks, rank, world, ctypes.byref(first), ctypes.byref(last))
+    mine = np.zeros(n_blocks, np.uint64)
+    mine[first.value:last.value] = full_blocks[first.value:last.value]
+    words = torch.from_numpy(mine.view(np.uint32).astype(np.int64))     # gloo has no u32 sum; int64 holds every partial sum exactly
+    dist.all_reduce(words)
+    merged_blocks = words.numpy().astype(np.uint32).view(np.uint64)
+    minec = np.zeros(n_clusters, np.uint32)
+    minec[rank::world] = full_clusters[rank::world]
+    wc = torch.from_numpy(minec.astype(np.int64))
+    dist.all_reduce(wc)
+    sizes = torch.tensor([last.value - first.value], dtype=torch.int64)
+    dist.all_reduce(sizes)
+    if rank == 0:
+        q.put((bool(np.array_equal(merged_blocks, full_blocks)), bool(np.array_equal(wc.numpy().astype(np.uint32), full_clusters)), int(sizes.item())))
+    dist.destroy_process_group()
+
+
+def test_stage_output_merge_by_allreduce_gloo():
+    world, n_blocks, n_clusters = 2, 1001, 77
+    ctx = mp.get_context("spawn")
+    q = ctx.SimpleQueue()
+    port = _free_port()
+    procs = [ctx.Process(target=_merge_worker, args=(r, world, port, n_blocks, n_clusters, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(120)
+        assert p.exitcode == 0
+    ok_blocks, ok_clusters, covered = q.get()
+    assert ok_blocks and ok_clusters and covered == n_blocks
+
+
+def test_shard_range_is_a_disjoint_cover():
+    import ctypes
+    from basis_universal_b200 import lib
+    for n in (0, 1, 7, 64, 1001, 1 << 20):
+        for world in (1, 2, 3, 8):
+            covered = 0
+            prev_last = 0
+            for rank in range(world):
+                first, last = ctypes.c_uint32(0), ctypes.c_uint32(0)
+                lib().b200_shard_range(n, rank, world, ctypes.byref(first), ctypes.byref(last))
+                assert first.value == prev_last or first.value == n
+                assert first.value <= last.value <= n
+                covered += last.value - first.value
+                prev_last = last.value
+            assert covered == n
