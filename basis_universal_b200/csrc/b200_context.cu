@@ -58,7 +58,7 @@ extern "C" void b200_destroy_context(b200_context* ctx)
 	cudaStreamSynchronize(ctx->stream);
 	b200_tsvq_release(ctx);
 	b200_comm_release(ctx);
-	void* bufs[] = { ctx->d_in, ctx->d_out, ctx->d_meta, ctx->d_cands, ctx->d_slots, ctx->d_lists, ctx->d_etc_blocks };
+	void* bufs[] = { ctx->d_in, ctx->d_out, ctx->d_meta, ctx->d_cands, ctx->d_errs, ctx->d_slots, ctx->d_lists, ctx->d_etc_blocks };
 	for (void* p : bufs) if (p) cudaFreeAsync(p, ctx->stream);
 	for (void* p : ctx->d_aux) if (p) cudaFreeAsync(p, ctx->stream);
 	cudaStreamSynchronize(ctx->stream);

@@ -40,6 +40,11 @@ namespace
 	};
 	nccl_api g_nccl;
 	char g_dist_err[256] = "";
+
+	// An NCCL unique id makes ONE communicator. A compressor creates a context per image (basis_compressor does), so the
+	// communicator is kept for the life of the process and every context initialised with the same id attaches to it.
+	struct comm_cache { bool valid = false; uint8_t id[128]; ncclComm_t comm = nullptr; int rank = 0, world = 1, device = -1; };
+	comm_cache g_comm;
 }
 
 static_assert(sizeof(ncclUniqueId) == 128, "b200_comm_unique_id hands out 128 bytes");
@@ -63,18 +68,26 @@ extern "C" int b200_comm_init(b200_context* ctx, int rank, int world, const uint
 	if (ctx->comm) { ctx->fail("b200_comm_init: the context already has a communicator"); return 0; }
 	if (world == 1) { ctx->rank = 0; ctx->world = 1; return 1; }
 	if (!g_nccl.load(ctx->err, sizeof(ctx->err))) return 0;
+	if (g_comm.valid && !memcmp(g_comm.id, pId128, 128))
+	{
+		if (g_comm.rank != rank || g_comm.world != world || g_comm.device != ctx->device) { ctx->fail("b200_comm_init: this id already made a communicator with another rank/world/device"); return 0; }
+		ctx->comm = g_comm.comm; ctx->rank = rank; ctx->world = world;
+		return 1;
+	}
 	ncclUniqueId id;
 	memcpy(&id, pId128, 128);
 	ncclComm_t comm = nullptr;
 	const ncclResult_t r = g_nccl.CommInitRank(&comm, world, id, rank);
 	if (r != ncclSuccess) { snprintf(ctx->err, sizeof(ctx->err), "ncclCommInitRank: %s", g_nccl.GetErrorString(r)); return 0; }
+	if (g_comm.valid) g_nccl.CommDestroy(g_comm.comm); // a new id replaces the cached communicator (no context uses the old one any more in a well-formed host)
+	g_comm.valid = true; memcpy(g_comm.id, pId128, 128); g_comm.comm = comm; g_comm.rank = rank; g_comm.world = world; g_comm.device = ctx->device;
 	ctx->comm = comm; ctx->rank = rank; ctx->world = world;
 	return 1;
 }
 
 void b200_comm_release(b200_context* ctx)
 {
-	if (ctx && ctx->comm) { g_nccl.CommDestroy(static_cast<ncclComm_t>(ctx->comm)); ctx->comm = nullptr; ctx->world = 1; ctx->rank = 0; }
+	if (ctx && ctx->comm) { ctx->comm = nullptr; ctx->world = 1; ctx->rank = 0; } // the communicator itself lives in g_comm until the process ends or a new id arrives
 }
 
 // [first, last) of `rank`'s share of n per-block units: equal contiguous ranges of ceil(n / world), the tail ranks short or empty.

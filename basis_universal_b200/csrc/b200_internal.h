@@ -28,6 +28,7 @@ struct b200_context
 	void* d_out; size_t out_cap;     // encoded blocks
 	void* d_meta; size_t meta_cap;   // per-block class + partition ranks
 	void* d_cands; size_t cands_cap; // candidate records, slot-major
+	void* d_errs; size_t errs_cap;   // (uastc_err, bc7_err) per candidate, slot-major: the selection's input
 	void* d_slots; size_t slots_cap; // slot schedule
 	void* d_lists; size_t lists_cap; // per slot-class compacted block lists + their counters
 	void* d_aux[6]; size_t aux_cap[6]; // ETC1S stage inputs/outputs, RDO state

@@ -9,6 +9,7 @@
 // Build: nvcc -gencode arch=compute_100a,code=sm_100a --fmad=false (no FMA contraction: the reference is built for baseline
 // x86-64, and bit-exactness includes its float/double rounding; SURVEY.md section 7 hard part 1).
 #include "b200_internal.h"
+#define BU_UASTC_ENCODER_TU 1 // the kernels of this translation unit stage the colour-cell tables (bu_ccc.h)
 #include "bu_slots.h"
 
 using namespace bu;
@@ -97,13 +98,44 @@ __global__ void __launch_bounds__(128, BU_CLS_MINB) k_classify_rank(const uint4*
 
 // gridDim.y = slot index within the launch's slot class; candidates are stored slot-major (cands[slot][block], 64 B records).
 __global__ void __launch_bounds__(128, BU_CAND_MINB) k_candidates(const uint4* __restrict__ blocks, uint32_t n, const block_meta* __restrict__ meta,
-	candidate* __restrict__ cands, const slot_desc* __restrict__ slots, uint32_t first_slot, const uint32_t* __restrict__ list, const uint32_t* __restrict__ count, level_opts o)
+	candidate* __restrict__ cands, uint2* __restrict__ errs, const slot_desc* __restrict__ slots, uint32_t first_slot, const uint32_t* __restrict__ list, const uint32_t* __restrict__ count, level_opts o)
 {
 	const uint32_t li = blockIdx.x * blockDim.x + threadIdx.x;
-	if (li >= __ldg(count)) return;
-	const uint32_t i = __ldg(list + li);
 	const uint32_t si = first_slot + blockIdx.y;
 	const slot_desc s = slots[si];
+#if defined(BU_STAGE_TABLES) && defined(__CUDA_ARCH__)
+	if (blockIdx.x * blockDim.x >= __ldg(count)) return; // whole CTA beyond the work list
+	{
+		// TMA bulk copies of the mode's four table rows into shared memory, completion on one mbarrier
+		__shared__ __align__(8) unsigned long long s_mbar;
+		const uint32_t mbar = (uint32_t)__cvta_generic_to_shared(&s_mbar);
+		if (threadIdx.x == 0)
+		{
+			asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(mbar));
+			asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+		}
+		__syncthreads();
+		if (threadIdx.x == 0)
+		{
+			const bu_tables* T = &d_tables;
+			const uint32_t wbits = T->mode_weight_bits[s.mode], rs = (uint32_t)T->range_slot[T->mode_endpoint_range[s.mode]];
+			const uint32_t dst[4] = { (uint32_t)__cvta_generic_to_shared(bu_stage::s_rows.su), (uint32_t)__cvta_generic_to_shared(bu_stage::s_rows.nearest),
+				(uint32_t)__cvta_generic_to_shared(bu_stage::s_rows.wt), (uint32_t)__cvta_generic_to_shared(bu_stage::s_rows.wx) };
+			const void* src[4] = { T->sorted_unq + rs * 256, T->nearest + rs * 256, T->weights + wbits * 32, T->weightsx + wbits * 32 * 4 };
+			const uint32_t bytes[4] = { 256, 256, 32, 512 };
+			asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(mbar), "r"(256u + 256u + 32u + 512u) : "memory");
+			for (int k = 0; k < 4; k++)
+				asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" :: "r"(dst[k]), "l"(src[k]), "r"(bytes[k]), "r"(mbar) : "memory");
+		}
+		uint32_t done;
+		do
+		{
+			asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }" : "=r"(done) : "r"(mbar), "r"(0u) : "memory");
+		} while (!done);
+	}
+#endif
+	if (li >= __ldg(count)) return;
+	const uint32_t i = __ldg(list + li);
 	const block_meta m = meta[i];
 	uint32_t px[16];
 	load_block(blocks, i, px);
@@ -112,28 +144,30 @@ __global__ void __launch_bounds__(128, BU_CAND_MINB) k_candidates(const uint4* _
 	const uint4* src = reinterpret_cast<const uint4*>(&c);
 	uint4* d4 = reinterpret_cast<uint4*>(cands + (size_t)si * n + i);
 	d4[0] = src[0]; d4[1] = src[1]; d4[2] = src[2]; d4[3] = src[3];
+	errs[(size_t)si * n + i] = make_uint2(c.uastc_err, c.bc7_err); // what the selection in k_finish reads: 8 B per slot, coalesced across blocks
 }
 
 // One thread per block. (A cooperative 8-lanes-per-block variant was measured in round 1: 33.5 ms vs 23.8 ms for this
 // one -- the stage is issue-bound, not latency-bound, so spreading a block over lanes only adds redundant instructions.)
 // A slot's record exists iff the slot is active for the block's class (same predicate that built the work lists).
-__global__ void __launch_bounds__(128, BU_FIN_MINB) k_finish(const uint4* __restrict__ blocks, uint32_t n, const block_meta* __restrict__ meta,
-	const candidate* __restrict__ cands, const slot_desc* __restrict__ slots, uint32_t nslots, uint4* __restrict__ out, level_opts o, int level, uint32_t flags)
+// CAP bounds the per-thread selection arrays (thread-local memory): 32 covers levels 0-3, MAX_SLOTS level 4.
+template<int CAP> __global__ void __launch_bounds__(128, BU_FIN_MINB) k_finish(const uint4* __restrict__ blocks, uint32_t n, const block_meta* __restrict__ meta,
+	const candidate* __restrict__ cands, const uint2* __restrict__ errs, const slot_desc* __restrict__ slots, uint32_t nslots, uint4* __restrict__ out, level_opts o, int level, uint32_t flags)
 {
 	const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
 	if (i >= n) return;
 	const block_meta m = meta[i];
 	if (m.k.solid) return;
 
-	uint32_t ue[MAX_SLOTS], be[MAX_SLOTS];
-	uint8_t modes[MAX_SLOTS], idx[MAX_SLOTS];
+	uint32_t ue[CAP], be[CAP];
+	uint8_t modes[CAP], idx[CAP];
 	uint32_t cnt = 0;
 	for (uint32_t s = 0; s < nslots; s++)
 	{
 		const slot_desc sd = slots[s];
 		if (!slot_active(sd, m.k, o)) continue;
-		const candidate* c = cands + (size_t)s * n + i;
-		ue[cnt] = c->uastc_err; be[cnt] = c->bc7_err; modes[cnt] = sd.mode; idx[cnt] = (uint8_t)s;
+		const uint2 e = __ldg(errs + (size_t)s * n + i);
+		ue[cnt] = e.x; be[cnt] = e.y; modes[cnt] = sd.mode; idx[cnt] = (uint8_t)s;
 		cnt++;
 	}
 	const int best = select_candidate(cnt, ue, be, modes, flags);
@@ -167,6 +201,7 @@ static bool uastc_encode_chunk(b200_context* ctx, const uint4* dBlocks, uint32_t
 
 	if (!ctx->reserve(ctx->d_meta, ctx->meta_cap, (size_t)n * sizeof(block_meta))) return false;
 	if (!ctx->reserve(ctx->d_cands, ctx->cands_cap, (size_t)n * nslots * sizeof(candidate))) return false;
+	if (!ctx->reserve(ctx->d_errs, ctx->errs_cap, (size_t)n * nslots * sizeof(uint2))) return false;
 	if (!ctx->reserve(ctx->d_slots, ctx->slots_cap, sizeof(slot_desc) * MAX_SLOTS)) return false;
 	B200_CUDA_OK(ctx, cudaMemcpyAsync(ctx->d_slots, slots, sizeof(slot_desc) * nslots, cudaMemcpyHostToDevice, ctx->stream));
 
@@ -188,6 +223,7 @@ static bool uastc_encode_chunk(b200_context* ctx, const uint4* dBlocks, uint32_t
 	const uint32_t tpb = 128, gx = (n + tpb - 1) / tpb;
 	block_meta* meta = static_cast<block_meta*>(ctx->d_meta);
 	candidate* cands = static_cast<candidate*>(ctx->d_cands);
+	uint2* errs = static_cast<uint2*>(ctx->d_errs);
 	const slot_desc* d_slots = static_cast<const slot_desc*>(ctx->d_slots);
 
 	cudaEvent_t* ev = ctx->chunk_events();
@@ -200,11 +236,12 @@ static bool uastc_encode_chunk(b200_context* ctx, const uint4* dBlocks, uint32_t
 	for (int k = 0; k < 3; k++)
 	{
 		if (!class_count[k]) continue;
-		k_candidates<<<dim3(gx, class_count[k]), tpb, 0, ctx->stream>>>(dBlocks, n, meta, cands, d_slots, class_first[k], wl.list[k], wl.counts + k, o);
+		k_candidates<<<dim3(gx, class_count[k]), tpb, 0, ctx->stream>>>(dBlocks, n, meta, cands, errs, d_slots, class_first[k], wl.list[k], wl.counts + k, o);
 		ctx->launches++; __atomic_add_fetch(&g_b200_total_launches, 1, __ATOMIC_RELAXED);
 	}
 	if (ev) cudaEventRecord(ev[2], ctx->stream);
-	k_finish<<<gx, tpb, 0, ctx->stream>>>(dBlocks, n, meta, cands, d_slots, nslots, dOut, o, level, flags);
+	if (nslots <= 32) k_finish<32><<<gx, tpb, 0, ctx->stream>>>(dBlocks, n, meta, cands, errs, d_slots, nslots, dOut, o, level, flags);
+	else k_finish<MAX_SLOTS><<<gx, tpb, 0, ctx->stream>>>(dBlocks, n, meta, cands, errs, d_slots, nslots, dOut, o, level, flags);
 	ctx->launches++; __atomic_add_fetch(&g_b200_total_launches, 1, __ATOMIC_RELAXED);
 	if (ev) cudaEventRecord(ev[3], ctx->stream);
 	B200_CUDA_OK(ctx, cudaGetLastError());

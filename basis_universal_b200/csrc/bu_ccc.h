@@ -15,6 +15,39 @@
 #include "bu_common.h"
 #include "bu_tables.h"
 
+// The four table rows the colour-cell optimiser reads are a function of the mode alone (endpoint range, weight bits), and every
+// thread of a k_candidates CTA runs the same mode. With BU_STAGE_TABLES the kernel bulk-copies those rows (1056 B) into shared
+// memory once per CTA (TMA, cp.async.bulk + mbarrier) and the optimiser reads them there; otherwise they are read from the
+// bu_tables aggregate in global memory through L1. Same values either way; tools/ab_bench.py measures the difference.
+#if defined(BU_STAGE_TABLES) && defined(BU_UASTC_ENCODER_TU) && defined(__CUDA_ARCH__) // only the translation unit whose kernel stages the rows
+namespace bu_stage
+{
+	struct rows { uint8_t su[256]; uint8_t nearest[256]; uint8_t wt[32]; float wx[128]; };
+	__shared__ __align__(128) rows s_rows;
+}
+#define BU_ROW_SU(T, cfg) (bu_stage::s_rows.su)
+#define BU_ROW_NEAREST(T, cfg) (bu_stage::s_rows.nearest)
+#define BU_ROW_WT(T, cfg) (bu_stage::s_rows.wt)
+#define BU_ROW_WX(T, cfg) (bu_stage::s_rows.wx)
+#else
+#define BU_ROW_SU(T, cfg) ((T)->sorted_unq + (cfg).slot * 256)
+#define BU_ROW_NEAREST(T, cfg) ((T)->nearest + (cfg).slot * 256)
+#define BU_ROW_WT(T, cfg) ((T)->weights + (cfg).wbits * 32)
+#define BU_ROW_WX(T, cfg) ((T)->weightsx + (cfg).wbits * 32 * 4)
+#endif
+
+// The interpolated-colour table of cell_evaluate (<= 32 words, indexed by a data-dependent selector, hence not register-resident):
+// thread-local memory by default; with BU_WC_SMEM a per-thread column of a shared-memory array (word i of thread t at [i][t]:
+// conflict-free whatever the selectors are), which cannot be evicted to L2 / DRAM the way local-memory lines are.
+#if defined(BU_WC_SMEM) && defined(BU_UASTC_ENCODER_TU) && defined(__CUDA_ARCH__)
+namespace bu_stage { __shared__ uint32_t s_wc[32 * 128]; } // k_candidates runs 128 threads per CTA
+#define BU_WC_DECL uint32_t* const wc_ = bu_stage::s_wc + threadIdx.x;
+#define BU_WC(i) wc_[(i) * 128]
+#else
+#define BU_WC_DECL uint32_t wc_[32];
+#define BU_WC(i) wc_[i]
+#endif
+
 namespace bu {
 
 struct cell_cfg
@@ -38,9 +71,9 @@ struct cell_fit
 
 BU_NI inline void cell_evaluate(const bu_tables* T, const cell_cfg& cfg, const uint32_t* px, uint32_t n, const uint8_t* lo, const uint8_t* hi, cell_fit& fit, const uint8_t* force_sel = nullptr)
 {
-	const uint8_t* su = T->sorted_unq + cfg.slot * 256;
+	const uint8_t* su = BU_ROW_SU(T, cfg);
 	const uint32_t N = 1u << cfg.wbits;
-	const uint8_t* wt = T->weights + cfg.wbits * 32;
+	const uint8_t* wt = BU_ROW_WT(T, cfg);
 
 	int lc[4], dc[4];
 	for (int c = 0; c < 4; c++)
@@ -51,9 +84,9 @@ BU_NI inline void cell_evaluate(const bu_tables* T, const cell_cfg& cfg, const u
 
 	// Interpolated colours, channels (0,2) and (1,3) on 16-bit lanes. RGB cells keep byte 3 of the inner entries zero
 	// (the RGB metric never reads it).
-	uint32_t wc[32];
-	wc[0] = px_make(lc[0], lc[1], lc[2], lc[3]);
-	wc[N - 1] = px_make(lc[0] + dc[0], lc[1] + dc[1], lc[2] + dc[2], lc[3] + dc[3]);
+	BU_WC_DECL
+	BU_WC(0) = px_make(lc[0], lc[1], lc[2], lc[3]);
+	BU_WC(N - 1) = px_make(lc[0] + dc[0], lc[1] + dc[1], lc[2] + dc[2], lc[3] + dc[3]);
 	{
 		const uint32_t l02 = (uint32_t)lc[0] | ((uint32_t)lc[2] << 16), h02 = (uint32_t)(lc[0] + dc[0]) | ((uint32_t)(lc[2] + dc[2]) << 16);
 		const uint32_t l13 = cfg.has_alpha ? ((uint32_t)lc[1] | ((uint32_t)lc[3] << 16)) : (uint32_t)lc[1];
@@ -62,7 +95,7 @@ BU_NI inline void cell_evaluate(const bu_tables* T, const cell_cfg& cfg, const u
 		for (uint32_t i = 1; i + 1 < N; i++)
 		{
 			const uint32_t w = wt[i];
-			wc[i] = astc_lerp_x2(l02, h02, w) | (astc_lerp_x2(l13, h13, w) << 8);
+			BU_WC(i) = astc_lerp_x2(l02, h02, w) | (astc_lerp_x2(l13, h13, w) << 8);
 		}
 	}
 
@@ -76,7 +109,7 @@ BU_NI inline void cell_evaluate(const bu_tables* T, const cell_cfg& cfg, const u
 		for (uint32_t i = 0; i < n; i++)
 		{
 			const uint32_t s = force_sel[i];
-			total += dist_masked(wc[s], px[i], cmask);
+			total += dist_masked(BU_WC(s), px[i], cmask);
 			st[i] = (uint8_t)s;
 		}
 	}
@@ -97,7 +130,7 @@ BU_NI inline void cell_evaluate(const bu_tables* T, const cell_cfg& cfg, const u
 			const int dot = dot_s16x4_u8x4(dc01, dc23, p) - K;
 			int s = (int)((float)dot * f + .5f);
 			s = clampi(s, 1, (int)N - 1);
-			const uint32_t e0 = dist_masked(wc[s - 1], p, cmask), e1 = dist_masked(wc[s], p, cmask);
+			const uint32_t e0 = dist_masked(BU_WC(s - 1), p, cmask), e1 = dist_masked(BU_WC(s), p, cmask);
 			uint32_t e = e1;
 			if (e0 == e1) { if (s == 1) s = 0; }   // prefer the non-interpolated endpoint
 			else if (e0 < e1) { e = e0; --s; }
@@ -128,7 +161,7 @@ BU_NI inline uint64_t cell_try_endpoints(const bu_tables* T, const cell_cfg& cfg
 {
 	float xl[4], xh[4];
 	uint8_t lo0[4], hi0[4];
-	const uint8_t* nearest = T->nearest + cfg.slot * 256;
+	const uint8_t* nearest = BU_ROW_NEAREST(T, cfg);
 	for (int c = 0; c < 4; c++)
 	{
 		xl[c] = saturatef_(xl_in[c]);
@@ -170,7 +203,7 @@ BU_NI inline uint64_t cell_try_endpoints(const bu_tables* T, const cell_cfg& cfg
 
 BU_NI inline void cell_least_squares(const bu_tables* T, const cell_cfg& cfg, const uint32_t* px, uint32_t n, const uint8_t* sel, float* xl, float* xh)
 {
-	const float* wx = T->weightsx + cfg.wbits * 32 * 4;
+	const float* wx = BU_ROW_WX(T, cfg);
 	const int nc = cfg.has_alpha ? 4 : 3;
 	double z00 = 0.0, z10 = 0.0, z11 = 0.0;
 	double q00[4] = { 0, 0, 0, 0 }, t[4] = { 0, 0, 0, 0 };
@@ -242,8 +275,8 @@ BU_FI const uint8_t* cell_one_colour_table(const bu_tables* T, const cell_cfg& c
 BU_NI inline uint64_t cell_one_colour(const bu_tables* T, const cell_cfg& cfg, const uint8_t* tab, uint32_t sel, uint32_t alpha_index,
 	const uint32_t* px, uint32_t n, const uint32_t* c4, uint8_t* lo, uint8_t* hi)
 {
-	const uint8_t* su = T->sorted_unq + cfg.slot * 256;
-	const uint32_t w = T->weights[cfg.wbits * 32 + sel];
+	const uint8_t* su = BU_ROW_SU(T, cfg);
+	const uint32_t w = BU_ROW_WT(T, cfg)[sel];
 	for (int c = 0; c < 3; c++) { lo[c] = tab[c4[c] * 2]; hi[c] = tab[c4[c] * 2 + 1]; }
 	if (cfg.has_alpha) { lo[3] = tab[c4[3] * 2]; hi[3] = tab[c4[3] * 2 + 1]; }
 	else { lo[3] = (uint8_t)alpha_index; hi[3] = (uint8_t)alpha_index; }

@@ -11,16 +11,17 @@ struct bu_tables
 	int8_t   range_slot[21];          // range -> slot, -1 if unused
 	uint16_t range_levels[8];         // astc_get_levels (transcoder.cpp:14460)
 	uint8_t  unq[8 * 256];            // [slot][ASTC index]    -> 8-bit value   (g_astc_unquant, transcoder.cpp:14467)
-	uint8_t  sorted_unq[8 * 256];     // [slot][sorted order]  -> 8-bit value   (g_astc_sorted_order_unquant, bc7enc.cpp:93)
+	alignas(16) uint8_t  sorted_unq[8 * 256];     // (16-byte aligned rows: bulk-copied to shared memory by k_candidates)
+	                                  // [slot][sorted order]  -> 8-bit value   (g_astc_sorted_order_unquant, bc7enc.cpp:93)
 	uint8_t  sorted_idx[8 * 256];     // [slot][sorted order]  -> ASTC index
-	uint8_t  nearest[8 * 256];        // [slot][8-bit value]   -> sorted order  (g_astc_nearest_sorted_index, bc7enc.cpp:95)
+	alignas(16) uint8_t  nearest[8 * 256];        // [slot][8-bit value]   -> sorted order  (g_astc_nearest_sorted_index, bc7enc.cpp:95)
 
 	// Optimal single-colour endpoints {lo,hi} in sorted order (bc7enc.cpp:75-91, built at bc7enc.cpp:219-391).
 	uint8_t  one_r8_w3[512], one_r8_w2[512], one_r7_w2[512], one_r13_w2[512], one_r11_w5[512];
 
 	// Interpolation weights by weight-bit count 1..5 (transcoder.cpp:14582-14587) and the float LS forms (bc7enc.cpp:44-65).
-	uint8_t  weights[6 * 32];
-	float    weightsx[6 * 32 * 4];
+	alignas(16) uint8_t  weights[6 * 32];
+	alignas(16) float    weightsx[6 * 32 * 4];
 	uint8_t  bc7_weights4[16];
 
 	// UASTC mode properties (transcoder.cpp:14415-14427), Huffman mode codes (14380), BISE bits/trits/quints (14430).
