@@ -67,6 +67,7 @@ extern "C" void b200_destroy_context(b200_context* ctx)
 	cudaEventDestroy(ctx->ev_t0);
 	cudaEventDestroy(ctx->ev_t1);
 	for (uint32_t i = 0; i < ctx->stage_ev_count; i++) cudaEventDestroy(ctx->stage_ev[i]);
+	if (ctx->copy_in) { cudaStreamDestroy(ctx->copy_in); if (ctx->copy_out) cudaStreamDestroy(ctx->copy_out); for (int i = 0; i < 64; i++) if (ctx->pipe_ev[i]) cudaEventDestroy(ctx->pipe_ev[i]); }
 	cudaStreamDestroy(ctx->stream);
 	delete ctx;
 }

@@ -75,10 +75,78 @@ struct px_blocks_src
 	__device__ __forceinline__ uint32_t weight(uint64_t) const { return 1u; }
 };
 
+// A cluster is optimised by a TEAM whose members stride its texels: a warp (shuffle reductions), or for the few very large
+// clusters a whole CTA (warp reductions + shared memory). All decisions are taken on team-reduced values, so control flow is
+// uniform across the team and both teams compute exactly what one CPU thread computes.
+struct warp_team
+{
+	uint32_t rank, bloom_word;
+	static constexpr uint32_t size = 32;
+	__device__ explicit warp_team() : rank(threadIdx.x & 31), bloom_word(0) {}
+	__device__ __forceinline__ uint64_t sum(uint64_t v) { return warp_sum_u64(v); }
+	__device__ __forceinline__ void minmax(uint32_t& mn, uint32_t& mx)
+	{
+#pragma unroll
+		for (int m = 16; m >= 1; m >>= 1) { mn = min(mn, __shfl_xor_sync(0xffffffffu, mn, m)); mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, m)); }
+	}
+	// The CPU optimiser's 1024-bit Bloom filter of tried base colours (etc.cpp:1072), one 32-bit word per lane.
+	__device__ __forceinline__ bool bloom_test_and_set(uint32_t r5, uint32_t g5, uint32_t b5)
+	{
+		const uint32_t kh = hash_hsieh3(r5, g5, b5);
+		const uint32_t h0 = kh & 1023, h1 = (kh >> 10) & 1023;
+		const uint32_t w0 = __shfl_sync(0xffffffffu, bloom_word, h0 >> 5), w1 = __shfl_sync(0xffffffffu, bloom_word, h1 >> 5);
+		if ((w0 >> (h0 & 31)) & (w1 >> (h1 & 31)) & 1) return false;
+		if (rank == (h0 >> 5)) bloom_word |= 1u << (h0 & 31);
+		if (rank == (h1 >> 5)) bloom_word |= 1u << (h1 & 31);
+		return true;
+	}
+};
+
+#define ETC1S_CTA_TEAM 256
+struct cta_team_smem { uint64_t part[ETC1S_CTA_TEAM / 32]; uint32_t mn[ETC1S_CTA_TEAM / 32], mx[ETC1S_CTA_TEAM / 32]; uint32_t bloom[32]; };
+struct cta_team
+{
+	uint32_t rank;
+	cta_team_smem* S;
+	static constexpr uint32_t size = ETC1S_CTA_TEAM;
+	__device__ explicit cta_team(cta_team_smem* s) : rank(threadIdx.x), S(s) { if (threadIdx.x < 32) s->bloom[threadIdx.x] = 0; __syncthreads(); }
+	__device__ __forceinline__ uint64_t sum(uint64_t v)
+	{
+		v = warp_sum_u64(v);
+		if (!(rank & 31)) S->part[rank >> 5] = v;
+		__syncthreads();
+		uint64_t t = 0;
+#pragma unroll
+		for (int w = 0; w < ETC1S_CTA_TEAM / 32; w++) t += S->part[w];
+		__syncthreads();
+		return t;
+	}
+	__device__ __forceinline__ void minmax(uint32_t& mn, uint32_t& mx)
+	{
+#pragma unroll
+		for (int m = 16; m >= 1; m >>= 1) { mn = min(mn, __shfl_xor_sync(0xffffffffu, mn, m)); mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, m)); }
+		if (!(rank & 31)) { S->mn[rank >> 5] = mn; S->mx[rank >> 5] = mx; }
+		__syncthreads();
+#pragma unroll
+		for (int w = 0; w < ETC1S_CTA_TEAM / 32; w++) { mn = min(mn, S->mn[w]); mx = max(mx, S->mx[w]); }
+		__syncthreads();
+	}
+	__device__ __forceinline__ bool bloom_test_and_set(uint32_t r5, uint32_t g5, uint32_t b5)
+	{
+		const uint32_t kh = hash_hsieh3(r5, g5, b5);
+		const uint32_t h0 = kh & 1023, h1 = (kh >> 10) & 1023;
+		const bool seen = ((S->bloom[h0 >> 5] >> (h0 & 31)) & (S->bloom[h1 >> 5] >> (h1 & 31)) & 1) != 0;
+		__syncthreads();
+		if (!seen && !rank) { S->bloom[h0 >> 5] |= 1u << (h0 & 31); S->bloom[h1 >> 5] |= 1u << (h1 & 31); }
+		__syncthreads();
+		return !seen;
+	}
+};
+
 // Weighted error of base colour (r5,g5,b5) against the cluster's texels for every non-pruned intensity table; returns the
-// best (first strictly smaller) table and its error. Uniform across the warp.
-template<typename Src> __device__ void cluster_evaluate(const bu_tables* T, bool perceptual, const Src& src,
-	uint32_t lane, uint32_t spread, uint32_t r5, uint32_t g5, uint32_t b5, etc1s_solution& best, bool prune)
+// best (first strictly smaller) table and its error. Uniform across the team.
+template<typename Src, typename Team> __device__ void cluster_evaluate(const bu_tables* T, bool perceptual, const Src& src, Team& team,
+	uint32_t spread, uint32_t r5, uint32_t g5, uint32_t b5, etc1s_solution& best, bool prune)
 {
 	const uint64_t n = src.n;
 	uint64_t trial_err = (uint64_t)INT64_MAX;
@@ -90,7 +158,7 @@ template<typename Src> __device__ void cluster_evaluate(const bu_tables* T, bool
 		uint32_t colors[4];
 		etc1s_block_colors(T, r5, g5, b5, inten, colors);
 		uint64_t total = 0;
-		for (uint64_t i = lane; i < n; i += 32)
+		for (uint64_t i = team.rank; i < n; i += Team::size)
 		{
 			const uint32_t p = src.pixel(i);
 			uint32_t be = etc_color_distance(perceptual, p, colors[0]);
@@ -99,31 +167,19 @@ template<typename Src> __device__ void cluster_evaluate(const bu_tables* T, bool
 			be = min(be, etc_color_distance(perceptual, p, colors[3]));
 			total += (uint64_t)be * (uint64_t)src.weight(i);
 		}
-		total = warp_sum_u64(total);
+		total = team.sum(total);
 		if (total < trial_err) { trial_err = total; trial_inten = inten; valid = true; }
 	}
 	if (trial_err < best.err) { best.err = trial_err; best.r5 = r5; best.g5 = g5; best.b5 = b5; best.inten = trial_inten; best.valid = valid ? 1u : 0u; }
 }
 
-// The CPU optimiser's 1024-bit Bloom filter of tried base colours (etc.cpp:1072), one 32-bit word per lane.
-__device__ __forceinline__ bool warp_bloom_test_and_set(uint32_t& my_word, uint32_t lane, uint32_t r5, uint32_t g5, uint32_t b5)
-{
-	const uint32_t kh = hash_hsieh3(r5, g5, b5);
-	const uint32_t h0 = kh & 1023, h1 = (kh >> 10) & 1023;
-	const uint32_t w0 = __shfl_sync(0xffffffffu, my_word, h0 >> 5), w1 = __shfl_sync(0xffffffffu, my_word, h1 >> 5);
-	if ((w0 >> (h0 & 31)) & (w1 >> (h1 & 31)) & 1) return false;
-	if (lane == (h0 >> 5)) my_word |= 1u << (h0 & 31);
-	if (lane == (h1 >> 5)) my_word |= 1u << (h1 & 31);
-	return true;
-}
-
-// One warp optimises one cluster (etc1_optimizer over the cluster's texels); returns the packed base colour + intensity table.
-template<typename Src> __device__ uint64_t cluster_optimize(const bu_tables* T, bool perceptual, const Src& src, uint32_t lane, uint32_t total_perms, int flavour)
+// One team optimises one cluster (etc1_optimizer over the cluster's texels); returns the packed base colour + intensity table.
+template<typename Src, typename Team> __device__ uint64_t cluster_optimize(const bu_tables* T, bool perceptual, const Src& src, Team& team, uint32_t total_perms, int flavour)
 {
 	const uint64_t n = src.n;
 	uint32_t mn[3] = { 255, 255, 255 }, mx[3] = { 0, 0, 0 };
 	uint64_t sum[3] = { 0, 0, 0 }, tw = 0;
-	for (uint64_t i = lane; i < n; i += 32)
+	for (uint64_t i = team.rank; i < n; i += Team::size)
 	{
 		const uint32_t p = src.pixel(i);
 		const uint64_t w = src.weight(i);
@@ -136,15 +192,10 @@ template<typename Src> __device__ uint64_t cluster_optimize(const bu_tables* T, 
 	}
 	for (int c = 0; c < 3; c++)
 	{
-#pragma unroll
-		for (int m = 16; m >= 1; m >>= 1)
-		{
-			mn[c] = min(mn[c], __shfl_xor_sync(0xffffffffu, mn[c], m));
-			mx[c] = max(mx[c], __shfl_xor_sync(0xffffffffu, mx[c], m));
-		}
-		sum[c] = warp_sum_u64(sum[c]);
+		team.minmax(mn[c], mx[c]);
+		sum[c] = team.sum(sum[c]);
 	}
-	tw = warp_sum_u64(tw);
+	tw = team.sum(tw);
 
 	float avg[3];
 	for (int c = 0; c < 3; c++) avg[c] = (float)sum[c] / (float)tw;
@@ -154,18 +205,17 @@ template<typename Src> __device__ uint64_t cluster_optimize(const bu_tables* T, 
 	const bool prune = !cpu || total_perms <= 16;
 	const uint32_t r0 = etc1s_round5(avg[0], flavour), g0 = etc1s_round5(avg[1], flavour), b0 = etc1s_round5(avg[2], flavour);
 
-	uint32_t bloom_word = 0;
-	if (cpu) warp_bloom_test_and_set(bloom_word, lane, r0, g0, b0);
+	if (cpu) team.bloom_test_and_set(r0, g0, b0);
 	etc1s_solution best;
 	best.err = UINT64_MAX; best.r5 = best.g5 = best.b5 = best.inten = 0; best.lsb_plane = best.msb_plane = 0; best.valid = 0;
-	cluster_evaluate(T, perceptual, src, lane, spread, r0, g0, b0, best, prune);
+	cluster_evaluate(T, perceptual, src, team, spread, r0, g0, b0, best, prune);
 	if (best.err != 0)
 		for (uint32_t perm = 0; perm < total_perms; perm++)
 		{
 			uint32_t r1, g1, b1;
 			if (!etc1s_cluster_fit_step(T, best, avg, perm, r1, g1, b1, flavour)) continue;
-			if (cpu && !warp_bloom_test_and_set(bloom_word, lane, r1, g1, b1)) continue;
-			cluster_evaluate(T, perceptual, src, lane, spread, r1, g1, b1, best, prune);
+			if (cpu && !team.bloom_test_and_set(r1, g1, b1)) continue;
+			cluster_evaluate(T, perceptual, src, team, spread, r1, g1, b1, best, prune);
 			if (best.err == 0) break;
 		}
 	return etc1s_pack(best.r5, best.g5, best.b5, best.inten, 0, 0); // the kernel defines no selectors for clusters
@@ -178,23 +228,41 @@ __global__ void __launch_bounds__(128) k_etc1s_pixel_clusters(const b200_pixel_c
 	if (warp >= total_clusters) return;
 	px_list_src src;
 	src.px = pixels + clusters[warp].first_pixel_index; src.wts = weights + clusters[warp].first_pixel_index; src.n = clusters[warp].total_pixels;
-	const uint64_t r = cluster_optimize(&d_tables, perceptual_i != 0, src, lane, total_perms, flavour);
+	warp_team team;
+	const uint64_t r = cluster_optimize(&d_tables, perceptual_i != 0, src, team, total_perms, flavour);
 	if (lane == 0) out[warp] = r;
 }
 
 // Endpoint clusters as CSR lists of block indices into the resident source blocks; `order` lists the clusters largest first
 // so that the long ones start early (a cluster is one warp's serial work).
 __global__ void __launch_bounds__(128) k_etc1s_endpoint_clusters(const uint32_t* __restrict__ blocks, const uint32_t* __restrict__ offsets, const uint32_t* __restrict__ bidx,
-	const uint32_t* __restrict__ order, uint32_t total_clusters, uint64_t* __restrict__ out, int perceptual_i, uint32_t total_perms, int flavour, uint32_t rank, uint32_t world)
+	const uint32_t* __restrict__ order, uint32_t first, uint32_t total_clusters, uint64_t* __restrict__ out, int perceptual_i, uint32_t total_perms, int flavour, uint32_t rank, uint32_t world)
 {
-	const uint32_t warp = ((blockIdx.x * blockDim.x + threadIdx.x) >> 5) * world + rank, lane = threadIdx.x & 31; // every world-th cluster of the size-sorted order
+	const uint32_t warp = first + ((blockIdx.x * blockDim.x + threadIdx.x) >> 5) * world + rank, lane = threadIdx.x & 31; // every world-th cluster of the size-sorted order, after the big ones
 	if (warp >= total_clusters) return;
 	const uint32_t c = order[warp];
 	px_blocks_src src;
 	src.blocks = blocks; src.bidx = bidx + offsets[c]; src.n = (uint64_t)(offsets[c + 1] - offsets[c]) * 16;
 	uint64_t r = 0;
-	if (src.n) r = cluster_optimize(&d_tables, perceptual_i != 0, src, lane, total_perms, flavour);
+	warp_team team;
+	if (src.n) r = cluster_optimize(&d_tables, perceptual_i != 0, src, team, total_perms, flavour);
 	if (lane == 0) out[c] = r;
+}
+
+// The same for the largest clusters (>= ETC1S_BIG_CLUSTER_BLOCKS blocks), one CTA each: `order[0 .. n_big)` are those clusters.
+#define ETC1S_BIG_CLUSTER_BLOCKS 128
+__global__ void __launch_bounds__(ETC1S_CTA_TEAM) k_etc1s_endpoint_clusters_big(const uint32_t* __restrict__ blocks, const uint32_t* __restrict__ offsets, const uint32_t* __restrict__ bidx,
+	const uint32_t* __restrict__ order, uint32_t n_big, uint64_t* __restrict__ out, int perceptual_i, uint32_t total_perms, int flavour, uint32_t rank, uint32_t world)
+{
+	__shared__ cta_team_smem S;
+	const uint32_t k = blockIdx.x * world + rank;
+	if (k >= n_big) return;
+	const uint32_t c = order[k];
+	px_blocks_src src;
+	src.blocks = blocks; src.bidx = bidx + offsets[c]; src.n = (uint64_t)(offsets[c + 1] - offsets[c]) * 16;
+	cta_team team(&S);
+	const uint64_t r = cluster_optimize(&d_tables, perceptual_i != 0, src, team, total_perms, flavour);
+	if (!threadIdx.x) out[c] = r;
 }
 
 // ---- create_optimized_selector_codebook: one warp per selector cluster ---------------------------------------------------------
@@ -590,13 +658,15 @@ extern "C" int b200_etc1s_encode_endpoint_clusters(b200_context* ctx, void* pOut
 	const uint32_t total_indices = pCluster_offsets[total_clusters];
 	for (uint32_t i = 0; i < total_indices; i++)
 		if (pCluster_block_indices[i] >= ctx->etc_total_blocks) { ctx->fail("b200_etc1s_encode_endpoint_clusters: block index out of range"); return 0; }
-	// Launch order: clusters bucketed by size class (floor(log2(size))), largest class first
+	// Launch order: clusters by size class (floor(log2(size))), largest class first; clusters of >= ETC1S_BIG_CLUSTER_BLOCKS blocks
+	// (a power of two, so whole classes) form the prefix that gets one CTA each.
 	uint32_t* order = static_cast<uint32_t*>(malloc((size_t)total_clusters * 4));
 	if (!order) { ctx->fail("b200_etc1s_encode_endpoint_clusters: out of host memory"); return 0; }
+	uint32_t n_big = 0;
 	{
 		uint32_t counts[33] = { 0 }, ofs[33];
 		auto cls = [&](uint32_t c) { const uint32_t sz = pCluster_offsets[c + 1] - pCluster_offsets[c]; uint32_t b = 0; while (b < 32 && (1u << b) <= sz) b++; return 32 - b; };
-		for (uint32_t i = 0; i < total_clusters; i++) counts[cls(i)]++;
+		for (uint32_t i = 0; i < total_clusters; i++) { counts[cls(i)]++; if (pCluster_offsets[i + 1] - pCluster_offsets[i] >= ETC1S_BIG_CLUSTER_BLOCKS) n_big++; }
 		uint32_t acc = 0;
 		for (int b = 0; b < 33; b++) { ofs[b] = acc; acc += counts[b]; }
 		for (uint32_t i = 0; i < total_clusters; i++) order[ofs[cls(i)]++] = i;
@@ -610,9 +680,17 @@ extern "C" int b200_etc1s_encode_endpoint_clusters(b200_context* ctx, void* pOut
 	if (!shard_prepare_output(ctx, 0, (size_t)total_clusters * 8)) return 0;
 	B200_CUDA_OK(ctx, cudaEventRecord(ctx->ev0, ctx->stream));
 	const uint32_t warps_per_cta = 4, world = (uint32_t)(ctx->world > 1 ? ctx->world : 1);
-	const uint32_t my_clusters = (total_clusters + world - 1) / world;
+	if (n_big)
+	{
+		k_etc1s_endpoint_clusters_big<<<(n_big + world - 1) / world, ETC1S_CTA_TEAM, 0, ctx->stream>>>(static_cast<const uint32_t*>(ctx->d_etc_blocks),
+			static_cast<const uint32_t*>(ctx->d_aux[1]), static_cast<const uint32_t*>(ctx->d_aux[2]), static_cast<const uint32_t*>(ctx->d_aux[3]), n_big,
+			static_cast<uint64_t*>(ctx->d_aux[0]), perceptual, total_perms, ctx->etc_flavour, (uint32_t)ctx->rank, world);
+		ctx->launches++; __atomic_add_fetch(&g_b200_total_launches, 1, __ATOMIC_RELAXED);
+	}
+	const uint32_t my_clusters = (total_clusters - n_big + world - 1) / world;
+	if (my_clusters)
 	k_etc1s_endpoint_clusters<<<(my_clusters + warps_per_cta - 1) / warps_per_cta, warps_per_cta * 32, 0, ctx->stream>>>(static_cast<const uint32_t*>(ctx->d_etc_blocks),
-		static_cast<const uint32_t*>(ctx->d_aux[1]), static_cast<const uint32_t*>(ctx->d_aux[2]), static_cast<const uint32_t*>(ctx->d_aux[3]), total_clusters,
+		static_cast<const uint32_t*>(ctx->d_aux[1]), static_cast<const uint32_t*>(ctx->d_aux[2]), static_cast<const uint32_t*>(ctx->d_aux[3]), n_big, total_clusters,
 		static_cast<uint64_t*>(ctx->d_aux[0]), perceptual, total_perms, ctx->etc_flavour, (uint32_t)ctx->rank, world);
 	return finish(ctx, pOutput_blocks, 0, (size_t)total_clusters * 8, B200_STAT_ETC1S_ENDPOINT_CLUSTERS);
 }

@@ -17,6 +17,7 @@ struct b200_context
 	int device;
 	cudaStream_t stream;
 	cudaEvent_t ev0, ev1, ev_t0, ev_t1;
+	cudaStream_t copy_in, copy_out; cudaEvent_t pipe_ev[64]; // host-pointer UASTC encode: H2D / D2H streams and per-piece events (created on first use)
 	cudaEvent_t stage_ev[64 * 4]; uint32_t stage_ev_count, stage_ev_used; // 4 events per chunk: before k0, k1, k2, after k2
 	float stage_ms[3];
 	float last_ms;

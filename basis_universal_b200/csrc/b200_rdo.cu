@@ -55,8 +55,6 @@ __device__ __forceinline__ void st_bits(uint4* p, const block_bits& b) { uint4 v
 
 #define RDO_THREADS 256
 
-struct rdo_prologue { rdo_step st; uint32_t px[16]; uint32_t state; };
-
 // chains[c] = { first block, one past the last block } of chain c in the (possibly multi-slice) block array
 __global__ void __launch_bounds__(RDO_THREADS) k_rdo_chain(uint4* blocks, const uint4* __restrict__ pixels, const uint2* __restrict__ chains,
 	hist_entry* hist_all, uint32_t hist_cap, uint8_t* modified, rdo_params p, int* failed)
@@ -72,21 +70,21 @@ __global__ void __launch_bounds__(RDO_THREADS) k_rdo_chain(uint4* blocks, const 
 	__shared__ float s_t[RDO_THREADS / 32];
 	__shared__ uint32_t s_i[RDO_THREADS / 32];
 	__shared__ uint32_t s_winner;
-	// Everything a step needs that depends on the block alone (its unpacked form, source texels, error of the current encoding,
-	// smoothness scale, BC7-transcode endpoints, selector field) is independent of the steps before it. So the chain advances in
-	// batches of RDO_THREADS blocks: first every THREAD prepares one block of the batch (fully parallel; the per-block work is
-	// the expensive part of a step that ends in "skip"), then the batch's steps run in order with all threads on the trials.
+	// Everything a step needs that depends on the block alone (its unpacked form, source texels, error, smoothness scale,
+	// selector field) is independent of the steps before it: each of the CTA's 8 warps prepares one of the next 8 blocks, then
+	// the 8 steps run in order with all 256 threads on the trials. (Measured alternative, round 2: one block per THREAD, 256 per
+	// batch -- 4096^2 level 2 with 4 chains 5.98 s instead of 4.69 s: consecutive blocks use different modes, so a warp of 32
+	// per-thread prologues serialises ~10 divergent paths, which costs more than 8 warp-uniform prologues per 8 blocks.)
 	enum { PRO_OK = 0, PRO_SOLID = 1, PRO_SKIP = 2, PRO_BAD = 3 };
-	extern __shared__ __align__(16) unsigned char s_dyn[];
-	rdo_prologue* s_pro = reinterpret_cast<rdo_prologue*>(s_dyn);
+	struct prologue { rdo_step st; uint32_t px[16]; uint32_t state; };
+	__shared__ prologue s_pro[RDO_THREADS / 32];
 
-	for (uint32_t base = first; base < last; base += RDO_THREADS)
+	for (uint32_t base = first; base < last; base += RDO_THREADS / 32)
 	{
 		{
-			const uint32_t bi = base + tid;
+			const uint32_t bi = base + (tid >> 5);
 			if (bi < last)
 			{
-				rdo_prologue& P = s_pro[tid];
 				rdo_step st;
 				uint32_t px[16];
 				uint32_t state = PRO_OK;
@@ -108,33 +106,37 @@ __global__ void __launch_bounds__(RDO_THREADS) k_rdo_chain(uint4* blocks, const 
 					st.cur_sel_bits = bits_read(st.bits, st.first_sel_bit, n0);
 					if (st.cur_rms_err >= p.skip_block_rms_thresh) state = PRO_SKIP;
 				}
-				P.state = state;
-				if (state == PRO_OK || state == PRO_SKIP)
+				if ((tid & 31) == 0)
 				{
-					P.st = st;
-					for (int k = 0; k < 16; k++) P.px[k] = px[k];
+					prologue& P = s_pro[tid >> 5];
+					P.state = state;
+					if (state == PRO_OK || state == PRO_SKIP)
+					{
+						P.st = st;
+						for (int k = 0; k < 16; k++) P.px[k] = px[k];
+					}
 				}
 			}
 		}
 		__syncthreads();
 
-	const uint32_t batch_end = (base + RDO_THREADS < last) ? base + RDO_THREADS : last;
-	for (uint32_t bi = base; bi < batch_end; bi++)
+	for (uint32_t bi = base; bi < last && bi < base + RDO_THREADS / 32; bi++)
 	{
-		const rdo_prologue& P = s_pro[bi - base];
+		const prologue& P = s_pro[bi - base];
 		if (P.state == PRO_BAD) { if (!tid) *failed = 1; return; }
 		if (P.state == PRO_SOLID) continue;
+		// read in place from shared memory (s_pro is only rewritten after the barrier that ends the batch): copying the 270-byte
+		// record into every thread's local memory was a quarter of a step's memory traffic
+		const rdo_step& st = P.st;
+		const uint32_t* px = P.px;
+		const uint32_t n0 = st.total_sel_bits < 64 ? st.total_sel_bits : 64;
+
 		if (P.state == PRO_SKIP)
 		{
-			// thread 0 alone touches the history between two trial steps; the barrier at the top of the next trial step publishes it
-			if (!tid) hist_set(hist, hmask, P.st.first_sel_bit, P.st.cur_sel_bits, bi);
+			if (!tid) hist_set(hist, hmask, st.first_sel_bit, st.cur_sel_bits, bi);
+			__syncthreads();
 			continue;
 		}
-		__syncthreads();
-		const rdo_step st = P.st;
-		uint32_t px[16];
-		for (int k = 0; k < 16; k++) px[k] = P.px[k];
-		const uint32_t n0 = st.total_sel_bits < 64 ? st.total_sel_bits : 64;
 
 		const int found = hist_find(hist, hmask, st.first_sel_bit, st.cur_sel_bits);
 		const int cur_bits = (found < 0) ? (int)((st.total_sel_bits * p.lz_literal_cost) / 100) : (int)match_cost_estimate((bi - (uint32_t)found) * 16);
@@ -193,9 +195,9 @@ __global__ void __launch_bounds__(RDO_THREADS) k_rdo_chain(uint4* blocks, const 
 				hist_set(hist, hmask, st.first_sel_bit, bits_read(nb, st.first_sel_bit, n0), bi);
 			}
 		}
-		__syncthreads(); // the winner's history insert must be complete before thread 0 registers the following skipped blocks
+		__syncthreads();
 	}
-		__syncthreads(); // s_pro is rewritten by the next batch; blocks[] written by a winner are re-read by its prologue
+		__syncthreads(); // s_pro is rewritten by the next batch
 	}
 }
 
@@ -279,11 +281,7 @@ static int rdo_run_device(b200_context* ctx, uint4* d_blocks, const uint4* d_pix
 	free(h_chains);
 	if (e != cudaSuccess) { ctx->fail_cuda("b200_uastc_rdo: setup", e); return 0; }
 	B200_CUDA_OK(ctx, cudaEventRecord(ctx->ev0, ctx->stream));
-	{
-		static bool attr_set = false; // the prologue batch (one record per thread) needs more than the default 48 KB
-		if (!attr_set) { B200_CUDA_OK(ctx, cudaFuncSetAttribute(k_rdo_chain, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(rdo_prologue) * RDO_THREADS))); attr_set = true; }
-	}
-	k_rdo_chain<<<num_chains, RDO_THREADS, sizeof(rdo_prologue) * RDO_THREADS, ctx->stream>>>(d_blocks, d_pixels, d_chains, static_cast<hist_entry*>(ctx->d_aux[4]), cap, modified, p, failed);
+	k_rdo_chain<<<num_chains, RDO_THREADS, 0, ctx->stream>>>(d_blocks, d_pixels, d_chains, static_cast<hist_entry*>(ctx->d_aux[4]), cap, modified, p, failed);
 	const int lvl = (int)(flags & 0xF);
 	k_rdo_rehint<<<(num_blocks + 127) / 128, 128, 0, ctx->stream>>>(d_blocks, d_pixels, num_blocks, modified, make_level_opts(lvl), lvl, flags, failed);
 	ctx->launches = 2; __atomic_add_fetch(&g_b200_total_launches, 2, __ATOMIC_RELAXED);

@@ -192,6 +192,39 @@ namespace
 		uint8_t side[NT];
 	};
 
+	// ACCUMULATE-phase helpers: add the tile's terms in member order; four members per iteration so that the shared-memory loads
+	// run ahead of the add chain, which is the only dependency between iterations.
+	template<int D, int NT> __device__ __forceinline__ float tile_sum_side(const tile_smem<D, NT>& S, uint32_t nt, uint32_t c, uint32_t want, float acc)
+	{
+		uint32_t k = 0;
+		for (; k + 4 <= nt; k += 4)
+		{
+			const uint32_t sd = *reinterpret_cast<const uint32_t*>(S.side + k);
+			const float a0 = S.p[k][c], a1 = S.p[k + 1][c], a2 = S.p[k + 2][c], a3 = S.p[k + 3][c];
+			if ((sd & 0xFFu) == want) acc += a0;
+			if (((sd >> 8) & 0xFFu) == want) acc += a1;
+			if (((sd >> 16) & 0xFFu) == want) acc += a2;
+			if ((sd >> 24) == want) acc += a3;
+		}
+		for (; k < nt; k++) if (S.side[k] == want) acc += S.p[k][c];
+		return acc;
+	}
+	template<int D, int NT> __device__ __forceinline__ double tile_sum_side_t(const tile_smem<D, NT>& S, uint32_t nt, uint32_t want, double acc)
+	{
+		uint32_t k = 0;
+		for (; k + 4 <= nt; k += 4)
+		{
+			const uint32_t sd = *reinterpret_cast<const uint32_t*>(S.side + k);
+			const float a0 = S.t[k], a1 = S.t[k + 1], a2 = S.t[k + 2], a3 = S.t[k + 3];
+			if ((sd & 0xFFu) == want) acc += (double)a0;
+			if (((sd >> 8) & 0xFFu) == want) acc += (double)a1;
+			if (((sd >> 16) & 0xFFu) == want) acc += (double)a2;
+			if ((sd >> 24) == want) acc += (double)a3;
+		}
+		for (; k < nt; k++) if (S.side[k] == want) acc += (double)S.t[k];
+		return acc;
+	}
+
 	// ---- prepare_root (enc.h:1696-1721) -------------------------------------------------------------------------------------
 
 	template<int D, int NT> __global__ void __launch_bounds__(NT) k_tsvq_root(const float* __restrict__ vecs, const float* __restrict__ wf, const unsigned long long* __restrict__ w64,
@@ -223,8 +256,18 @@ namespace
 			}
 			__syncthreads();
 			const uint32_t nt = (count - base < (uint32_t)NT) ? count - base : (uint32_t)NT;
-			if (tid < D) { for (uint32_t k = 0; k < nt; k++) acc += S.p[k][tid]; }
-			else if (tid == D) { for (uint32_t k = 0; k < nt; k++) acc_d += (double)S.t[k]; }
+			if (tid < D)
+			{
+				uint32_t k = 0;
+				for (; k + 4 <= nt; k += 4) { const float a0 = S.p[k][tid], a1 = S.p[k + 1][tid], a2 = S.p[k + 2][tid], a3 = S.p[k + 3][tid]; acc += a0; acc += a1; acc += a2; acc += a3; }
+				for (; k < nt; k++) acc += S.p[k][tid];
+			}
+			else if (tid == D)
+			{
+				uint32_t k = 0;
+				for (; k + 4 <= nt; k += 4) { const float a0 = S.t[k], a1 = S.t[k + 1], a2 = S.t[k + 2], a3 = S.t[k + 3]; acc_d += (double)a0; acc_d += (double)a1; acc_d += (double)a2; acc_d += (double)a3; }
+				for (; k < nt; k++) acc_d += (double)S.t[k];
+			}
 			__syncthreads();
 		}
 		if (tid < D) s_sum[tid] = acc; else if (tid == D) s_tt = acc_d;
@@ -320,7 +363,16 @@ namespace
 					__syncthreads();
 					const uint32_t nt = (count - base < (uint32_t)NT) ? count - base : (uint32_t)NT;
 					if (tid < NE)
-						for (uint32_t k = 0; k < nt; k++) acc = acc + S.p[k][ex] * (S.t[k] * S.p[k][ey]);
+					{
+						uint32_t k = 0;
+						for (; k + 4 <= nt; k += 4)
+						{
+							const float q0 = S.p[k][ex] * (S.t[k] * S.p[k][ey]), q1 = S.p[k + 1][ex] * (S.t[k + 1] * S.p[k + 1][ey]);
+							const float q2 = S.p[k + 2][ex] * (S.t[k + 2] * S.p[k + 2][ey]), q3 = S.p[k + 3][ex] * (S.t[k + 3] * S.p[k + 3][ey]);
+							acc = acc + q0; acc = acc + q1; acc = acc + q2; acc = acc + q3;
+						}
+						for (; k < nt; k++) acc = acc + S.p[k][ex] * (S.t[k] * S.p[k][ey]);
+					}
 					__syncthreads();
 				}
 				if (tid < NE) s_cov[ex * D + ey] = acc;
@@ -353,11 +405,7 @@ namespace
 					}
 					__syncthreads();
 					const uint32_t nt = (count - base < (uint32_t)NT) ? count - base : (uint32_t)NT;
-					if (tid < 2 * D)
-					{
-						const uint32_t want = tid / D, c = tid % D;
-						for (uint32_t k = 0; k < nt; k++) if (S.side[k] == want) acc += S.p[k][c];
-					}
+					if (tid < 2 * D) acc = tile_sum_side<D, NT>(S, nt, tid % D, tid / D, acc);
 					__syncthreads();
 				}
 				if (tid < 2 * D) s_sum[tid] = acc;
@@ -410,16 +458,8 @@ namespace
 					}
 					__syncthreads();
 					const uint32_t nt = (count - base < (uint32_t)NT) ? count - base : (uint32_t)NT;
-					if (tid < 2 * D)
-					{
-						const uint32_t want = tid / D, c = tid % D;
-						for (uint32_t k = 0; k < nt; k++) if (S.side[k] == want) acc += S.p[k][c];
-					}
-					else if (tid < 2 * D + 2)
-					{
-						const uint32_t want = tid - 2 * D;
-						for (uint32_t k = 0; k < nt; k++) if (S.side[k] == want) acc_d += (double)S.t[k];
-					}
+					if (tid < 2 * D) acc = tile_sum_side<D, NT>(S, nt, tid % D, tid / D, acc);
+					else if (tid < 2 * D + 2) acc_d = tile_sum_side_t<D, NT>(S, nt, tid - 2 * D, acc_d);
 					__syncthreads();
 				}
 				if (tid < 2 * D) s_sum[tid] = acc; else if (tid < 2 * D + 2) s_tt[tid - 2 * D] = acc_d;

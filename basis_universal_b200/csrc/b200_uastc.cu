@@ -277,6 +277,10 @@ extern "C" int b200_uastc_encode_blocks_device(b200_context* ctx, const void* dB
 	return 1;
 }
 
+// Host-pointer form. Large inputs are cut into pieces that flow through three streams: H2D of piece i+1 and D2H of piece i-1 overlap
+// the kernels of piece i (two copy engines + the SMs), so the call costs ~ the kernels plus one piece's copy each way instead of
+// copy + kernels + copy in series (at level 0 the 80 MiB of PCIe traffic is as long as the kernels). Needs pinned host memory to
+// overlap; with pageable memory the copies serialise and the result is the same.
 extern "C" int b200_uastc_encode_blocks(b200_context* ctx, const void* pBlocks, uint32_t num_blocks, void* pOut, uint32_t flags)
 {
 	if (!ctx) return 0;
@@ -288,19 +292,57 @@ extern "C" int b200_uastc_encode_blocks(b200_context* ctx, const void* pBlocks, 
 	if (!ctx->reserve(ctx->d_in, ctx->in_cap, (size_t)num_blocks * 64)) return 0;
 	if (!ctx->reserve(ctx->d_out, ctx->out_cap, (size_t)num_blocks * 16)) return 0;
 
-	float total_ms = 0;
 	const uint32_t chunk = uastc_chunk_blocks(flags);
-	// Copies and kernels are issued chunk by chunk on one stream; the copy engine runs ahead of / behind the SMs.
-	B200_CUDA_OK(ctx, cudaMemcpyAsync(ctx->d_in, pBlocks, (size_t)num_blocks * 64, cudaMemcpyHostToDevice, ctx->stream));
-	B200_CUDA_OK(ctx, cudaEventRecord(ctx->ev0, ctx->stream));
-	for (uint32_t first = 0; first < num_blocks; first += chunk)
+	uint32_t piece = chunk;
+	const uint32_t PIECES = 8;
+	if (num_blocks >= PIECES * 32768u) { piece = (num_blocks + PIECES - 1) / PIECES; piece = (piece + 1023u) & ~1023u; if (piece > chunk) piece = chunk; }
+	const uint32_t npieces = (num_blocks + piece - 1) / piece;
+	const bool pipelined = npieces > 1 && npieces <= 32;
+	if (pipelined && !ctx->copy_in)
 	{
-		const uint32_t n = (num_blocks - first < chunk) ? (num_blocks - first) : chunk;
-		if (!uastc_encode_chunk(ctx, static_cast<const uint4*>(ctx->d_in) + (size_t)first * 4, n, static_cast<uint4*>(ctx->d_out) + first, flags)) return 0;
+		if (cudaStreamCreateWithFlags(&ctx->copy_in, cudaStreamNonBlocking) != cudaSuccess || cudaStreamCreateWithFlags(&ctx->copy_out, cudaStreamNonBlocking) != cudaSuccess)
+		{ ctx->fail("b200_uastc_encode_blocks: stream creation failed"); return 0; }
+		for (int i = 0; i < 64; i++)
+			if (cudaEventCreateWithFlags(&ctx->pipe_ev[i], cudaEventDisableTiming) != cudaSuccess) { ctx->fail("b200_uastc_encode_blocks: event creation failed"); return 0; }
 	}
-	B200_CUDA_OK(ctx, cudaEventRecord(ctx->ev1, ctx->stream));
-	B200_CUDA_OK(ctx, cudaMemcpyAsync(pOut, ctx->d_out, (size_t)num_blocks * 16, cudaMemcpyDeviceToHost, ctx->stream));
-	B200_CUDA_OK(ctx, cudaStreamSynchronize(ctx->stream));
+
+	float total_ms = 0;
+	B200_CUDA_OK(ctx, cudaEventRecord(ctx->ev0, ctx->stream));
+	if (!pipelined)
+	{
+		B200_CUDA_OK(ctx, cudaMemcpyAsync(ctx->d_in, pBlocks, (size_t)num_blocks * 64, cudaMemcpyHostToDevice, ctx->stream));
+		for (uint32_t first = 0; first < num_blocks; first += chunk)
+		{
+			const uint32_t n = (num_blocks - first < chunk) ? (num_blocks - first) : chunk;
+			if (!uastc_encode_chunk(ctx, static_cast<const uint4*>(ctx->d_in) + (size_t)first * 4, n, static_cast<uint4*>(ctx->d_out) + first, flags)) return 0;
+		}
+		B200_CUDA_OK(ctx, cudaEventRecord(ctx->ev1, ctx->stream));
+		B200_CUDA_OK(ctx, cudaMemcpyAsync(pOut, ctx->d_out, (size_t)num_blocks * 16, cudaMemcpyDeviceToHost, ctx->stream));
+		B200_CUDA_OK(ctx, cudaStreamSynchronize(ctx->stream));
+	}
+	else
+	{
+		// the copy streams start after whatever the main stream had queued (ev0), the main stream ends after the last D2H
+		B200_CUDA_OK(ctx, cudaStreamWaitEvent(ctx->copy_in, ctx->ev0, 0));
+		for (uint32_t k = 0; k < npieces; k++)
+		{
+			const uint32_t first = k * piece, n = (num_blocks - first < piece) ? (num_blocks - first) : piece;
+			B200_CUDA_OK(ctx, cudaMemcpyAsync(static_cast<uint8_t*>(ctx->d_in) + (size_t)first * 64, static_cast<const uint8_t*>(pBlocks) + (size_t)first * 64, (size_t)n * 64, cudaMemcpyHostToDevice, ctx->copy_in));
+			B200_CUDA_OK(ctx, cudaEventRecord(ctx->pipe_ev[k], ctx->copy_in));
+		}
+		for (uint32_t k = 0; k < npieces; k++)
+		{
+			const uint32_t first = k * piece, n = (num_blocks - first < piece) ? (num_blocks - first) : piece;
+			B200_CUDA_OK(ctx, cudaStreamWaitEvent(ctx->stream, ctx->pipe_ev[k], 0));
+			if (!uastc_encode_chunk(ctx, static_cast<const uint4*>(ctx->d_in) + (size_t)first * 4, n, static_cast<uint4*>(ctx->d_out) + first, flags)) return 0;
+			B200_CUDA_OK(ctx, cudaEventRecord(ctx->pipe_ev[32 + k], ctx->stream));
+			B200_CUDA_OK(ctx, cudaStreamWaitEvent(ctx->copy_out, ctx->pipe_ev[32 + k], 0));
+			B200_CUDA_OK(ctx, cudaMemcpyAsync(static_cast<uint8_t*>(pOut) + (size_t)first * 16, static_cast<uint8_t*>(ctx->d_out) + (size_t)first * 16, (size_t)n * 16, cudaMemcpyDeviceToHost, ctx->copy_out));
+		}
+		B200_CUDA_OK(ctx, cudaEventRecord(ctx->ev1, ctx->stream));
+		B200_CUDA_OK(ctx, cudaStreamSynchronize(ctx->copy_out));
+		B200_CUDA_OK(ctx, cudaStreamSynchronize(ctx->stream));
+	}
 	B200_CUDA_OK(ctx, cudaEventElapsedTime(&total_ms, ctx->ev0, ctx->ev1));
 	ctx->last_ms = total_ms;
 	ctx->collect_stage_times();
