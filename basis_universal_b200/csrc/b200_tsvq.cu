@@ -225,14 +225,48 @@ namespace
 		return acc;
 	}
 
+	// Pass driver. Plain form (PIPE = false, TS threads): load tile / barrier / accumulate / barrier. Pipelined form (PIPE = true,
+	// 2 * TS threads, used for nodes with many members): threads TS .. 2TS-1 are LOADERS that stage tile t + 1 into the other buffer
+	// while threads 0 .. TS-1 (the ACCUMULATORS among them) add tile t: the per-member arithmetic and its global loads run under the
+	// add chain, one barrier per tile. load(member index, tile, slot); acc(tile, members in tile).
+	template<bool PIPE, int TS, typename Tile, typename LoadF, typename AccF> __device__ __forceinline__ void run_pass(uint32_t count, Tile* tiles, LoadF load, AccF acc)
+	{
+		const uint32_t tid = threadIdx.x;
+		if (!PIPE)
+		{
+			for (uint32_t base = 0; base < count; base += TS)
+			{
+				if (base + tid < count) load(base + tid, tiles[0], tid);
+				__syncthreads();
+				acc(tiles[0], (count - base < (uint32_t)TS) ? count - base : (uint32_t)TS);
+				__syncthreads();
+			}
+		}
+		else
+		{
+			const bool loader = tid >= (uint32_t)TS;
+			const uint32_t slot = tid - TS;
+			if (loader && slot < count) load(slot, tiles[0], slot);
+			__syncthreads();
+			uint32_t t = 0;
+			for (uint32_t base = 0; base < count; base += TS, t ^= 1)
+			{
+				if (loader) { const uint32_t i = base + TS + slot; if (i < count) load(i, tiles[t ^ 1], slot); }
+				else acc(tiles[t], (count - base < (uint32_t)TS) ? count - base : (uint32_t)TS);
+				__syncthreads();
+			}
+		}
+	}
+
 	// ---- prepare_root (enc.h:1696-1721) -------------------------------------------------------------------------------------
 
-	template<int D, int NT> __global__ void __launch_bounds__(NT) k_tsvq_root(const float* __restrict__ vecs, const float* __restrict__ wf, const unsigned long long* __restrict__ w64,
+	template<int D, int TS, bool PIPE> __global__ void __launch_bounds__(PIPE ? 2 * TS : TS) k_tsvq_root(const float* __restrict__ vecs, const float* __restrict__ wf, const unsigned long long* __restrict__ w64,
 		const uint32_t* __restrict__ members, node_rec<D>* nodes, const uint32_t* __restrict__ root_ids, root_out* out)
 	{
+		constexpr int NT = PIPE ? 2 * TS : TS;
 		__shared__ double s_part[(NT / 32) * 1];
 		__shared__ double s_out[1];
-		__shared__ tile_smem<D, NT> S;
+		__shared__ tile_smem<D, TS> S[PIPE ? 2 : 1];
 		__shared__ float s_sum[D];
 		__shared__ double s_tt;
 		node_rec<D>& nd = nodes[root_ids[blockIdx.x]];
@@ -240,36 +274,33 @@ namespace
 		double wsum = 0;
 		float acc = 0.0f;
 		double acc_d = 0.0;
-		for (uint32_t base = 0; base < count; base += NT)
-		{
-			const uint32_t i = base + tid;
-			if (i < count)
+		run_pass<PIPE, TS>(count, S,
+			[&](uint32_t i, tile_smem<D, TS>& T, uint32_t slot)
 			{
 				const uint32_t m = members[start + i];
 				float v[D];
 				load_vec<D>(vecs, m, v);
 				const float w = wf[m];
 #pragma unroll
-				for (int c = 0; c < D; c++) S.p[tid][c] = v[c] * w;   // root.m_origin += v * (float)weight
-				S.t[tid] = dot_f<D>(v, v) * w;                          // ttsum += v.dot(v) * weight
-				wsum += (double)w64[m];                                  // integers: exact in any order
-			}
-			__syncthreads();
-			const uint32_t nt = (count - base < (uint32_t)NT) ? count - base : (uint32_t)NT;
-			if (tid < D)
+				for (int c = 0; c < D; c++) T.p[slot][c] = v[c] * w;   // root.m_origin += v * (float)weight
+				T.t[slot] = dot_f<D>(v, v) * w;                          // ttsum += v.dot(v) * weight
+				wsum += (double)w64[m];                                    // integers: exact in any order
+			},
+			[&](const tile_smem<D, TS>& T, uint32_t nt)
 			{
-				uint32_t k = 0;
-				for (; k + 4 <= nt; k += 4) { const float a0 = S.p[k][tid], a1 = S.p[k + 1][tid], a2 = S.p[k + 2][tid], a3 = S.p[k + 3][tid]; acc += a0; acc += a1; acc += a2; acc += a3; }
-				for (; k < nt; k++) acc += S.p[k][tid];
-			}
-			else if (tid == D)
-			{
-				uint32_t k = 0;
-				for (; k + 4 <= nt; k += 4) { const float a0 = S.t[k], a1 = S.t[k + 1], a2 = S.t[k + 2], a3 = S.t[k + 3]; acc_d += (double)a0; acc_d += (double)a1; acc_d += (double)a2; acc_d += (double)a3; }
-				for (; k < nt; k++) acc_d += (double)S.t[k];
-			}
-			__syncthreads();
-		}
+				if (tid < D)
+				{
+					uint32_t k = 0;
+					for (; k + 4 <= nt; k += 4) { const float a0 = T.p[k][tid], a1 = T.p[k + 1][tid], a2 = T.p[k + 2][tid], a3 = T.p[k + 3][tid]; acc += a0; acc += a1; acc += a2; acc += a3; }
+					for (; k < nt; k++) acc += T.p[k][tid];
+				}
+				else if (tid == D)
+				{
+					uint32_t k = 0;
+					for (; k + 4 <= nt; k += 4) { const float a0 = T.t[k], a1 = T.t[k + 1], a2 = T.t[k + 2], a3 = T.t[k + 3]; acc_d += (double)a0; acc_d += (double)a1; acc_d += (double)a2; acc_d += (double)a3; }
+					for (; k < nt; k++) acc_d += (double)T.t[k];
+				}
+			});
 		if (tid < D) s_sum[tid] = acc; else if (tid == D) s_tt = acc_d;
 		block_sum<1, NT>([&](int) -> double { return wsum; }, s_part, s_out);
 		if (!tid)
@@ -315,14 +346,16 @@ namespace
 		for (int i = 0; i < D; i++) axis_out[i] = axis[i];
 	}
 
-	template<int D, int NT> __global__ void __launch_bounds__(NT) k_tsvq_split(const float* __restrict__ vecs, const float* __restrict__ wf, const unsigned long long* __restrict__ w64,
+	template<int D, int TS, bool PIPE> __global__ void __launch_bounds__(PIPE ? 2 * TS : TS) k_tsvq_split(const float* __restrict__ vecs, const float* __restrict__ wf, const unsigned long long* __restrict__ w64,
 		uint32_t* members, uint32_t* tmp, uint8_t* side, node_rec<D>* nodes, const uint32_t* __restrict__ frontier, uint32_t child_base, split_out* out)
 	{
+		constexpr int NT = PIPE ? 2 * TS : TS;
 		constexpr int NE = D * (D + 1) / 2; // upper-triangle entries of the covariance matrix, one thread each
-		static_assert(NT >= NE && NT >= 2 * D + 2, "one thread per accumulator");
+		static_assert(TS >= NE && TS >= 2 * D + 2, "one thread per accumulator");
+		typedef tile_smem<D, TS> tile_t;
 		__shared__ double s_part[(NT / 32) * 3];
 		__shared__ double s_out[3];
-		__shared__ tile_smem<D, NT> S;
+		__shared__ tile_t S[PIPE ? 2 : 1];
 		__shared__ float s_origin[D], s_axis[D], s_l[D], s_r[D], s_cov[D * D], s_sum[2 * D];
 		__shared__ double s_tt[2];
 		__shared__ uint32_t s_warp[NT / 32];
@@ -348,33 +381,28 @@ namespace
 				int ex = 0, ey = 0;
 				if (tid < NE) { int k = (int)tid; while (k >= D - ex) { k -= D - ex; ex++; } ey = ex + k; }
 				float acc = 0.0f;
-				for (uint32_t base = 0; base < count; base += NT)
-				{
-					const uint32_t i = base + tid;
-					if (i < count)
+				run_pass<PIPE, TS>(count, S,
+					[&](uint32_t i, tile_t& T, uint32_t slot)
 					{
 						const uint32_t m = mem[i];
 						float v[D];
 						load_vec<D>(vecs, m, v);
 #pragma unroll
-						for (int c = 0; c < D; c++) S.p[tid][c] = v[c] - s_origin[c];
-						S.t[tid] = wf[m];
-					}
-					__syncthreads();
-					const uint32_t nt = (count - base < (uint32_t)NT) ? count - base : (uint32_t)NT;
-					if (tid < NE)
+						for (int c = 0; c < D; c++) T.p[slot][c] = v[c] - s_origin[c];
+						T.t[slot] = wf[m];
+					},
+					[&](const tile_t& T, uint32_t nt)
 					{
+						if (tid >= NE) return;
 						uint32_t k = 0;
 						for (; k + 4 <= nt; k += 4)
 						{
-							const float q0 = S.p[k][ex] * (S.t[k] * S.p[k][ey]), q1 = S.p[k + 1][ex] * (S.t[k + 1] * S.p[k + 1][ey]);
-							const float q2 = S.p[k + 2][ex] * (S.t[k + 2] * S.p[k + 2][ey]), q3 = S.p[k + 3][ex] * (S.t[k + 3] * S.p[k + 3][ey]);
+							const float q0 = T.p[k][ex] * (T.t[k] * T.p[k][ey]), q1 = T.p[k + 1][ex] * (T.t[k + 1] * T.p[k + 1][ey]);
+							const float q2 = T.p[k + 2][ex] * (T.t[k + 2] * T.p[k + 2][ey]), q3 = T.p[k + 3][ex] * (T.t[k + 3] * T.p[k + 3][ey]);
 							acc = acc + q0; acc = acc + q1; acc = acc + q2; acc = acc + q3;
 						}
-						for (; k < nt; k++) acc = acc + S.p[k][ex] * (S.t[k] * S.p[k][ey]);
-					}
-					__syncthreads();
-				}
+						for (; k < nt; k++) acc = acc + T.p[k][ex] * (T.t[k] * T.p[k][ey]);
+					});
 				if (tid < NE) s_cov[ex * D + ey] = acc;
 			}
 			__syncthreads();
@@ -386,10 +414,8 @@ namespace
 				double lw = 0, rw = 0;
 				const uint32_t half = count / 2;
 				float acc = 0.0f;
-				for (uint32_t base = 0; base < count; base += NT)
-				{
-					const uint32_t i = base + tid;
-					if (i < count)
+				run_pass<PIPE, TS>(count, S,
+					[&](uint32_t i, tile_t& T, uint32_t slot)
 					{
 						const uint32_t m = mem[i];
 						float v[D], dv[D];
@@ -398,16 +424,12 @@ namespace
 #pragma unroll
 						for (int c = 0; c < D; c++) dv[c] = v[c] - s_origin[c];
 						const bool right = mode ? (i >= half) : (dot_f<D>(dv, s_axis) >= 0.0f);
-						S.side[tid] = right ? 1 : 0;
+						T.side[slot] = right ? 1 : 0;
 #pragma unroll
-						for (int c = 0; c < D; c++) S.p[tid][c] = v[c] * w;
+						for (int c = 0; c < D; c++) T.p[slot][c] = v[c] * w;
 						if (right) rw += (double)w; else lw += (double)w; // double sums of float-valued integers: exact in any order
-					}
-					__syncthreads();
-					const uint32_t nt = (count - base < (uint32_t)NT) ? count - base : (uint32_t)NT;
-					if (tid < 2 * D) acc = tile_sum_side<D, NT>(S, nt, tid % D, tid / D, acc);
-					__syncthreads();
-				}
+					},
+					[&](const tile_t& T, uint32_t nt) { if (tid < 2 * D) acc = tile_sum_side<D, TS>(T, nt, tid % D, tid / D, acc); });
 				if (tid < 2 * D) s_sum[tid] = acc;
 				block_sum<2, NT>([&](int k) -> double { return k ? rw : lw; }, s_part, s_out);
 				const double l_weight = s_out[0], r_weight = s_out[1];
@@ -431,10 +453,8 @@ namespace
 				double lw = 0, rw = 0, lc = 0;
 				float acc = 0.0f;
 				double acc_d = 0.0;
-				for (uint32_t base = 0; base < count; base += NT)
-				{
-					const uint32_t i = base + tid;
-					if (i < count)
+				run_pass<PIPE, TS>(count, S,
+					[&](uint32_t i, tile_t& T, uint32_t slot)
 					{
 						const uint32_t m = mem[i];
 						float v[D];
@@ -450,18 +470,17 @@ namespace
 						else right = (i == 0); // members are unique vectors, so only the first one equals "firstVec" (enc.h:2037-2061)
 						const float w = wf[m];
 #pragma unroll
-						for (int c = 0; c < D; c++) S.p[tid][c] = v[c] * w; // v * (float)weight
-						S.t[tid] = (float)w64[m] * dot_f<D>(v, v);            // weight * v.dot(v)
-						S.side[tid] = right ? 1 : 0;
+						for (int c = 0; c < D; c++) T.p[slot][c] = v[c] * w;  // v * (float)weight
+						T.t[slot] = (float)w64[m] * dot_f<D>(v, v);             // weight * v.dot(v)
+						T.side[slot] = right ? 1 : 0;
 						sd[i] = right ? 1 : 0;
 						if (right) rw += (double)w64[m]; else { lw += (double)w64[m]; lc += 1.0; }
-					}
-					__syncthreads();
-					const uint32_t nt = (count - base < (uint32_t)NT) ? count - base : (uint32_t)NT;
-					if (tid < 2 * D) acc = tile_sum_side<D, NT>(S, nt, tid % D, tid / D, acc);
-					else if (tid < 2 * D + 2) acc_d = tile_sum_side_t<D, NT>(S, nt, tid - 2 * D, acc_d);
-					__syncthreads();
-				}
+					},
+					[&](const tile_t& T, uint32_t nt)
+					{
+						if (tid < 2 * D) acc = tile_sum_side<D, TS>(T, nt, tid % D, tid / D, acc);
+						else if (tid < 2 * D + 2) acc_d = tile_sum_side_t<D, TS>(T, nt, tid - 2 * D, acc_d);
+					});
 				if (tid < 2 * D) s_sum[tid] = acc; else if (tid < 2 * D + 2) s_tt[tid - 2 * D] = acc_d;
 				block_sum<3, NT>([&](int k) -> double { return k == 0 ? lw : (k == 1 ? rw : lc); }, s_part, s_out);
 				l_weight = (unsigned long long)s_out[0]; r_weight = (unsigned long long)s_out[1];
@@ -664,7 +683,7 @@ namespace
 			if (!st->frontier.reserve((size_t)n * 4, ctx->stream) || !st->results.reserve((size_t)n * sizeof(root_out), ctx->stream)) { ctx->fail("b200_tsvq_generate: out of device memory"); return false; }
 			if (cudaMemcpyAsync(st->nodes.as<node_rec<D>>() + base, recs.data(), (size_t)n * sizeof(node_rec<D>), cudaMemcpyHostToDevice, ctx->stream) != cudaSuccess) return false;
 			if (cudaMemcpyAsync(st->frontier.p, rid.data(), (size_t)n * 4, cudaMemcpyHostToDevice, ctx->stream) != cudaSuccess) return false;
-			k_tsvq_root<D, 256><<<n, 256, 0, ctx->stream>>>(st->uvec.as<float>(), st->uwf.as<float>(), st->uw64.as<unsigned long long>(), st->members.as<uint32_t>(),
+			k_tsvq_root<D, 256, true><<<n, 512, 0, ctx->stream>>>(st->uvec.as<float>(), st->uwf.as<float>(), st->uw64.as<unsigned long long>(), st->members.as<uint32_t>(),
 				st->nodes.as<node_rec<D>>(), st->frontier.as<uint32_t>(), st->results.as<root_out>());
 			ctx->launches++; __atomic_add_fetch(&g_b200_total_launches, 1, __ATOMIC_RELAXED);
 			std::vector<root_out> ro(n);
@@ -689,16 +708,17 @@ namespace
 			if (cudaMemcpyAsync(st->frontier.p, order.data(), (size_t)n * 4, cudaMemcpyHostToDevice, ctx->stream) != cudaSuccess) return false;
 			const float* vecs = st->uvec.as<float>(); const float* wf = st->uwf.as<float>(); const unsigned long long* w64 = st->uw64.as<unsigned long long>();
 			uint32_t* members = st->members.as<uint32_t>(); uint32_t* tmp = st->tmp_members.as<uint32_t>(); uint8_t* side = st->side.as<uint8_t>();
-			constexpr int NT_SMALL = (D == 6) ? 64 : 160; // >= D (D + 1) / 2 accumulator threads
 			node_rec<D>* nodes = st->nodes.as<node_rec<D>>();
+			constexpr int NT_SMALL = (D == 6) ? 64 : 160; // >= D (D + 1) / 2 accumulator threads
 			if (n_big)
 			{
-				k_tsvq_split<D, 256><<<n_big, 256, 0, ctx->stream>>>(vecs, wf, w64, members, tmp, side, nodes, st->frontier.as<uint32_t>(), child_base, st->results.as<split_out>());
+				// many members: 256-member tiles, 256 accumulator-side threads + 256 loader threads (pipelined passes)
+				k_tsvq_split<D, 256, true><<<n_big, 512, 0, ctx->stream>>>(vecs, wf, w64, members, tmp, side, nodes, st->frontier.as<uint32_t>(), child_base, st->results.as<split_out>());
 				ctx->launches++; __atomic_add_fetch(&g_b200_total_launches, 1, __ATOMIC_RELAXED);
 			}
 			if (n > n_big)
 			{
-				k_tsvq_split<D, NT_SMALL><<<n - n_big, NT_SMALL, 0, ctx->stream>>>(vecs, wf, w64, members, tmp, side, nodes, st->frontier.as<uint32_t>() + n_big, child_base + 2 * n_big, st->results.as<split_out>() + n_big);
+				k_tsvq_split<D, NT_SMALL, false><<<n - n_big, NT_SMALL, 0, ctx->stream>>>(vecs, wf, w64, members, tmp, side, nodes, st->frontier.as<uint32_t>() + n_big, child_base + 2 * n_big, st->results.as<split_out>() + n_big);
 				ctx->launches++; __atomic_add_fetch(&g_b200_total_launches, 1, __ATOMIC_RELAXED);
 			}
 			std::vector<split_out> so(n);

@@ -293,9 +293,10 @@ extern "C" int b200_uastc_encode_blocks(b200_context* ctx, const void* pBlocks, 
 	if (!ctx->reserve(ctx->d_out, ctx->out_cap, (size_t)num_blocks * 16)) return 0;
 
 	const uint32_t chunk = uastc_chunk_blocks(flags);
+	// Pieces stay large: every piece is five launches with their own tail waves (eight pieces of 2^17 blocks cost +6 ms at level 2,
+	// measured), so a 2^20-block image is cut in two unless the level's own chunking (level 4: 2^18) already cuts finer.
 	uint32_t piece = chunk;
-	const uint32_t PIECES = 8;
-	if (num_blocks >= PIECES * 32768u) { piece = (num_blocks + PIECES - 1) / PIECES; piece = (piece + 1023u) & ~1023u; if (piece > chunk) piece = chunk; }
+	if (num_blocks >= (1u << 19) && piece > (1u << 19)) piece = 1u << 19;
 	const uint32_t npieces = (num_blocks + piece - 1) / piece;
 	const bool pipelined = npieces > 1 && npieces <= 32;
 	if (pipelined && !ctx->copy_in)

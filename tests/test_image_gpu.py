@@ -36,6 +36,22 @@ def test_extract_strided_rows(ops, ref):
     assert np.array_equal(ops.extract_source_blocks(view), ref_extract(ref, np.ascontiguousarray(view)))
 
 
+def test_extract_bottom_right_crop_and_flipped_rows(ops, ref):
+    """A sub-rectangle that ends at the last byte of the parent allocation: the last row only has width * 4 valid bytes, so the
+    host-to-device copy must not read pitch * height (that would run x0 * 4 bytes past the allocation). Rows with a negative
+    stride (a vertically flipped view) are copied by the wrapper, not passed through."""
+    big = util.synth(64, 3)
+    view = big[64 - 23:, 64 - 30:]           # bottom-right corner, 23 x 30
+    assert np.array_equal(ops.extract_source_blocks(view), ref_extract(ref, np.ascontiguousarray(view)))
+    flipped = big[::-1, 10:50]
+    assert np.array_equal(ops.extract_source_blocks(flipped), ref_extract(ref, np.ascontiguousarray(flipped)))
+    from basis_universal_b200 import uastc
+    enc = uastc.Encoder(0)
+    want = enc.encode_uastc(ref_extract(ref, np.ascontiguousarray(view)), 1)
+    assert np.array_equal(enc.encode_image(view, 1), want)
+    enc.close()
+
+
 def test_extract_empty(ops):
     assert ops.extract_source_blocks(np.zeros((0, 0, 4), np.uint8)).shape == (0, 64)
 
