@@ -293,12 +293,14 @@ extern "C" int b200_uastc_encode_blocks(b200_context* ctx, const void* pBlocks, 
 	if (!ctx->reserve(ctx->d_out, ctx->out_cap, (size_t)num_blocks * 16)) return 0;
 
 	const uint32_t chunk = uastc_chunk_blocks(flags);
-	// Pieces stay large: every piece is five launches with their own tail waves (eight pieces of 2^17 blocks cost +6 ms at level 2,
-	// measured), so a 2^20-block image is cut in two unless the level's own chunking (level 4: 2^18) already cuts finer.
+	// Only where the copies are comparable to the kernels (levels 0 and 1: 4 and 14 ms of kernels per 2^20 blocks against ~2 ms of
+	// PCIe): every piece is five launches with their own tail waves, and at level 2 (32 ms of kernels) two pieces gave 34.1 ms
+	// against 33.9 ms unpipelined and eight pieces 39.7 ms (measured), so levels >= 2 keep the single copy / kernels / copy sequence.
 	uint32_t piece = chunk;
-	if (num_blocks >= (1u << 19) && piece > (1u << 19)) piece = 1u << 19;
+	const int level_ = clampi((int)(flags & 7), 0, 4);
+	if (level_ <= 1 && num_blocks >= (1u << 19)) piece = 1u << 18;
 	const uint32_t npieces = (num_blocks + piece - 1) / piece;
-	const bool pipelined = npieces > 1 && npieces <= 32;
+	const bool pipelined = level_ <= 1 && npieces > 1 && npieces <= 32;
 	if (pipelined && !ctx->copy_in)
 	{
 		if (cudaStreamCreateWithFlags(&ctx->copy_in, cudaStreamNonBlocking) != cudaSuccess || cudaStreamCreateWithFlags(&ctx->copy_out, cudaStreamNonBlocking) != cudaSuccess)

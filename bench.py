@@ -615,7 +615,8 @@ def run_etc1s(args, rank, local_rank, world, cfg):
                         "backend_ms_per_step": 1e3 * be / args.steps},
                 "gpu_launches": int(launches), "kernel_ms_per_step": kernel_ms / args.steps,
                 "stage_kernels_per_step": {k: {"ms": v["kernel_ms"] / args.steps, "launches": v["launches"] // args.steps} for k, v in fam.items() if v["launches"]},
-                "roofline": {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": ncu_traffic(dom), "peak_source": peak_kind,
+                "roofline": {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                             "traffic": ncu_traffic({"etc1s_find_selector_clusters": "k_etc1s_fosc"}.get(dom, "k_" + dom)), "peak_source": peak_kind,
                              "note": "dominant per-block kernel family of the frontend; algorithmic 64 B per block per pass (SURVEY 8d: 24 B/texel over the six mandatory passes); "
                                      "average launch duration from CUDA events inside the library"},
                 "cpu_baseline": {"value": cpu_tx / 1e6 / cpu_t, "unit": "Mtexel/s", "cores": cores["threads_used"], "kind": "reference", "sample": cpu_desc, "host": cores}}
