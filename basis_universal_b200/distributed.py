@@ -1,6 +1,9 @@
-"""Multi-GPU plumbing for the ETC1S path: per-block stages shard by block rows with no collective; the
-codebook stage needs one exchange -- a SUM all-reduce of the 2^18-bin endpoint-key histogram -- after which every rank holds
-the same global training set and can run the (deterministic) clusterer replicated. UASTC needs no collective at all."""
+"""torch.distributed helpers for hosts that shard the ETC1S training sets themselves: a SUM all-reduce of the
+2^18-bin endpoint-key histogram and an all-gatherv of the selector training pairs give every rank the global training set, after
+which the (deterministic) clusterer runs replicated. The drop-in path does not need them -- there the library's own communicator
+(b200_comm_*, csrc/b200_dist.cu) merges each stage's output -- and UASTC needs no collective at all.
+Contract of the *_device entry points these helpers call: they run on the context's own (non-blocking) stream, so the caller
+synchronises its stream before the call (torch.cuda.synchronize below) and the call returns only after its own stream is idle."""
 import numpy as np
 
 from . import etc1s, sharding
@@ -21,12 +24,16 @@ def global_endpoint_training_set(ctx, blocks_x, blocks_y, all_blocks, perceptual
     import torch
     first, last = sharding.block_range(blocks_x, blocks_y, rank, world_size)
     local = np.ascontiguousarray(all_blocks[first:last])
-    ctx.set_pixel_blocks(local)
-    etc_blocks = ctx.encode_etc1s_blocks(perceptual, total_perms)
-    d_blocks = torch.from_numpy(etc_blocks).cuda()
-    d_hist = torch.zeros(1 << 18, dtype=torch.int32, device="cuda")
-    torch.cuda.synchronize()
-    ctx.endpoint_histogram_device(d_blocks.data_ptr(), etc_blocks.shape[0], d_hist.data_ptr())
+    dev = torch.device("cuda", ctx.device)                  # the context's device, not torch's current one
+    d_hist = torch.zeros(1 << 18, dtype=torch.int32, device=dev)
+    if local.shape[0]:
+        ctx.set_pixel_blocks(local)
+        etc_blocks = ctx.encode_etc1s_blocks(perceptual, total_perms)
+        d_blocks = torch.from_numpy(etc_blocks).to(dev)
+        torch.cuda.synchronize(dev)
+        ctx.endpoint_histogram_device(d_blocks.data_ptr(), etc_blocks.shape[0], d_hist.data_ptr())
+    else:
+        etc_blocks = np.zeros((0, 8), np.uint8)              # more ranks than block rows: this rank contributes a zero histogram
     allreduce_endpoint_histogram(d_hist, group)
     hist = d_hist.cpu().numpy().astype(np.uint32)
     return etc_blocks, etc1s.training_vectors_from_histogram(hist)

@@ -24,6 +24,7 @@ class Etc1sContext:
 
     def __init__(self, device=0):
         self._lib = lib()
+        self.device = int(device)
         self._ctx = self._lib.b200_create_context(int(device))
         if not self._ctx:
             raise B200Error("b200_create_context failed: " + self._lib.b200_last_error(None).decode())

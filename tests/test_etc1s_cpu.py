@@ -95,3 +95,26 @@ def test_cpu_flavour_matches_reference_cpu_optimizer(ref, emu, blocks, perceptua
     got = np.zeros_like(want)
     emu.lib.emu_etc1s_encode_blocks_flavour(_ptr(blocks), blocks.shape[0], _ptr(got), perceptual, perms, 1)
     assert np.array_equal(got, want)
+
+
+def test_training_vectors_from_colliding_keys_are_merged():
+    """Distinct 18-bit keys can give the same vec6F: with intensity table 7 (+-183) every channel value 9..22 (5 bits, i.e. 74..181 at
+    8 bits) clamps to low 0 / high 255, so 14^3 keys collapse to (0,0,0,1,1,1). The clusterer's std::map merges them
+    (enc.h:2228-2260); merge_training_vectors is that merge (lexicographic order, summed weights)."""
+    import numpy as np
+    from basis_universal_b200 import etc1s
+    hist = np.zeros(1 << 18, np.uint32)
+    n = 0
+    for r5 in (9, 15, 22):
+        for g5 in (9, 22):
+            for b5 in (10, 21):
+                hist[(r5 << 13) | (g5 << 8) | (b5 << 3) | 7] = 2 * (n + 1)
+                n += 1
+    hist[(3 << 13) | (3 << 8) | (3 << 3) | 0] = 4     # one ordinary key
+    keys, vecs, weights = etc1s.training_vectors_from_histogram(hist)
+    assert len(keys) == n + 1
+    u, w = etc1s.merge_training_vectors(vecs, weights)
+    assert u.shape[0] == 2
+    assert np.array_equal(u[0], np.array([0, 0, 0, 1, 1, 1], np.float32)) or np.array_equal(u[1], np.array([0, 0, 0, 1, 1, 1], np.float32))
+    assert int(w.sum()) == int(hist.sum()) and sorted(int(x) for x in w) == sorted([4, int(hist.sum()) - 4])
+    assert np.all(np.lexsort(u.T[::-1]) == np.arange(u.shape[0]))   # lexicographic order, the std::map's
