@@ -62,9 +62,12 @@ def test_rdo_batch_equals_per_slice_reference(enc, ref):
     assert np.array_equal(got, want)
 
 
-def test_rdo_4096_four_chains_device_resident(enc, ref):
+def test_rdo_4096_four_chains_device_resident(enc):
     """Full-size slice (1 048 576 blocks, 4 chains of 262 144): encode and RDO back to back in HBM through the _device entry
-    points, bit-exact with the reference's 4-thread uastc_rdo on the same encoded blocks."""
+    points. Pinned against the compiled reference's own run over the whole image (oracle/_ref on the CPU: encode_uastc with
+    flags 2|512 -> md5 f2d51fcf..., then uastc_rdo(lambda 1.0, total_jobs 4) -> md5 df47a1bc..., 12 blocks modified; 14 s + 45 s
+    on 8 cores), so the GPU test does not have to repeat the 3-minute CPU pass."""
+    import hashlib
     import torch
     src = util.image_to_blocks(util.synth(4096, 1234))
     flags = 2 | 512
@@ -74,9 +77,25 @@ def test_rdo_4096_four_chains_device_resident(enc, ref):
     torch.cuda.synchronize()
     enc.encode_uastc_device(d_src.data_ptr(), n, d_out.data_ptr(), flags)
     blocks = d_out.cpu().numpy()
+    assert hashlib.md5(blocks.tobytes()).hexdigest() == "f2d51fcf380bb2243d0143ae3c077fed"
     enc.uastc_rdo_batch_device(d_out.data_ptr(), d_src.data_ptr(), [n], uastc.uastc_rdo_params(lambda_=1.0), flags, 4)
     ms = enc.last_kernel_ms
     got = d_out.cpu().numpy()
-    want = util.ref_rdo(ref, blocks, src, 1.0, flags, 4)
     print("RDO 4096^2, 4 chains: %.1f ms on the GPU, %d blocks modified" % (ms, int((got != blocks).any(1).sum())))
+    assert int((got != blocks).any(1).sum()) == 12
+    assert hashlib.md5(got.tobytes()).hexdigest() == "df47a1bcfab09916169b2b2d8f8ee479"
+
+
+def test_rdo_2048_natural_content_four_chains(enc, ref):
+    """A slice where RDO actually rewrites blocks (kodim03 tiled to 2048 x 1024: 131 072 blocks, 4 chains), against the reference."""
+    import os
+    g = np.load(os.path.join(util.GOLDEN, "kodim03_uastc_l0.npz"))
+    img = np.ascontiguousarray(np.tile(g["image"], (2, 3, 1))[:1024, :2048])
+    src = util.image_to_blocks(img)
+    flags = 2 | 512
+    blocks = enc.encode_uastc(src, flags)
+    want = util.ref_rdo(ref, blocks, src, 1.0, flags, 4)
+    got = enc.uastc_rdo(blocks, src, uastc.uastc_rdo_params(lambda_=1.0), flags, 4)
+    print("RDO 2048x1024 natural: %.1f ms on the GPU, %d of %d blocks modified" % (enc.last_kernel_ms, int((got != blocks).any(1).sum()), len(blocks)))
+    assert (want != blocks).any(1).sum() > len(blocks) // 20
     assert np.array_equal(got, want)
