@@ -162,3 +162,32 @@ def test_bu_c_api_on_top_of_the_dropin(dropin):
     cpu = compress(dropin, img, 128 | cFlagThreaded)
     (c_rgb, c_y) = psnr(dropin, cpu, img)
     assert abs(g_y - c_y) <= 0.02 and abs(g_rgb - c_rgb) <= 0.02
+
+
+def _run_tool(args, cwd):
+    import subprocess
+    tool = os.path.join(util.ROOT, "integration", "_build", "basisu")
+    if not os.path.exists(tool):
+        pytest.skip("integration/_build/basisu did not travel (built by integration/Makefile where /root/reference exists)")
+    r = subprocess.run([tool] + args, cwd=cwd, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    return r.stdout
+
+
+def test_basisu_tool_cli_on_the_dropin(tmp_path):
+    """BASELINE config 1 with the reference's own CLI, unmodified (basisu_tool.cpp linked against the drop-in library):
+    `basisu -uastc -uastc_level 0 -opencl kodim03.png` -> 393347 B, md5 6d98eb72..., blocks encoded by the B200; and the ETC1S default
+    (`basisu -opencl kodim03.png`, -q 128, comp_level 1) gives the same file as the CPU run of the same binary."""
+    png = os.path.join(util.ROOT, "oracle", "_ref", "test_files", "kodim03.png")
+    if not os.path.exists(png):
+        pytest.skip("oracle/_ref/test_files/kodim03.png did not travel")
+    out = _run_tool(["-uastc", "-uastc_level", "0", "-basis", "-opencl", "-output_file", str(tmp_path / "u.basis"), png], tmp_path)
+    assert "OpenCL: 1" in out, "the tool did not see the GPU seam"
+    data = open(tmp_path / "u.basis", "rb").read()
+    assert len(data) == 393347 and hashlib.md5(data).hexdigest() == "6d98eb72a9a3112ff55344132a28b042"
+    out = _run_tool(["-basis", "-opencl", "-output_file", str(tmp_path / "e_gpu.basis"), png], tmp_path)
+    assert "OpenCL: 1" in out
+    _run_tool(["-basis", "-output_file", str(tmp_path / "e_cpu.basis"), png], tmp_path)
+    gpu, cpu = open(tmp_path / "e_gpu.basis", "rb").read(), open(tmp_path / "e_cpu.basis", "rb").read()
+    print(f"basisu CLI ETC1S q128 kodim03: CPU {len(cpu)} B, B200 {len(gpu)} B")
+    assert gpu == cpu

@@ -168,3 +168,17 @@ def test_python_wrappers_raise_without_a_gpu():
     for ctor in (uastc.Encoder, etc1s.Etc1sContext, image.ImageOps):
         with pytest.raises(B200Error):
             ctor(0)
+
+
+def test_reference_cli_on_the_dropin_library_cpu_path(tmp_path):
+    """integration/_build/basisu = the reference's basisu_tool.cpp, unmodified, linked against the drop-in library (patched
+    compressor + GPU seam adapter). Without -opencl (and without a GPU) it must still be the reference encoder: config 1's KAT."""
+    import subprocess
+    tool = os.path.join(util.ROOT, "integration", "_build", "basisu")
+    png = os.path.join(util.ROOT, "oracle", "_ref", "test_files", "kodim03.png")
+    if not (os.path.exists(tool) and os.path.exists(png)):
+        pytest.skip("drop-in CLI or test image not built here")
+    r = subprocess.run([tool, "-uastc", "-uastc_level", "0", "-basis", "-output_file", str(tmp_path / "k.basis"), png], cwd=tmp_path, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-1000:] + r.stderr[-1000:]
+    data = open(tmp_path / "k.basis", "rb").read()
+    assert len(data) == 393347 and hashlib.md5(data).hexdigest() == "6d98eb72a9a3112ff55344132a28b042"
