@@ -64,12 +64,16 @@ __device__ __forceinline__ uint64_t warp_sum_u64(uint64_t v)
 // place from the resident source-block array, every texel with weight 1 (b200_etc1s_encode_endpoint_clusters).
 struct px_list_src
 {
+	static constexpr bool forced = false, unit_weights = false;
+	__device__ __forceinline__ uint32_t selector(uint64_t) const { return 0; }
 	const uint32_t* __restrict__ px; const uint32_t* __restrict__ wts; uint64_t n;
 	__device__ __forceinline__ uint32_t pixel(uint64_t i) const { return px[i]; }
 	__device__ __forceinline__ uint32_t weight(uint64_t i) const { return wts[i]; }
 };
 struct px_blocks_src
 {
+	static constexpr bool forced = false, unit_weights = true;
+	__device__ __forceinline__ uint32_t selector(uint64_t) const { return 0; }
 	const uint32_t* __restrict__ blocks; const uint32_t* __restrict__ bidx; uint64_t n; // n = 16 * number of blocks
 	__device__ __forceinline__ uint32_t pixel(uint64_t i) const { return __ldg(blocks + (size_t)__ldg(bidx + (i >> 4)) * 16 + (i & 15)); }
 	__device__ __forceinline__ uint32_t weight(uint64_t) const { return 1u; }
@@ -143,83 +147,16 @@ struct cta_team
 	}
 };
 
-// Weighted error of base colour (r5,g5,b5) against the cluster's texels for every non-pruned intensity table; returns the
-// best (first strictly smaller) table and its error. Uniform across the team.
-template<typename Src, typename Team> __device__ void cluster_evaluate(const bu_tables* T, bool perceptual, const Src& src, Team& team,
-	uint32_t spread, uint32_t r5, uint32_t g5, uint32_t b5, etc1s_solution& best, bool prune)
+// The same with an imposed selector per texel (etc1_optimizer::params::m_pForce_selectors, etc.cpp:1137, 1198-1202): `sels[k]` holds
+// the 16 selectors of the k-th listed block, texel (x, y) at bits 2 * (x + 4 * y).
+struct px_blocks_forced_src
 {
-	const uint64_t n = src.n;
-	uint64_t trial_err = (uint64_t)INT64_MAX;
-	uint32_t trial_inten = 0;
-	bool valid = false;
-	for (uint32_t inten = 0; inten < 8; inten++)
-	{
-		if (prune && !T->eval_dist[inten * 256 + spread]) continue;
-		uint32_t colors[4];
-		etc1s_block_colors(T, r5, g5, b5, inten, colors);
-		uint64_t total = 0;
-		for (uint64_t i = team.rank; i < n; i += Team::size)
-		{
-			const uint32_t p = src.pixel(i);
-			uint32_t be = etc_color_distance(perceptual, p, colors[0]);
-			be = min(be, etc_color_distance(perceptual, p, colors[1]));
-			be = min(be, etc_color_distance(perceptual, p, colors[2]));
-			be = min(be, etc_color_distance(perceptual, p, colors[3]));
-			total += (uint64_t)be * (uint64_t)src.weight(i);
-		}
-		total = team.sum(total);
-		if (total < trial_err) { trial_err = total; trial_inten = inten; valid = true; }
-	}
-	if (trial_err < best.err) { best.err = trial_err; best.r5 = r5; best.g5 = g5; best.b5 = b5; best.inten = trial_inten; best.valid = valid ? 1u : 0u; }
-}
-
-// One team optimises one cluster (etc1_optimizer over the cluster's texels); returns the packed base colour + intensity table.
-template<typename Src, typename Team> __device__ uint64_t cluster_optimize(const bu_tables* T, bool perceptual, const Src& src, Team& team, uint32_t total_perms, int flavour)
-{
-	const uint64_t n = src.n;
-	uint32_t mn[3] = { 255, 255, 255 }, mx[3] = { 0, 0, 0 };
-	uint64_t sum[3] = { 0, 0, 0 }, tw = 0;
-	for (uint64_t i = team.rank; i < n; i += Team::size)
-	{
-		const uint32_t p = src.pixel(i);
-		const uint64_t w = src.weight(i);
-		for (uint32_t c = 0; c < 3; c++)
-		{
-			const uint32_t v = px_c(p, c);
-			mn[c] = min(mn[c], v); mx[c] = max(mx[c], v); sum[c] += w * v;
-		}
-		tw += w;
-	}
-	for (int c = 0; c < 3; c++)
-	{
-		team.minmax(mn[c], mx[c]);
-		sum[c] = team.sum(sum[c]);
-	}
-	tw = team.sum(tw);
-
-	float avg[3];
-	for (int c = 0; c < 3; c++) avg[c] = (float)sum[c] / (float)tw;
-	const uint32_t spread = (uint32_t)max(max((int)mx[0] - (int)mn[0], (int)mx[1] - (int)mn[1]), (int)mx[2] - (int)mn[2]);
-	if (total_perms <= 4) flavour = ETC1S_FLAVOUR_OCL;
-	const bool cpu = flavour == ETC1S_FLAVOUR_CPU;
-	const bool prune = !cpu || total_perms <= 16;
-	const uint32_t r0 = etc1s_round5(avg[0], flavour), g0 = etc1s_round5(avg[1], flavour), b0 = etc1s_round5(avg[2], flavour);
-
-	if (cpu) team.bloom_test_and_set(r0, g0, b0);
-	etc1s_solution best;
-	best.err = UINT64_MAX; best.r5 = best.g5 = best.b5 = best.inten = 0; best.lsb_plane = best.msb_plane = 0; best.valid = 0;
-	cluster_evaluate(T, perceptual, src, team, spread, r0, g0, b0, best, prune);
-	if (best.err != 0)
-		for (uint32_t perm = 0; perm < total_perms; perm++)
-		{
-			uint32_t r1, g1, b1;
-			if (!etc1s_cluster_fit_step(T, best, avg, perm, r1, g1, b1, flavour)) continue;
-			if (cpu && !team.bloom_test_and_set(r1, g1, b1)) continue;
-			cluster_evaluate(T, perceptual, src, team, spread, r1, g1, b1, best, prune);
-			if (best.err == 0) break;
-		}
-	return etc1s_pack(best.r5, best.g5, best.b5, best.inten, 0, 0); // the kernel defines no selectors for clusters
-}
+	static constexpr bool forced = true, unit_weights = true;
+	const uint32_t* __restrict__ blocks; const uint32_t* __restrict__ bidx; const uint32_t* __restrict__ sels; uint64_t n;
+	__device__ __forceinline__ uint32_t pixel(uint64_t i) const { return __ldg(blocks + (size_t)__ldg(bidx + (i >> 4)) * 16 + (i & 15)); }
+	__device__ __forceinline__ uint32_t weight(uint64_t) const { return 1u; }
+	__device__ __forceinline__ uint32_t selector(uint64_t i) const { return (__ldg(sels + (i >> 4)) >> (2 * (uint32_t)(i & 15))) & 3u; }
+};
 
 __global__ void __launch_bounds__(128) k_etc1s_pixel_clusters(const b200_pixel_cluster* __restrict__ clusters, uint32_t total_clusters,
 	const uint32_t* __restrict__ pixels, const uint32_t* __restrict__ weights, uint64_t* __restrict__ out, int perceptual_i, uint32_t total_perms, int flavour)
@@ -263,6 +200,41 @@ __global__ void __launch_bounds__(ETC1S_CTA_TEAM) k_etc1s_endpoint_clusters_big(
 	cta_team team(&S);
 	const uint64_t r = cluster_optimize(&d_tables, perceptual_i != 0, src, team, total_perms, flavour);
 	if (!threadIdx.x) out[c] = r;
+}
+
+// ---- reoptimize_remapped_endpoints (frontend.cpp:2996-3090): per endpoint cluster, the optimiser with the blocks' selectors imposed,
+// plus the error of the cluster's current endpoint with the same selectors. out3[c] = { packed colour + table, new error, current error }.
+struct reopt_out { uint64_t packed, new_err, cur_err; };
+template<typename Team> __device__ void reoptimize_cluster(const bu_tables* T, bool perceptual, const uint32_t* __restrict__ blocks, const uint32_t* __restrict__ offsets, const uint32_t* __restrict__ bidx,
+	const uint32_t* __restrict__ sels, const uint32_t* __restrict__ cur_c5i, uint32_t c, Team& team, uint32_t total_perms, int flavour, reopt_out* out, bool writer)
+{
+	px_blocks_forced_src src;
+	src.blocks = blocks; src.bidx = bidx + offsets[c]; src.sels = sels + offsets[c]; src.n = (uint64_t)(offsets[c + 1] - offsets[c]) * 16;
+	reopt_out r; r.packed = 0; r.new_err = 0; r.cur_err = 0;
+	if (src.n)
+	{
+		const uint32_t cur = cur_c5i[c];
+		r.cur_err = cluster_forced_error(T, perceptual, src, team, cur & 255, (cur >> 8) & 255, (cur >> 16) & 255, cur >> 24);
+		r.packed = cluster_optimize(T, perceptual, src, team, total_perms, flavour, &r.new_err);
+	}
+	if (writer) out[c] = r;
+}
+__global__ void __launch_bounds__(128) k_etc1s_reoptimize_clusters(const uint32_t* __restrict__ blocks, const uint32_t* __restrict__ offsets, const uint32_t* __restrict__ bidx, const uint32_t* __restrict__ sels,
+	const uint32_t* __restrict__ cur_c5i, const uint32_t* __restrict__ order, uint32_t first, uint32_t total_clusters, reopt_out* __restrict__ out, int perceptual_i, uint32_t total_perms, int flavour, uint32_t rank, uint32_t world)
+{
+	const uint32_t warp = first + ((blockIdx.x * blockDim.x + threadIdx.x) >> 5) * world + rank;
+	if (warp >= total_clusters) return;
+	warp_team team;
+	reoptimize_cluster(&d_tables, perceptual_i != 0, blocks, offsets, bidx, sels, cur_c5i, order[warp], team, total_perms, flavour, out, (threadIdx.x & 31) == 0);
+}
+__global__ void __launch_bounds__(ETC1S_CTA_TEAM) k_etc1s_reoptimize_clusters_big(const uint32_t* __restrict__ blocks, const uint32_t* __restrict__ offsets, const uint32_t* __restrict__ bidx, const uint32_t* __restrict__ sels,
+	const uint32_t* __restrict__ cur_c5i, const uint32_t* __restrict__ order, uint32_t n_big, reopt_out* __restrict__ out, int perceptual_i, uint32_t total_perms, int flavour, uint32_t rank, uint32_t world)
+{
+	__shared__ cta_team_smem S;
+	const uint32_t k = blockIdx.x * world + rank;
+	if (k >= n_big) return;
+	cta_team team(&S);
+	reoptimize_cluster(&d_tables, perceptual_i != 0, blocks, offsets, bidx, sels, cur_c5i, order[k], team, total_perms, flavour, out, threadIdx.x == 0);
 }
 
 // ---- create_optimized_selector_codebook: one warp per selector cluster ---------------------------------------------------------
@@ -648,6 +620,22 @@ extern "C" int b200_etc1s_selector_training(b200_context* ctx, const void* pEtc_
 	return 1;
 }
 
+// Launch order of per-cluster kernels: clusters by size class (floor(log2(size))), largest class first; clusters of >=
+// ETC1S_BIG_CLUSTER_BLOCKS blocks (a power of two, so whole classes) form the prefix that gets one CTA each. malloc'd; caller frees.
+static uint32_t* cluster_launch_order(const uint32_t* offsets, uint32_t total_clusters, uint32_t& n_big)
+{
+	uint32_t* order = static_cast<uint32_t*>(malloc((size_t)total_clusters * 4));
+	if (!order) return nullptr;
+	n_big = 0;
+	uint32_t counts[33] = { 0 }, ofs[33];
+	auto cls = [&](uint32_t c) { const uint32_t sz = offsets[c + 1] - offsets[c]; uint32_t b = 0; while (b < 32 && (1u << b) <= sz) b++; return 32 - b; };
+	for (uint32_t i = 0; i < total_clusters; i++) { counts[cls(i)]++; if (offsets[i + 1] - offsets[i] >= ETC1S_BIG_CLUSTER_BLOCKS) n_big++; }
+	uint32_t acc = 0;
+	for (int b = 0; b < 33; b++) { ofs[b] = acc; acc += counts[b]; }
+	for (uint32_t i = 0; i < total_clusters; i++) order[ofs[cls(i)]++] = i;
+	return order;
+}
+
 extern "C" int b200_etc1s_encode_endpoint_clusters(b200_context* ctx, void* pOutput_blocks, uint32_t total_clusters, const uint32_t* pCluster_offsets,
 	const uint32_t* pCluster_block_indices, int perceptual, uint32_t total_perms)
 {
@@ -658,19 +646,9 @@ extern "C" int b200_etc1s_encode_endpoint_clusters(b200_context* ctx, void* pOut
 	const uint32_t total_indices = pCluster_offsets[total_clusters];
 	for (uint32_t i = 0; i < total_indices; i++)
 		if (pCluster_block_indices[i] >= ctx->etc_total_blocks) { ctx->fail("b200_etc1s_encode_endpoint_clusters: block index out of range"); return 0; }
-	// Launch order: clusters by size class (floor(log2(size))), largest class first; clusters of >= ETC1S_BIG_CLUSTER_BLOCKS blocks
-	// (a power of two, so whole classes) form the prefix that gets one CTA each.
-	uint32_t* order = static_cast<uint32_t*>(malloc((size_t)total_clusters * 4));
-	if (!order) { ctx->fail("b200_etc1s_encode_endpoint_clusters: out of host memory"); return 0; }
 	uint32_t n_big = 0;
-	{
-		uint32_t counts[33] = { 0 }, ofs[33];
-		auto cls = [&](uint32_t c) { const uint32_t sz = pCluster_offsets[c + 1] - pCluster_offsets[c]; uint32_t b = 0; while (b < 32 && (1u << b) <= sz) b++; return 32 - b; };
-		for (uint32_t i = 0; i < total_clusters; i++) { counts[cls(i)]++; if (pCluster_offsets[i + 1] - pCluster_offsets[i] >= ETC1S_BIG_CLUSTER_BLOCKS) n_big++; }
-		uint32_t acc = 0;
-		for (int b = 0; b < 33; b++) { ofs[b] = acc; acc += counts[b]; }
-		for (uint32_t i = 0; i < total_clusters; i++) order[ofs[cls(i)]++] = i;
-	}
+	uint32_t* order = cluster_launch_order(pCluster_offsets, total_clusters, n_big);
+	if (!order) { ctx->fail("b200_etc1s_encode_endpoint_clusters: out of host memory"); return 0; }
 	bool ok = upload(ctx, 1, pCluster_offsets, ((size_t)total_clusters + 1) * 4) && upload(ctx, 2, pCluster_block_indices, (size_t)total_indices * 4) && upload(ctx, 3, order, (size_t)total_clusters * 4);
 	if (ok) ok = ctx->reserve(ctx->d_aux[0], ctx->aux_cap[0], (size_t)total_clusters * 8);
 	if (ok && cudaStreamSynchronize(ctx->stream) != cudaSuccess) ok = false; // `order` is pageable host memory about to be freed
@@ -717,4 +695,62 @@ extern "C" int b200_etc1s_optimize_selector_codebook(b200_context* ctx, const vo
 		static_cast<const uint2*>(ctx->d_aux[1]), static_cast<const uint32_t*>(ctx->d_aux[2]), static_cast<const uint32_t*>(ctx->d_aux[3]), total_clusters,
 		static_cast<uint32_t*>(ctx->d_aux[0]), perceptual, (uint32_t)ctx->rank, world);
 	return finish(ctx, pOutput_selectors, 0, (size_t)total_clusters * 4, B200_STAT_ETC1S_SELECTOR_CODEBOOK);
+}
+
+extern "C" int b200_etc1s_reoptimize_endpoint_clusters(b200_context* ctx, uint32_t total_clusters, const uint32_t* pCluster_offsets, const uint32_t* pCluster_block_indices,
+	const uint32_t* pBlock_selectors, const void* pCluster_color5_inten, void* pOut_color5_inten, uint64_t* pOut_new_err, uint64_t* pOut_cur_err, int perceptual, uint32_t total_perms)
+{
+	ETC_CHECK_BLOCKS(ctx, "b200_etc1s_reoptimize_endpoint_clusters");
+	if (!total_clusters) return 1;
+	if (total_perms > 165) { ctx->fail("b200_etc1s_reoptimize_endpoint_clusters: total_perms > 165"); return 0; }
+	if (!pCluster_offsets || !pCluster_block_indices || !pBlock_selectors || !pCluster_color5_inten || !pOut_color5_inten || !pOut_new_err || !pOut_cur_err)
+	{ ctx->fail("b200_etc1s_reoptimize_endpoint_clusters: null buffer"); return 0; }
+	const uint32_t total_indices = pCluster_offsets[total_clusters];
+	for (uint32_t i = 0; i < total_indices; i++)
+		if (pCluster_block_indices[i] >= ctx->etc_total_blocks) { ctx->fail("b200_etc1s_reoptimize_endpoint_clusters: block index out of range"); return 0; }
+	uint32_t n_big = 0;
+	uint32_t* order = cluster_launch_order(pCluster_offsets, total_clusters, n_big);
+	if (!order) { ctx->fail("b200_etc1s_reoptimize_endpoint_clusters: out of host memory"); return 0; }
+	bool ok = upload(ctx, 1, pCluster_offsets, ((size_t)total_clusters + 1) * 4) && upload(ctx, 2, pCluster_block_indices, (size_t)total_indices * 4) && upload(ctx, 3, order, (size_t)total_clusters * 4) &&
+		upload(ctx, 4, pBlock_selectors, (size_t)total_indices * 4) && upload(ctx, 5, pCluster_color5_inten, (size_t)total_clusters * 4);
+	if (ok) ok = ctx->reserve(ctx->d_aux[0], ctx->aux_cap[0], (size_t)total_clusters * sizeof(reopt_out));
+	if (ok && cudaStreamSynchronize(ctx->stream) != cudaSuccess) ok = false; // `order` is pageable host memory about to be freed
+	free(order);
+	if (!ok) return 0;
+	ctx->launches = 0;
+	if (!shard_prepare_output(ctx, 0, (size_t)total_clusters * sizeof(reopt_out))) return 0;
+	B200_CUDA_OK(ctx, cudaEventRecord(ctx->ev0, ctx->stream));
+	const uint32_t warps_per_cta = 4, world = (uint32_t)(ctx->world > 1 ? ctx->world : 1);
+	const uint32_t* d_blocks = static_cast<const uint32_t*>(ctx->d_etc_blocks);
+	const uint32_t* d_off = static_cast<const uint32_t*>(ctx->d_aux[1]); const uint32_t* d_idx = static_cast<const uint32_t*>(ctx->d_aux[2]);
+	const uint32_t* d_order = static_cast<const uint32_t*>(ctx->d_aux[3]); const uint32_t* d_sels = static_cast<const uint32_t*>(ctx->d_aux[4]);
+	const uint32_t* d_cur = static_cast<const uint32_t*>(ctx->d_aux[5]);
+	reopt_out* d_out = static_cast<reopt_out*>(ctx->d_aux[0]);
+	if (n_big)
+	{
+		k_etc1s_reoptimize_clusters_big<<<(n_big + world - 1) / world, ETC1S_CTA_TEAM, 0, ctx->stream>>>(d_blocks, d_off, d_idx, d_sels, d_cur, d_order, n_big, d_out, perceptual, total_perms, ctx->etc_flavour, (uint32_t)ctx->rank, world);
+		ctx->launches++; __atomic_add_fetch(&g_b200_total_launches, 1, __ATOMIC_RELAXED);
+	}
+	const uint32_t my_clusters = (total_clusters - n_big + world - 1) / world;
+	if (my_clusters)
+	{
+		k_etc1s_reoptimize_clusters<<<(my_clusters + warps_per_cta - 1) / warps_per_cta, warps_per_cta * 32, 0, ctx->stream>>>(d_blocks, d_off, d_idx, d_sels, d_cur, d_order, n_big, total_clusters, d_out,
+			perceptual, total_perms, ctx->etc_flavour, (uint32_t)ctx->rank, world);
+		ctx->launches++; __atomic_add_fetch(&g_b200_total_launches, 1, __ATOMIC_RELAXED);
+	}
+	reopt_out* h = static_cast<reopt_out*>(malloc((size_t)total_clusters * sizeof(reopt_out)));
+	if (!h) { ctx->fail("b200_etc1s_reoptimize_endpoint_clusters: out of host memory"); return 0; }
+	const int fin = finish(ctx, h, 0, (size_t)total_clusters * sizeof(reopt_out), B200_STAT_ETC1S_REOPTIMIZE_CLUSTERS);
+	if (fin)
+	{
+		uint8_t* c5i = static_cast<uint8_t*>(pOut_color5_inten);
+		for (uint32_t c = 0; c < total_clusters; c++)
+		{
+			const uint32_t w = (uint32_t)h[c].packed; // etc_block bytes 0..3: R5<<3, G5<<3, B5<<3, inten0<<5 | ...
+			c5i[c * 4 + 0] = (uint8_t)((w >> 3) & 31); c5i[c * 4 + 1] = (uint8_t)((w >> 11) & 31); c5i[c * 4 + 2] = (uint8_t)((w >> 19) & 31); c5i[c * 4 + 3] = (uint8_t)((w >> 29) & 7);
+			pOut_new_err[c] = h[c].new_err; pOut_cur_err[c] = h[c].cur_err;
+		}
+	}
+	free(h);
+	return fin;
 }

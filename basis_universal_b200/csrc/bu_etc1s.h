@@ -224,4 +224,121 @@ BU_FI uint64_t etc1s_block_error(const bu_tables* T, bool perceptual, const uint
 	return total;
 }
 
+// ---- cluster optimiser (etc1_optimizer over an arbitrary texel set) ---------------------------------------------------------
+// A cluster is optimised by a TEAM whose members stride its texels (b200_etc1s.cu: a warp or a CTA; the host emulation: one
+// thread). Src supplies pixel(i) / weight(i) / selector(i) and the traits `forced` (selectors imposed) and `unit_weights`.
+// Weighted error of base colour (r5,g5,b5) against the cluster's texels for every non-pruned intensity table; returns the
+// best (first strictly smaller) table and its error. Uniform across the team.
+template<typename Src, typename Team> BU_HD inline void cluster_evaluate(const bu_tables* T, bool perceptual, const Src& src, Team& team,
+	uint32_t spread, uint32_t r5, uint32_t g5, uint32_t b5, etc1s_solution& best, bool prune)
+{
+	const uint64_t n = src.n;
+	uint64_t trial_err = (uint64_t)INT64_MAX;
+	uint32_t trial_inten = 0;
+	bool valid = false;
+	for (uint32_t inten = 0; inten < 8; inten++)
+	{
+		if (prune && !T->eval_dist[inten * 256 + spread]) continue;
+		uint32_t colors[4];
+		etc1s_block_colors(T, r5, g5, b5, inten, colors);
+		uint64_t total = 0;
+		for (uint64_t i = team.rank; i < n; i += Team::size)
+		{
+			const uint32_t p = src.pixel(i);
+			uint32_t be;
+			if (Src::forced)
+			{
+				const uint32_t sl = src.selector(i);
+				be = etc_color_distance(perceptual, p, sl == 0 ? colors[0] : (sl == 1 ? colors[1] : (sl == 2 ? colors[2] : colors[3])));
+			}
+			else
+			{
+				be = etc_color_distance(perceptual, p, colors[0]);
+				be = minu(be, etc_color_distance(perceptual, p, colors[1]));
+				be = minu(be, etc_color_distance(perceptual, p, colors[2]));
+				be = minu(be, etc_color_distance(perceptual, p, colors[3]));
+			}
+			total += (uint64_t)be * (uint64_t)src.weight(i);
+		}
+		total = team.sum(total);
+		if (total < trial_err) { trial_err = total; trial_inten = inten; valid = true; }
+	}
+	if (trial_err < best.err) { best.err = trial_err; best.r5 = r5; best.g5 = g5; best.b5 = b5; best.inten = trial_inten; best.valid = valid ? 1u : 0u; }
+}
+
+// One team optimises one cluster (etc1_optimizer over the cluster's texels); returns the packed base colour + intensity table.
+template<typename Src, typename Team> BU_HD inline uint64_t cluster_optimize(const bu_tables* T, bool perceptual, const Src& src, Team& team, uint32_t total_perms, int flavour, uint64_t* pErr = nullptr)
+{
+	const uint64_t n = src.n;
+	uint32_t mn[3] = { 255, 255, 255 }, mx[3] = { 0, 0, 0 };
+	uint64_t sum[3] = { 0, 0, 0 }, tw = 0;
+	for (uint64_t i = team.rank; i < n; i += Team::size)
+	{
+		const uint32_t p = src.pixel(i);
+		const uint64_t w = src.weight(i);
+		for (uint32_t c = 0; c < 3; c++)
+		{
+			const uint32_t v = px_c(p, c);
+			mn[c] = minu(mn[c], v); mx[c] = maxu(mx[c], v); sum[c] += w * v;
+		}
+		tw += w;
+	}
+	for (int c = 0; c < 3; c++)
+	{
+		team.minmax(mn[c], mx[c]);
+		sum[c] = team.sum(sum[c]);
+	}
+	tw = team.sum(tw);
+
+	float avg[3];
+	for (int c = 0; c < 3; c++) avg[c] = (float)sum[c] / (float)tw;
+	if (Src::unit_weights && flavour == ETC1S_FLAVOUR_CPU && (sum[0] > (1ull << 24) || sum[1] > (1ull << 24) || sum[2] > (1ull << 24)))
+	{
+		// etc1_optimizer::init (etc.cpp:1022-1040) adds the texels to a float vector in member order; past 2^24 that sum rounds, so
+		// such a cluster (> 4112 blocks) repeats the serial float additions - every team member redundantly, the loads are broadcasts.
+		float f0 = 0.0f, f1 = 0.0f, f2 = 0.0f;
+		for (uint64_t i = 0; i < n; i++)
+		{
+			const uint32_t p = src.pixel(i);
+			f0 += (float)px_c(p, 0); f1 += (float)px_c(p, 1); f2 += (float)px_c(p, 2);
+		}
+		avg[0] = f0 / (float)n; avg[1] = f1 / (float)n; avg[2] = f2 / (float)n;
+	}
+	const uint32_t spread = maxu(maxu(mx[0] - mn[0], mx[1] - mn[1]), mx[2] - mn[2]);
+	if (total_perms <= 4) flavour = ETC1S_FLAVOUR_OCL;
+	const bool cpu = flavour == ETC1S_FLAVOUR_CPU;
+	const bool prune = !cpu || total_perms <= 16;
+	const uint32_t r0 = etc1s_round5(avg[0], flavour), g0 = etc1s_round5(avg[1], flavour), b0 = etc1s_round5(avg[2], flavour);
+
+	if (cpu) team.bloom_test_and_set(r0, g0, b0);
+	etc1s_solution best;
+	best.err = UINT64_MAX; best.r5 = best.g5 = best.b5 = best.inten = 0; best.lsb_plane = best.msb_plane = 0; best.valid = 0;
+	cluster_evaluate(T, perceptual, src, team, spread, r0, g0, b0, best, prune);
+	if (best.err != 0)
+		for (uint32_t perm = 0; perm < total_perms; perm++)
+		{
+			uint32_t r1, g1, b1;
+			if (!etc1s_cluster_fit_step(T, best, avg, perm, r1, g1, b1, flavour)) continue;
+			if (cpu && !team.bloom_test_and_set(r1, g1, b1)) continue;
+			cluster_evaluate(T, perceptual, src, team, spread, r1, g1, b1, best, prune);
+			if (best.err == 0) break;
+		}
+	if (pErr) *pErr = best.err;
+	return etc1s_pack(best.r5, best.g5, best.b5, best.inten, 0, 0); // the kernel defines no selectors for clusters
+}
+
+// Error of one given (colour, table) with the imposed selectors: the "current error" of reoptimize_remapped_endpoints (frontend.cpp:3033-3046).
+template<typename Src, typename Team> BU_HD inline uint64_t cluster_forced_error(const bu_tables* T, bool perceptual, const Src& src, Team& team, uint32_t r5, uint32_t g5, uint32_t b5, uint32_t inten)
+{
+	uint32_t colors[4];
+	etc1s_block_colors(T, r5, g5, b5, inten, colors);
+	uint64_t total = 0;
+	for (uint64_t i = team.rank; i < src.n; i += Team::size)
+	{
+		const uint32_t sl = src.selector(i);
+		total += etc_color_distance(perceptual, src.pixel(i), sl == 0 ? colors[0] : (sl == 1 ? colors[1] : (sl == 2 ? colors[2] : colors[3])));
+	}
+	return team.sum(total);
+}
+
 } // namespace bu

@@ -182,6 +182,22 @@ def _optimize_selector_codebook(self, etc_blocks, clusters, perceptual):
     return out
 
 
+def _reoptimize_endpoint_clusters(self, clusters, block_selectors, cluster_color5_inten, perceptual, total_perms):
+    """reoptimize_remapped_endpoints' per-cluster loop (frontend.cpp:3008-3090). clusters = list of block-index arrays;
+    block_selectors = one packed selector word per block OF THE SLICE (texel (x, y) at bits 2 * (x + 4 * y)); cluster_color5_inten
+    = (n, 4) uint8 current endpoints. -> (new (n, 4) uint8, new_err (n,) uint64, cur_err (n,) uint64)."""
+    off, idx = _csr(clusters)
+    sels = np.ascontiguousarray(np.asarray(block_selectors, np.uint32)[idx]) if idx.shape[0] else np.zeros(1, np.uint32)
+    cur = np.ascontiguousarray(cluster_color5_inten, np.uint8)
+    assert cur.shape == (len(clusters), 4)
+    out = np.zeros((len(clusters), 4), np.uint8)
+    new_err = np.zeros(len(clusters), np.uint64)
+    cur_err = np.zeros(len(clusters), np.uint64)
+    self._check(self._lib.b200_etc1s_reoptimize_endpoint_clusters(self._ctx, len(clusters), _p(off), _p(idx), _p(sels), _p(cur), _p(out), _p(new_err), _p(cur_err),
+                                                                    int(bool(perceptual)), int(total_perms)), "b200_etc1s_reoptimize_endpoint_clusters")
+    return out, new_err, cur_err
+
+
 def comm_unique_id():
     """128-byte NCCL id (rank 0 calls this, then broadcasts the bytes to the other ranks)."""
     buf = np.zeros(128, np.uint8)
@@ -208,6 +224,7 @@ Etc1sContext.comm_stats = _comm_stats
 Etc1sContext.tsvq_generate = _tsvq_generate
 Etc1sContext.encode_endpoint_clusters = _encode_endpoint_clusters
 Etc1sContext.optimize_selector_codebook = _optimize_selector_codebook
+Etc1sContext.reoptimize_endpoint_clusters = _reoptimize_endpoint_clusters
 
 
 def merge_selector_training(keys, weights):

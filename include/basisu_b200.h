@@ -175,6 +175,18 @@ int b200_etc1s_encode_endpoint_clusters(b200_context* ctx, void* pOutput_blocks,
 int b200_etc1s_optimize_selector_codebook(b200_context* ctx, const void* pEtc_blocks, uint32_t total_clusters, const uint32_t* pCluster_offsets,
 	const uint32_t* pCluster_block_indices, uint32_t* pOutput_selectors, int perceptual);
 
+/* basisu_frontend::reoptimize_remapped_endpoints, the per-cluster optimiser loop (encoder/basisu_frontend.cpp:3008-3090), which
+ * the ETC1S backend calls after its endpoint remapping (basisu_backend.cpp:162, 1284): for every endpoint cluster (CSR lists of
+ * block indices, as above) re-fit colour + intensity table over the cluster's texels with each texel's selector IMPOSED
+ * (etc1_optimizer::params::m_pForce_selectors; pBlock_selectors[k] = the 16 selectors of the k-th LISTED block, texel (x, y) at
+ * bits 2 * (x + 4 * y), i.e. parallel to pCluster_block_indices), and evaluate the cluster's current endpoint
+ * (pCluster_color5_inten: r5, g5, b5, table per cluster, 4 B) with the same selectors. total_perms is 64 (cETCQualitySlow) or
+ * 165 (cETCQualityUber, compression level 6). Outputs per cluster: the new endpoint (same 4-byte layout), its error and the
+ * current error; the caller keeps the reference's `new < current` rule. Empty clusters give zeros. */
+int b200_etc1s_reoptimize_endpoint_clusters(b200_context* ctx, uint32_t total_clusters, const uint32_t* pCluster_offsets, const uint32_t* pCluster_block_indices,
+	const uint32_t* pBlock_selectors, const void* pCluster_color5_inten, void* pOut_color5_inten, uint64_t* pOut_new_err, uint64_t* pOut_cur_err,
+	int perceptual, uint32_t total_perms);
+
 /* ---- ETC1S multi-GPU exchange point -------------------------------------------------------------------------------------- */
 
 /* Histogram of the 18-bit endpoint training keys (r5<<13 | g5<<8 | b5<<3 | inten) of `num_blocks` ETC1S blocks, each block
@@ -262,7 +274,7 @@ enum
 {
 	B200_STAT_ETC1S_ENCODE_BLOCKS = 0, B200_STAT_ETC1S_ENDPOINT_CLUSTERS = 1, B200_STAT_ETC1S_REFINE = 2, B200_STAT_ETC1S_DETERMINE_SELECTORS = 3,
 	B200_STAT_ETC1S_FIND_SELECTOR_CLUSTERS = 4, B200_STAT_ETC1S_SELECTOR_CODEBOOK = 5, B200_STAT_TSVQ = 6, B200_STAT_UASTC_ENCODE = 7, B200_STAT_UASTC_RDO = 8,
-	B200_STAT_COUNT = 9
+	B200_STAT_ETC1S_REOPTIMIZE_CLUSTERS = 9, B200_STAT_COUNT = 10
 };
 int b200_stats_get(const b200_context* ctx, uint32_t stat_id, float* pKernel_ms, uint32_t* pLaunches, uint32_t* pCalls);
 void b200_stats_reset(b200_context* ctx);

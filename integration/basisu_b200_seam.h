@@ -41,6 +41,13 @@ namespace basisu
 	bool opencl_b200_optimize_selector_codebook(opencl_context_ptr pContext, const etc_block* pEtc_blocks, uint32_t total_clusters,
 		const uint32_t* pCluster_offsets, const uint32_t* pCluster_block_indices, uint32_t* pOutput_selectors, bool perceptual);
 
+	// reoptimize_remapped_endpoints' per-cluster loop (frontend.cpp:3008-3090), called by the backend after endpoint remapping:
+	// pBlock_selectors[k] = packed selectors of the k-th listed block (texel (x, y) at bits 2 * (x + 4 * y)); endpoints travel as
+	// color_rgba(r5, g5, b5, intensity table). The caller applies `new_err < cur_err`.
+	bool opencl_b200_reoptimize_endpoint_clusters(opencl_context_ptr pContext, uint32_t total_clusters, const uint32_t* pCluster_offsets,
+		const uint32_t* pCluster_block_indices, const uint32_t* pBlock_selectors, const color_rgba* pCluster_color5_inten,
+		color_rgba* pNew_color5_inten, uint64_t* pNew_err, uint64_t* pCur_err, bool perceptual, uint32_t total_perms);
+
 	// Stage clocks of the patched compressor (basis_compressor::process): name -> seconds of the last run, readable from outside
 	// through `extern "C" double b200_dropin_stage_secs(const char* name)` (benchmarks; no effect on the output).
 	void opencl_b200_note_stage_secs(const char* pName, double secs);

@@ -194,6 +194,15 @@ namespace basisu
 			"opencl_b200_optimize_selector_codebook");
 	}
 
+	bool opencl_b200_reoptimize_endpoint_clusters(opencl_context_ptr p, uint32_t total_clusters, const uint32_t* pCluster_offsets,
+		const uint32_t* pCluster_block_indices, const uint32_t* pBlock_selectors, const color_rgba* pCluster_color5_inten,
+		color_rgba* pNew_color5_inten, uint64_t* pNew_err, uint64_t* pCur_err, bool perceptual, uint32_t total_perms)
+	{
+		if (!p) return false;
+		return report(p, b200_etc1s_reoptimize_endpoint_clusters(p->m_ctx, total_clusters, pCluster_offsets, pCluster_block_indices, pBlock_selectors, pCluster_color5_inten,
+			pNew_color5_inten, pNew_err, pCur_err, perceptual, total_perms), "opencl_b200_reoptimize_endpoint_clusters");
+	}
+
 	static std::mutex g_stage_mutex;
 	static std::map<std::string, double> g_stage_secs;
 

@@ -289,6 +289,52 @@ REF_API uint64_t ref_etc1s_encode_cluster(const uint8_t* pPixels, uint32_t n, ui
 	return r.m_error;
 }
 
+// The per-cluster body of basisu_frontend::reoptimize_remapped_endpoints (frontend.cpp:3018-3090): `nblocks` source blocks
+// (64 B each), one packed selector word per block (texel (x, y) at bits 2 * (x + 4 * y)), the cluster's current endpoint cur4 =
+// {r5, g5, b5, inten}. Returns the optimiser's error; out4 = new endpoint, *pCur_err = error of cur4 with the imposed selectors.
+REF_API uint64_t ref_etc1s_reoptimize_cluster(const uint8_t* pBlocks, uint32_t nblocks, const uint32_t* pSelectors, const uint8_t* cur4, uint32_t perceptual, uint32_t comp_level,
+	uint8_t* out4, uint64_t* pCur_err)
+{
+	ref_init();
+	const uint32_t n = nblocks * 16;
+	std::vector<color_rgba> px(n);
+	std::vector<uint8_t> force(n);
+	etc_block blk;
+	blk.set_block_color5_etc1s(color_rgba(cur4[0], cur4[1], cur4[2], 255));
+	blk.set_inten_tables_etc1s(cur4[3]);
+	blk.set_flip_bit(true);
+	uint64_t cur_err = 0;
+	for (uint32_t b = 0; b < nblocks; b++)
+	{
+		memcpy(&px[b * 16], pBlocks + (size_t)b * 64, 64);
+		for (uint32_t y = 0; y < 4; y++)
+			for (uint32_t x = 0; x < 4; x++)
+			{
+				const uint32_t sv = (pSelectors[b] >> (2 * (x + 4 * y))) & 3;
+				force[b * 16 + x + y * 4] = (uint8_t)sv;
+				blk.set_selector(x, y, sv);
+			}
+		cur_err += blk.evaluate_etc1_error(reinterpret_cast<const color_rgba*>(pBlocks + (size_t)b * 64), perceptual != 0);
+	}
+	etc1_optimizer optimizer;
+	etc1_optimizer::params p;
+	p.m_num_src_pixels = n;
+	p.m_pSrc_pixels = px.data();
+	p.m_use_color4 = false;
+	p.m_perceptual = perceptual != 0;
+	p.m_pForce_selectors = force.data();
+	p.m_quality = (comp_level == BASISU_MAX_ETC1S_COMPRESSION_LEVEL) ? cETCQualityUber : cETCQualitySlow;
+	etc1_optimizer::results r;
+	std::vector<uint8_t> sel(n);
+	r.m_n = n;
+	r.m_pSelectors = sel.data();
+	optimizer.init(p, r);
+	if (!optimizer.compute()) { *pCur_err = cur_err; return UINT64_MAX; }
+	out4[0] = r.m_block_color_unscaled.r; out4[1] = r.m_block_color_unscaled.g; out4[2] = r.m_block_color_unscaled.b; out4[3] = (uint8_t)r.m_block_inten_table;
+	*pCur_err = cur_err;
+	return r.m_error;
+}
+
 // ---- the steps either side of the per-block path -----------------------------------------------
 
 // basis_compressor::extract_source_blocks for one slice (comp.cpp:3207): image::extract_block_clamped per 4x4 block.

@@ -113,6 +113,55 @@ EMU_API void emu_etc1s_encode_blocks(const uint8_t* pBlocks, uint32_t n, uint8_t
 	}
 }
 
+// The cluster optimiser templates of bu_etc1s.h run by a team of one (the device runs them with a warp or a CTA).
+struct serial_team
+{
+	uint32_t rank = 0; etc1s_bloom bloom;
+	static constexpr uint32_t size = 1;
+	serial_team() { bloom_clear(bloom); }
+	uint64_t sum(uint64_t v) { return v; }
+	void minmax(uint32_t&, uint32_t&) {}
+	bool bloom_test_and_set(uint32_t r5, uint32_t g5, uint32_t b5) { return bu::bloom_test_and_set(bloom, r5, g5, b5); }
+};
+struct host_blocks_src
+{
+	static constexpr bool forced = false, unit_weights = true;
+	const uint32_t* px; uint64_t n;
+	uint32_t pixel(uint64_t i) const { return px[i]; }
+	uint32_t weight(uint64_t) const { return 1u; }
+	uint32_t selector(uint64_t) const { return 0; }
+};
+struct host_forced_src
+{
+	static constexpr bool forced = true, unit_weights = true;
+	const uint32_t* px; const uint32_t* sels; uint64_t n;
+	uint32_t pixel(uint64_t i) const { return px[i]; }
+	uint32_t weight(uint64_t) const { return 1u; }
+	uint32_t selector(uint64_t i) const { return (sels[i >> 4] >> (2 * (uint32_t)(i & 15))) & 3u; }
+};
+// One endpoint cluster of `nblocks` source blocks. pSelectors == NULL: b200_etc1s_encode_endpoint_clusters' per-cluster work;
+// else b200_etc1s_reoptimize_endpoint_clusters' (selectors imposed, *pCur_err = error of cur4 with them). out4 = {r5, g5, b5, inten}.
+EMU_API uint64_t emu_etc1s_optimize_cluster(const uint8_t* pBlocks, uint32_t nblocks, const uint32_t* pSelectors, const uint8_t* cur4, int perceptual, uint32_t total_perms, int flavour,
+	uint8_t* out4, uint64_t* pCur_err)
+{
+	serial_team team;
+	uint64_t err = 0, packed;
+	if (pSelectors)
+	{
+		host_forced_src src; src.px = reinterpret_cast<const uint32_t*>(pBlocks); src.sels = pSelectors; src.n = (uint64_t)nblocks * 16;
+		if (pCur_err) *pCur_err = cluster_forced_error(&g_tables, perceptual != 0, src, team, cur4[0], cur4[1], cur4[2], cur4[3]);
+		packed = cluster_optimize(&g_tables, perceptual != 0, src, team, total_perms, flavour, &err);
+	}
+	else
+	{
+		host_blocks_src src; src.px = reinterpret_cast<const uint32_t*>(pBlocks); src.n = (uint64_t)nblocks * 16;
+		packed = cluster_optimize(&g_tables, perceptual != 0, src, team, total_perms, flavour, &err);
+	}
+	const uint32_t w = (uint32_t)packed;
+	out4[0] = (uint8_t)((w >> 3) & 31); out4[1] = (uint8_t)((w >> 11) & 31); out4[2] = (uint8_t)((w >> 19) & 31); out4[3] = (uint8_t)((w >> 29) & 7);
+	return err;
+}
+
 EMU_API void emu_etc1s_determine_selectors(const uint8_t* pBlocks, uint32_t n, const uint32_t* pColor5_inten, uint8_t* pOut, int perceptual)
 {
 	for (uint32_t i = 0; i < n; i++)

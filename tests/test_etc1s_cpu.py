@@ -118,3 +118,103 @@ def test_training_vectors_from_colliding_keys_are_merged():
     assert np.array_equal(u[0], np.array([0, 0, 0, 1, 1, 1], np.float32)) or np.array_equal(u[1], np.array([0, 0, 0, 1, 1, 1], np.float32))
     assert int(w.sum()) == int(hist.sum()) and sorted(int(x) for x in w) == sorted([4, int(hist.sum()) - 4])
     assert np.all(np.lexsort(u.T[::-1]) == np.arange(u.shape[0]))   # lexicographic order, the std::map's
+
+
+def _cluster_cases(seed):
+    """Ragged clusters of the synthetic image's blocks (similar blocks together, like real endpoint clusters) + selectors per block."""
+    img = util.synth(128, seed)
+    blocks = util.image_to_blocks(img)
+    rng = np.random.default_rng(seed)
+    lum = blocks.reshape(blocks.shape[0], 16, 4)[:, :, :3].astype(np.int64).sum(axis=(1, 2))
+    order = np.argsort(lum, kind="stable").astype(np.uint32)
+    cuts = np.sort(rng.choice(np.arange(1, blocks.shape[0]), 40, replace=False))
+    return blocks, [c for c in np.split(order, cuts)], rng
+
+
+def emu_optimize_cluster(emu, blk, sels, cur4, perceptual, perms, flavour=1):
+    out4 = np.zeros(4, np.uint8)
+    cur_err = ctypes.c_uint64(0)
+    emu.lib.emu_etc1s_optimize_cluster.restype = ctypes.c_uint64
+    err = emu.lib.emu_etc1s_optimize_cluster(_ptr(blk), ctypes.c_uint32(blk.shape[0]), _ptr(sels) if sels is not None else None,
+                                             _ptr(cur4) if cur4 is not None else None, perceptual, ctypes.c_uint32(perms), flavour, _ptr(out4), ctypes.byref(cur_err))
+    return tuple(int(v) for v in out4), int(err), int(cur_err.value)
+
+
+def ref_reoptimize_cluster(ref, blk, sels, cur4, perceptual, comp_level):
+    out4 = np.zeros(4, np.uint8)
+    cur_err = ctypes.c_uint64(0)
+    ref.lib.ref_etc1s_reoptimize_cluster.restype = ctypes.c_uint64
+    err = ref.lib.ref_etc1s_reoptimize_cluster(_ptr(blk), ctypes.c_uint32(blk.shape[0]), _ptr(sels), _ptr(cur4), perceptual, comp_level, _ptr(out4), ctypes.byref(cur_err))
+    return tuple(int(v) for v in out4), int(err), int(cur_err.value)
+
+
+@pytest.mark.parametrize("perceptual", [0, 1])
+@pytest.mark.parametrize("comp_level,perms", [(1, 16), (2, 64), (6, 165)])
+def test_cluster_optimizer_matches_reference_cpu_optimizer(ref, emu, perceptual, comp_level, perms):
+    """The team-templated cluster optimiser (what the endpoint-cluster kernels run) against etc1_optimizer over the gathered texels."""
+    blocks, clusters, _ = _cluster_cases(31)
+    ref.lib.ref_etc1s_encode_cluster.restype = ctypes.c_uint64
+    for c in clusters:
+        blk = np.ascontiguousarray(blocks[c])
+        want4 = np.zeros(4, np.uint8)
+        want_err = ref.lib.ref_etc1s_encode_cluster(_ptr(blk), ctypes.c_uint32(blk.shape[0] * 16), perceptual, comp_level, _ptr(want4))
+        got4, got_err, _ = emu_optimize_cluster(emu, blk, None, None, perceptual, perms)
+        assert got4 == tuple(int(v) for v in want4) and got_err == want_err, len(c)
+
+
+@pytest.mark.parametrize("perceptual", [0, 1])
+@pytest.mark.parametrize("comp_level,perms", [(2, 64), (6, 165)])
+def test_reoptimize_cluster_with_forced_selectors_matches_reference(ref, emu, perceptual, comp_level, perms):
+    """reoptimize_remapped_endpoints' per-cluster body (frontend.cpp:3018-3090): imposed selectors, new and current error."""
+    blocks, clusters, rng = _cluster_cases(37)
+    n = blocks.shape[0]
+    etc = np.zeros((n, 8), np.uint8)
+    ref.lib.ref_etc1s_encode_blocks(_ptr(blocks), ctypes.c_uint32(n), _ptr(etc), perceptual, 1)
+    # selectors as the frontend has them: selector INDEX (0..3 = darkest..brightest) per texel, bits 2 * (x + 4 * y); taken from
+    # each block's own encoding so that they are meaningful, then a few blocks get random ones
+    sel_words = np.zeros(n, np.uint32)
+    raw_to_sel = np.array([2, 3, 1, 0], np.uint32)
+    for b in range(n):
+        msb = (int(etc[b, 4]) << 8) | int(etc[b, 5]); lsb = (int(etc[b, 6]) << 8) | int(etc[b, 7])
+        w = 0
+        for y in range(4):
+            for x in range(4):
+                bit = x * 4 + y
+                raw = ((lsb >> bit) & 1) | (((msb >> bit) & 1) << 1)
+                w |= int(raw_to_sel[raw]) << (2 * (x + 4 * y))
+        sel_words[b] = w
+    rnd = rng.choice(n, n // 10, replace=False)
+    sel_words[rnd] = rng.integers(0, 1 << 32, rnd.shape[0], dtype=np.uint64).astype(np.uint32)
+    improved = 0
+    for c in clusters:
+        blk = np.ascontiguousarray(blocks[c]); sels = np.ascontiguousarray(sel_words[c])
+        cur4 = np.array([etc[c[0], 0] >> 3, etc[c[0], 1] >> 3, etc[c[0], 2] >> 3, etc[c[0], 3] >> 5], np.uint8)  # some member's endpoint
+        want = ref_reoptimize_cluster(ref, blk, sels, cur4, perceptual, comp_level)
+        got = emu_optimize_cluster(emu, blk, sels, cur4, perceptual, perms)
+        assert got == want, (len(c), got, want)
+        improved += want[1] < want[2]
+    assert improved > 0
+
+
+def test_cluster_average_past_2_pow_24_follows_the_reference_float_sum(ref, emu):
+    """etc1_optimizer::init sums texels into a float (etc.cpp:1022-1040); past 2^24 (> 4112 bright blocks) that sum rounds, and the
+    optimiser's starting colour follows it. Here the red channel's exact mean rounds to 31 and the float-summed one to 30, and at comp_level 1 the
+    optimiser ends on red = 30 where an exact mean would end on 31 with a lower error."""
+    n = 4500
+    rng = np.random.default_rng(76)
+    red = rng.integers(248, 255, n * 16)
+    red = (red - (rng.random(n * 16) < 0.1135)).astype(np.uint8)
+    to5 = lambda a: int(np.float32(np.float32(np.float32(a * np.float32(31)) / np.float32(255)) + np.float32(.5)))
+    exact = np.float32(int(red.astype(np.int64).sum())) / np.float32(n * 16)
+    serial = np.cumsum(red.astype(np.float32), dtype=np.float32)[-1] / np.float32(n * 16)
+    assert (to5(exact), to5(serial)) == (31, 30)
+    blocks = np.empty((n * 16, 4), np.uint8)
+    blocks[:, 0] = red; blocks[:, 1] = rng.integers(100, 140, n * 16); blocks[:, 2] = rng.integers(50, 60, n * 16); blocks[:, 3] = 255
+    blocks = np.ascontiguousarray(blocks.reshape(n, 64))
+    ref.lib.ref_etc1s_encode_cluster.restype = ctypes.c_uint64
+    for perceptual, comp_level, perms in ((0, 1, 16), (1, 1, 16), (1, 2, 64)):
+        want4 = np.zeros(4, np.uint8)
+        want_err = ref.lib.ref_etc1s_encode_cluster(_ptr(blocks), ctypes.c_uint32(n * 16), perceptual, comp_level, _ptr(want4))
+        got4, got_err, _ = emu_optimize_cluster(emu, blocks, None, None, perceptual, perms)
+        assert got4 == tuple(int(v) for v in want4) and got_err == want_err
+    assert tuple(int(v) for v in want4)[0] in (30, 31)

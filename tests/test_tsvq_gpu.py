@@ -200,3 +200,78 @@ def test_selector_codebook_matches_reference(ctx, ref, perceptual):
     want = np.zeros(len(clusters), np.uint32)
     ref.lib.ref_optimize_selector_codebook(_ptr(blocks), _ptr(etc), len(clusters), _ptr(off), _ptr(idx), perceptual, _ptr(want))
     assert np.array_equal(got, want)
+
+
+def _selector_words(etc):
+    """Selector INDEX words (texel (x, y) at bits 2 * (x + 4 * y)) of encoded etc_blocks, as etc_block::get_selector gives them."""
+    raw_to_sel = np.array([2, 3, 1, 0], np.uint32)
+    msb = (etc[:, 4].astype(np.uint32) << 8) | etc[:, 5]
+    lsb = (etc[:, 6].astype(np.uint32) << 8) | etc[:, 7]
+    w = np.zeros(etc.shape[0], np.uint32)
+    for y in range(4):
+        for x in range(4):
+            bit = x * 4 + y
+            raw = ((lsb >> bit) & 1) | (((msb >> bit) & 1) << 1)
+            w |= raw_to_sel[raw] << np.uint32(2 * (x + 4 * y))
+    return w
+
+
+@pytest.mark.parametrize("perceptual", [0, 1])
+@pytest.mark.parametrize("comp_level,perms", [(2, 64), (6, 165)])
+def test_reoptimize_endpoint_clusters_match_reference(ctx, ref, perceptual, comp_level, perms):
+    """b200_etc1s_reoptimize_endpoint_clusters against reoptimize_remapped_endpoints' per-cluster body (frontend.cpp:3018-3090):
+    ragged clusters incl. an empty one and one large enough for the CTA-per-cluster kernel."""
+    img = util.synth(256, 41)
+    blocks = util.image_to_blocks(img)
+    n = blocks.shape[0]
+    ctx.set_pixel_blocks(blocks)
+    etc = np.zeros((n, 8), np.uint8)
+    ref.lib.ref_etc1s_encode_blocks(_ptr(blocks), ctypes.c_uint32(n), _ptr(etc), perceptual, 1)
+    sels = _selector_words(etc)
+    rng = np.random.default_rng(43)
+    rnd = rng.choice(n, n // 10, replace=False)
+    sels[rnd] = rng.integers(0, 1 << 32, rnd.shape[0], dtype=np.uint64).astype(np.uint32)
+    lum = blocks.reshape(n, 16, 4)[:, :, :3].astype(np.int64).sum(axis=(1, 2))
+    order = np.argsort(lum, kind="stable").astype(np.uint32)
+    cuts = np.sort(rng.choice(np.arange(1, n - 400), 70, replace=False))
+    clusters = [c for c in np.split(order[:n - 400], cuts)] + [np.zeros(0, np.uint32), order[n - 400:]]
+    cur = np.zeros((len(clusters), 4), np.uint8)
+    for i, c in enumerate(clusters):
+        if len(c):
+            e = etc[c[len(c) // 2]]
+            cur[i] = (e[0] >> 3, e[1] >> 3, e[2] >> 3, e[3] >> 5)
+    got4, got_new, got_cur = ctx.reoptimize_endpoint_clusters(clusters, sels, cur, perceptual, perms)
+    ref.lib.ref_etc1s_reoptimize_cluster.restype = ctypes.c_uint64
+    improved = 0
+    for i, c in enumerate(clusters):
+        if not len(c):
+            assert (int(got_new[i]), int(got_cur[i])) == (0, 0)
+            continue
+        blk = np.ascontiguousarray(blocks[c]); s = np.ascontiguousarray(sels[c])
+        want4 = np.zeros(4, np.uint8); want_cur = ctypes.c_uint64(0)
+        want_new = ref.lib.ref_etc1s_reoptimize_cluster(_ptr(blk), ctypes.c_uint32(len(c)), _ptr(s), _ptr(cur[i]), perceptual, comp_level, _ptr(want4), ctypes.byref(want_cur))
+        assert (tuple(int(v) for v in got4[i]), int(got_new[i]), int(got_cur[i])) == (tuple(int(v) for v in want4), want_new, want_cur.value), (i, len(c))
+        improved += want_new < want_cur.value
+    assert improved > 0
+
+
+def test_endpoint_cluster_past_2_pow_24_follows_the_reference_float_sum(ctx, ref):
+    """A 4500-block bright cluster: etc1_optimizer::init's float sum rounds past 2^24 and the CTA-per-cluster kernel follows it
+    (the same construction as tests/test_etc1s_cpu.py, where the exact mean is shown to end on another colour)."""
+    n = 4500
+    rng = np.random.default_rng(76)
+    red = rng.integers(248, 255, n * 16)
+    red = (red - (rng.random(n * 16) < 0.1135)).astype(np.uint8)
+    px = np.empty((n * 16, 4), np.uint8)
+    px[:, 0] = red; px[:, 1] = rng.integers(100, 140, n * 16); px[:, 2] = rng.integers(50, 60, n * 16); px[:, 3] = 255
+    blocks = np.ascontiguousarray(px.reshape(n, 64))
+    ctx.set_pixel_blocks(blocks)
+    clusters = [np.arange(n, dtype=np.uint32), np.arange(0, 40, dtype=np.uint32)]
+    ref.lib.ref_etc1s_encode_cluster.restype = ctypes.c_uint64
+    for perceptual, comp_level, perms in ((1, 1, 16), (0, 2, 64)):
+        got = ctx.encode_endpoint_clusters(clusters, perceptual, perms)
+        for i, c in enumerate(clusters):
+            blk = np.ascontiguousarray(blocks[c])
+            out4 = np.zeros(4, np.uint8)
+            ref.lib.ref_etc1s_encode_cluster(_ptr(blk), ctypes.c_uint32(len(c) * 16), perceptual, comp_level, _ptr(out4))
+            assert (got[i, 0] >> 3, got[i, 1] >> 3, got[i, 2] >> 3, got[i, 3] >> 5) == tuple(int(v) for v in out4), (i, perceptual)
