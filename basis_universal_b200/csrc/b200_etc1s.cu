@@ -208,13 +208,22 @@ struct reopt_out { uint64_t packed, new_err, cur_err; };
 template<typename Team> __device__ void reoptimize_cluster(const bu_tables* T, bool perceptual, const uint32_t* __restrict__ blocks, const uint32_t* __restrict__ offsets, const uint32_t* __restrict__ bidx,
 	const uint32_t* __restrict__ sels, const uint32_t* __restrict__ cur_c5i, uint32_t c, Team& team, uint32_t total_perms, int flavour, reopt_out* out, bool writer)
 {
-	px_blocks_forced_src src;
-	src.blocks = blocks; src.bidx = bidx + offsets[c]; src.sels = sels + offsets[c]; src.n = (uint64_t)(offsets[c + 1] - offsets[c]) * 16;
 	reopt_out r; r.packed = 0; r.new_err = 0; r.cur_err = 0;
-	if (src.n)
+	const uint32_t cur = cur_c5i[c];
+	const uint64_t n = (uint64_t)(offsets[c + 1] - offsets[c]) * 16;
+	if (n && sels)
 	{
-		const uint32_t cur = cur_c5i[c];
-		r.cur_err = cluster_forced_error(T, perceptual, src, team, cur & 255, (cur >> 8) & 255, (cur >> 16) & 255, cur >> 24);
+		px_blocks_forced_src src;
+		src.blocks = blocks; src.bidx = bidx + offsets[c]; src.sels = sels + offsets[c]; src.n = n;
+		r.cur_err = cluster_endpoint_error(T, perceptual, src, team, cur & 255, (cur >> 8) & 255, (cur >> 16) & 255, cur >> 24);
+		r.packed = cluster_optimize(T, perceptual, src, team, total_perms, flavour, &r.new_err);
+	}
+	else if (n)
+	{
+		// selectors free (generate_endpoint_codebook at step >= 1)
+		px_blocks_src src;
+		src.blocks = blocks; src.bidx = bidx + offsets[c]; src.n = n;
+		r.cur_err = cluster_endpoint_error(T, perceptual, src, team, cur & 255, (cur >> 8) & 255, (cur >> 16) & 255, cur >> 24);
 		r.packed = cluster_optimize(T, perceptual, src, team, total_perms, flavour, &r.new_err);
 	}
 	if (writer) out[c] = r;
@@ -235,6 +244,40 @@ __global__ void __launch_bounds__(ETC1S_CTA_TEAM) k_etc1s_reoptimize_clusters_bi
 	if (k >= n_big) return;
 	cta_team team(&S);
 	reoptimize_cluster(&d_tables, perceptual_i != 0, blocks, offsets, bidx, sels, cur_c5i, order[k], team, total_perms, flavour, out, threadIdx.x == 0);
+}
+
+// ---- compute_endpoint_subblock_error_vec (frontend.cpp:1006-1082): per block, the error of each of its two subblocks (texels 0-7 and
+// 8-15 of the flipped layout) against the endpoint of the block's cluster, best of the four colours per texel.
+__global__ void __launch_bounds__(128) k_etc1s_subblock_errors(const uint4* __restrict__ blocks, const uint32_t* __restrict__ c5i, uint32_t first, uint32_t last, uint2* __restrict__ out, int perceptual_i)
+{
+	const uint32_t i = first + blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= last) return;
+	const bool perceptual = perceptual_i != 0;
+	const uint32_t e = c5i[i];
+	// Reference behaviour kept: frontend.cpp:1043 passes the UNSCALED 5-bit colour to get_block_colors5(..., scaled = true), so the four
+	// colours are (r5 + m, g5 + m, b5 + m) clamped, not the expanded 8-bit base plus m. The ranking of subblocks that
+	// introduce_new_endpoint_clusters works from is defined by that.
+	uint32_t colors[4];
+	for (int k = 0; k < 4; k++)
+	{
+		const int m = d_tables.etc1_inten[(e >> 24) * 4 + k];
+		colors[k] = px_make((uint32_t)clamp255i((int)(e & 255) + m), (uint32_t)clamp255i((int)((e >> 8) & 255) + m), (uint32_t)clamp255i((int)((e >> 16) & 255) + m), 255);
+	}
+	uint32_t err[2] = { 0, 0 }; // <= 8 texels * max distance: fits 32 bits for both metrics
+	for (int q = 0; q < 4; q++)
+	{
+		const uint4 v = __ldg(blocks + (size_t)i * 4 + q);
+		const uint32_t px[4] = { v.x, v.y, v.z, v.w };
+		for (int k = 0; k < 4; k++)
+		{
+			uint32_t be = etc_color_distance(perceptual, px[k], colors[0]);
+			be = min(be, etc_color_distance(perceptual, px[k], colors[1]));
+			be = min(be, etc_color_distance(perceptual, px[k], colors[2]));
+			be = min(be, etc_color_distance(perceptual, px[k], colors[3]));
+			err[q >> 1] += be;
+		}
+	}
+	out[i] = make_uint2(err[0], err[1]);
 }
 
 // ---- create_optimized_selector_codebook: one warp per selector cluster ---------------------------------------------------------
@@ -703,7 +746,7 @@ extern "C" int b200_etc1s_reoptimize_endpoint_clusters(b200_context* ctx, uint32
 	ETC_CHECK_BLOCKS(ctx, "b200_etc1s_reoptimize_endpoint_clusters");
 	if (!total_clusters) return 1;
 	if (total_perms > 165) { ctx->fail("b200_etc1s_reoptimize_endpoint_clusters: total_perms > 165"); return 0; }
-	if (!pCluster_offsets || !pCluster_block_indices || !pBlock_selectors || !pCluster_color5_inten || !pOut_color5_inten || !pOut_new_err || !pOut_cur_err)
+	if (!pCluster_offsets || !pCluster_block_indices || !pCluster_color5_inten || !pOut_color5_inten || !pOut_new_err || !pOut_cur_err)
 	{ ctx->fail("b200_etc1s_reoptimize_endpoint_clusters: null buffer"); return 0; }
 	const uint32_t total_indices = pCluster_offsets[total_clusters];
 	for (uint32_t i = 0; i < total_indices; i++)
@@ -712,7 +755,7 @@ extern "C" int b200_etc1s_reoptimize_endpoint_clusters(b200_context* ctx, uint32
 	uint32_t* order = cluster_launch_order(pCluster_offsets, total_clusters, n_big);
 	if (!order) { ctx->fail("b200_etc1s_reoptimize_endpoint_clusters: out of host memory"); return 0; }
 	bool ok = upload(ctx, 1, pCluster_offsets, ((size_t)total_clusters + 1) * 4) && upload(ctx, 2, pCluster_block_indices, (size_t)total_indices * 4) && upload(ctx, 3, order, (size_t)total_clusters * 4) &&
-		upload(ctx, 4, pBlock_selectors, (size_t)total_indices * 4) && upload(ctx, 5, pCluster_color5_inten, (size_t)total_clusters * 4);
+		(!pBlock_selectors || upload(ctx, 4, pBlock_selectors, (size_t)total_indices * 4)) && upload(ctx, 5, pCluster_color5_inten, (size_t)total_clusters * 4);
 	if (ok) ok = ctx->reserve(ctx->d_aux[0], ctx->aux_cap[0], (size_t)total_clusters * sizeof(reopt_out));
 	if (ok && cudaStreamSynchronize(ctx->stream) != cudaSuccess) ok = false; // `order` is pageable host memory about to be freed
 	free(order);
@@ -723,7 +766,7 @@ extern "C" int b200_etc1s_reoptimize_endpoint_clusters(b200_context* ctx, uint32
 	const uint32_t warps_per_cta = 4, world = (uint32_t)(ctx->world > 1 ? ctx->world : 1);
 	const uint32_t* d_blocks = static_cast<const uint32_t*>(ctx->d_etc_blocks);
 	const uint32_t* d_off = static_cast<const uint32_t*>(ctx->d_aux[1]); const uint32_t* d_idx = static_cast<const uint32_t*>(ctx->d_aux[2]);
-	const uint32_t* d_order = static_cast<const uint32_t*>(ctx->d_aux[3]); const uint32_t* d_sels = static_cast<const uint32_t*>(ctx->d_aux[4]);
+	const uint32_t* d_order = static_cast<const uint32_t*>(ctx->d_aux[3]); const uint32_t* d_sels = pBlock_selectors ? static_cast<const uint32_t*>(ctx->d_aux[4]) : nullptr;
 	const uint32_t* d_cur = static_cast<const uint32_t*>(ctx->d_aux[5]);
 	reopt_out* d_out = static_cast<reopt_out*>(ctx->d_aux[0]);
 	if (n_big)
@@ -751,6 +794,29 @@ extern "C" int b200_etc1s_reoptimize_endpoint_clusters(b200_context* ctx, uint32
 			pOut_new_err[c] = h[c].new_err; pOut_cur_err[c] = h[c].cur_err;
 		}
 	}
+	free(h);
+	return fin;
+}
+
+extern "C" int b200_etc1s_subblock_errors(b200_context* ctx, const void* pBlock_color5_inten, uint64_t* pOut_errors, int perceptual)
+{
+	ETC_CHECK_BLOCKS(ctx, "b200_etc1s_subblock_errors");
+	if (!pBlock_color5_inten || !pOut_errors) { ctx->fail("b200_etc1s_subblock_errors: null buffer"); return 0; }
+	const uint32_t n = ctx->etc_total_blocks;
+	if (!upload(ctx, 1, pBlock_color5_inten, (size_t)n * 4)) return 0;
+	if (!ctx->reserve(ctx->d_aux[0], ctx->aux_cap[0], (size_t)n * 8)) return 0;
+	ctx->launches = 1; __atomic_add_fetch(&g_b200_total_launches, 1, __ATOMIC_RELAXED);
+	if (!shard_prepare_output(ctx, 0, (size_t)n * 8)) return 0;
+	B200_CUDA_OK(ctx, cudaEventRecord(ctx->ev0, ctx->stream));
+	uint32_t first, last;
+	shard_range(ctx, n, first, last);
+	if (last > first)
+		k_etc1s_subblock_errors<<<(last - first + 127) / 128, 128, 0, ctx->stream>>>(static_cast<const uint4*>(ctx->d_etc_blocks), static_cast<const uint32_t*>(ctx->d_aux[1]), first, last,
+			static_cast<uint2*>(ctx->d_aux[0]), perceptual);
+	uint32_t* h = static_cast<uint32_t*>(malloc((size_t)n * 8));
+	if (!h) { ctx->fail("b200_etc1s_subblock_errors: out of host memory"); return 0; }
+	const int fin = finish(ctx, h, 0, (size_t)n * 8, B200_STAT_ETC1S_REOPTIMIZE_CLUSTERS);
+	if (fin) for (size_t i = 0; i < (size_t)n * 2; i++) pOut_errors[i] = h[i];
 	free(h);
 	return fin;
 }

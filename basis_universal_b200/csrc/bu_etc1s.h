@@ -327,16 +327,31 @@ template<typename Src, typename Team> BU_HD inline uint64_t cluster_optimize(con
 	return etc1s_pack(best.r5, best.g5, best.b5, best.inten, 0, 0); // the kernel defines no selectors for clusters
 }
 
-// Error of one given (colour, table) with the imposed selectors: the "current error" of reoptimize_remapped_endpoints (frontend.cpp:3033-3046).
-template<typename Src, typename Team> BU_HD inline uint64_t cluster_forced_error(const bu_tables* T, bool perceptual, const Src& src, Team& team, uint32_t r5, uint32_t g5, uint32_t b5, uint32_t inten)
+// Error of one given (colour, table) over the cluster's texels: with the imposed selectors for a forced source (the "current error"
+// of reoptimize_remapped_endpoints, frontend.cpp:3033-3046), else with the best of the four colours per texel (the "previous error"
+// of generate_endpoint_codebook at step >= 1, frontend.cpp:1560-1590).
+template<typename Src, typename Team> BU_HD inline uint64_t cluster_endpoint_error(const bu_tables* T, bool perceptual, const Src& src, Team& team, uint32_t r5, uint32_t g5, uint32_t b5, uint32_t inten)
 {
 	uint32_t colors[4];
 	etc1s_block_colors(T, r5, g5, b5, inten, colors);
 	uint64_t total = 0;
 	for (uint64_t i = team.rank; i < src.n; i += Team::size)
 	{
-		const uint32_t sl = src.selector(i);
-		total += etc_color_distance(perceptual, src.pixel(i), sl == 0 ? colors[0] : (sl == 1 ? colors[1] : (sl == 2 ? colors[2] : colors[3])));
+		const uint32_t p = src.pixel(i);
+		uint32_t be;
+		if (Src::forced)
+		{
+			const uint32_t sl = src.selector(i);
+			be = etc_color_distance(perceptual, p, sl == 0 ? colors[0] : (sl == 1 ? colors[1] : (sl == 2 ? colors[2] : colors[3])));
+		}
+		else
+		{
+			be = etc_color_distance(perceptual, p, colors[0]);
+			be = minu(be, etc_color_distance(perceptual, p, colors[1]));
+			be = minu(be, etc_color_distance(perceptual, p, colors[2]));
+			be = minu(be, etc_color_distance(perceptual, p, colors[3]));
+		}
+		total += be;
 	}
 	return team.sum(total);
 }

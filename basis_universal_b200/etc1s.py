@@ -187,15 +187,27 @@ def _reoptimize_endpoint_clusters(self, clusters, block_selectors, cluster_color
     block_selectors = one packed selector word per block OF THE SLICE (texel (x, y) at bits 2 * (x + 4 * y)); cluster_color5_inten
     = (n, 4) uint8 current endpoints. -> (new (n, 4) uint8, new_err (n,) uint64, cur_err (n,) uint64)."""
     off, idx = _csr(clusters)
-    sels = np.ascontiguousarray(np.asarray(block_selectors, np.uint32)[idx]) if idx.shape[0] else np.zeros(1, np.uint32)
+    if block_selectors is None:   # free selectors: generate_endpoint_codebook at step >= 1 (frontend.cpp:1493-1606)
+        sels = None
+    else:
+        sels = np.ascontiguousarray(np.asarray(block_selectors, np.uint32)[idx]) if idx.shape[0] else np.zeros(1, np.uint32)
     cur = np.ascontiguousarray(cluster_color5_inten, np.uint8)
     assert cur.shape == (len(clusters), 4)
     out = np.zeros((len(clusters), 4), np.uint8)
     new_err = np.zeros(len(clusters), np.uint64)
     cur_err = np.zeros(len(clusters), np.uint64)
-    self._check(self._lib.b200_etc1s_reoptimize_endpoint_clusters(self._ctx, len(clusters), _p(off), _p(idx), _p(sels), _p(cur), _p(out), _p(new_err), _p(cur_err),
+    self._check(self._lib.b200_etc1s_reoptimize_endpoint_clusters(self._ctx, len(clusters), _p(off), _p(idx), _p(sels) if sels is not None else None, _p(cur), _p(out), _p(new_err), _p(cur_err),
                                                                     int(bool(perceptual)), int(total_perms)), "b200_etc1s_reoptimize_endpoint_clusters")
     return out, new_err, cur_err
+
+
+def _subblock_errors(self, block_color5_inten, perceptual):
+    """compute_endpoint_subblock_error_vec (frontend.cpp:1006): (n, 4) uint8 endpoint per block -> (n, 2) uint64 subblock errors."""
+    e = np.ascontiguousarray(block_color5_inten, np.uint8)
+    assert e.shape == (self.total_blocks, 4)
+    out = np.zeros((self.total_blocks, 2), np.uint64)
+    self._check(self._lib.b200_etc1s_subblock_errors(self._ctx, _p(e), _p(out), int(bool(perceptual))), "b200_etc1s_subblock_errors")
+    return out
 
 
 def comm_unique_id():
@@ -225,6 +237,7 @@ Etc1sContext.tsvq_generate = _tsvq_generate
 Etc1sContext.encode_endpoint_clusters = _encode_endpoint_clusters
 Etc1sContext.optimize_selector_codebook = _optimize_selector_codebook
 Etc1sContext.reoptimize_endpoint_clusters = _reoptimize_endpoint_clusters
+Etc1sContext.subblock_errors = _subblock_errors
 
 
 def merge_selector_training(keys, weights):

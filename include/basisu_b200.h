@@ -182,10 +182,20 @@ int b200_etc1s_optimize_selector_codebook(b200_context* ctx, const void* pEtc_bl
  * bits 2 * (x + 4 * y), i.e. parallel to pCluster_block_indices), and evaluate the cluster's current endpoint
  * (pCluster_color5_inten: r5, g5, b5, table per cluster, 4 B) with the same selectors. total_perms is 64 (cETCQualitySlow) or
  * 165 (cETCQualityUber, compression level 6). Outputs per cluster: the new endpoint (same 4-byte layout), its error and the
- * current error; the caller keeps the reference's `new < current` rule. Empty clusters give zeros. */
+ * current error; the caller keeps the reference's `new < current` rule. Empty clusters give zeros.
+ * pBlock_selectors == NULL: selectors are free (every texel takes the best of the four colours), which is the per-cluster body of
+ * generate_endpoint_codebook at refinement steps >= 1 (encoder/basisu_frontend.cpp:1493-1606): new endpoint + its error + the
+ * error of the cluster's previous endpoint; total_perms 16 / 64 / 165 as for b200_etc1s_encode_endpoint_clusters. */
 int b200_etc1s_reoptimize_endpoint_clusters(b200_context* ctx, uint32_t total_clusters, const uint32_t* pCluster_offsets, const uint32_t* pCluster_block_indices,
 	const uint32_t* pBlock_selectors, const void* pCluster_color5_inten, void* pOut_color5_inten, uint64_t* pOut_new_err, uint64_t* pOut_cur_err,
 	int perceptual, uint32_t total_perms);
+
+/* basisu_frontend::compute_endpoint_subblock_error_vec (encoder/basisu_frontend.cpp:1006-1082), the input of
+ * introduce_new_endpoint_clusters: for every block of the array given to b200_etc1s_set_pixel_blocks, the error of its two
+ * subblocks (flipped layout: texels 0-7 and 8-15) against the endpoint of the block's cluster (pBlock_color5_inten: r5, g5, b5,
+ * table per BLOCK, 4 B), best of the four colours per texel. pOut_errors[2 * block + subblock]. The reference evaluates this
+ * against the UNSCALED 5-bit base colour plus the table's modifiers (it passes scaled = true, frontend.cpp:1043); so does this. */
+int b200_etc1s_subblock_errors(b200_context* ctx, const void* pBlock_color5_inten, uint64_t* pOut_errors, int perceptual);
 
 /* ---- ETC1S multi-GPU exchange point -------------------------------------------------------------------------------------- */
 

@@ -48,6 +48,13 @@ namespace basisu
 		const uint32_t* pCluster_block_indices, const uint32_t* pBlock_selectors, const color_rgba* pCluster_color5_inten,
 		color_rgba* pNew_color5_inten, uint64_t* pNew_err, uint64_t* pCur_err, bool perceptual, uint32_t total_perms);
 
+	// (pBlock_selectors == nullptr: free selectors = generate_endpoint_codebook at refinement steps >= 1, frontend.cpp:1493-1606,
+	// with pCluster_color5_inten the previous endpoints and pCur_err their error.)
+
+	// compute_endpoint_subblock_error_vec (frontend.cpp:1006-1082): pOut_errors[2 * block + subblock] for every source block, against
+	// the endpoint of the block's cluster (pBlock_color5_inten: color_rgba(r5, g5, b5, table) per block).
+	bool opencl_b200_compute_subblock_errors(opencl_context_ptr pContext, const color_rgba* pBlock_color5_inten, uint64_t* pOut_errors, bool perceptual);
+
 	// Stage clocks of the patched compressor (basis_compressor::process): name -> seconds of the last run, readable from outside
 	// through `extern "C" double b200_dropin_stage_secs(const char* name)` (benchmarks; no effect on the output).
 	void opencl_b200_note_stage_secs(const char* pName, double secs);

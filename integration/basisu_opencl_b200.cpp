@@ -203,6 +203,12 @@ namespace basisu
 			pNew_color5_inten, pNew_err, pCur_err, perceptual, total_perms), "opencl_b200_reoptimize_endpoint_clusters");
 	}
 
+	bool opencl_b200_compute_subblock_errors(opencl_context_ptr p, const color_rgba* pBlock_color5_inten, uint64_t* pOut_errors, bool perceptual)
+	{
+		if (!p) return false;
+		return report(p, b200_etc1s_subblock_errors(p->m_ctx, pBlock_color5_inten, pOut_errors, perceptual), "opencl_b200_compute_subblock_errors");
+	}
+
 	static std::mutex g_stage_mutex;
 	static std::map<std::string, double> g_stage_secs;
 

@@ -335,6 +335,49 @@ REF_API uint64_t ref_etc1s_reoptimize_cluster(const uint8_t* pBlocks, uint32_t n
 	return r.m_error;
 }
 
+// The per-cluster body of generate_endpoint_codebook at step >= 1 (frontend.cpp:1493-1606): etc1_optimizer over the cluster's texels
+// (quality by comp_level) and the error of the previous endpoint prev4 = {r5, g5, b5, inten}, best of four colours per texel.
+REF_API uint64_t ref_etc1s_refit_cluster(const uint8_t* pBlocks, uint32_t nblocks, const uint8_t* prev4, uint32_t perceptual, uint32_t comp_level, uint8_t* out4, uint64_t* pPrev_err)
+{
+	const uint64_t new_err = ref_etc1s_encode_cluster(pBlocks, nblocks * 16, perceptual, comp_level, out4);
+	color_rgba block_colors[4];
+	etc_block::get_block_colors5(block_colors, color_rgba(prev4[0], prev4[1], prev4[2], 255), prev4[3], false);
+	const color_rgba* px = reinterpret_cast<const color_rgba*>(pBlocks);
+	uint64_t total = 0;
+	for (uint32_t i = 0; i < nblocks * 16; i++)
+	{
+		uint64_t best = UINT64_MAX;
+		for (uint32_t k = 0; k < 4; k++) best = minimum<uint64_t>(best, color_distance(perceptual != 0, px[i], block_colors[k], false));
+		total += best;
+	}
+	*pPrev_err = total;
+	return new_err;
+}
+
+// compute_endpoint_subblock_error_vec's inner body (frontend.cpp:1022-1066) for every block: pC5i = {r5, g5, b5, inten} per block.
+REF_API void ref_etc1s_subblock_errors(const uint8_t* pBlocks, uint32_t n, const uint8_t* pC5i, uint32_t perceptual, uint64_t* pOut)
+{
+	ref_init();
+	for (uint32_t b = 0; b < n; b++)
+	{
+		const color_rgba* px = reinterpret_cast<const color_rgba*>(pBlocks + (size_t)b * 64);
+		color_rgba block_colors[4];
+		etc_block::get_block_colors5(block_colors, color_rgba(pC5i[b * 4], pC5i[b * 4 + 1], pC5i[b * 4 + 2], 255), pC5i[b * 4 + 3], true);
+		for (uint32_t sub = 0; sub < 2; sub++)
+		{
+			uint64_t total = 0;
+			for (uint32_t i = 0; i < 8; i++)
+			{
+				const color_rgba& c = px[g_etc1_pixel_indices[1][sub][i]];
+				uint64_t best = UINT64_MAX;
+				for (uint32_t k = 0; k < 4; k++) best = minimum<uint64_t>(best, color_distance(perceptual != 0, c, block_colors[k], false));
+				total += best;
+			}
+			pOut[b * 2 + sub] = total;
+		}
+	}
+}
+
 // ---- the steps either side of the per-block path -----------------------------------------------
 
 // basis_compressor::extract_source_blocks for one slice (comp.cpp:3207): image::extract_block_clamped per 4x4 block.

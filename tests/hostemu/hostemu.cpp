@@ -140,7 +140,8 @@ struct host_forced_src
 	uint32_t selector(uint64_t i) const { return (sels[i >> 4] >> (2 * (uint32_t)(i & 15))) & 3u; }
 };
 // One endpoint cluster of `nblocks` source blocks. pSelectors == NULL: b200_etc1s_encode_endpoint_clusters' per-cluster work;
-// else b200_etc1s_reoptimize_endpoint_clusters' (selectors imposed, *pCur_err = error of cur4 with them). out4 = {r5, g5, b5, inten}.
+// else b200_etc1s_reoptimize_endpoint_clusters' (selectors imposed); *pCur_err = error of the endpoint cur4 (with the imposed
+// selectors, else best of four per texel). out4 = {r5, g5, b5, inten}.
 EMU_API uint64_t emu_etc1s_optimize_cluster(const uint8_t* pBlocks, uint32_t nblocks, const uint32_t* pSelectors, const uint8_t* cur4, int perceptual, uint32_t total_perms, int flavour,
 	uint8_t* out4, uint64_t* pCur_err)
 {
@@ -149,12 +150,13 @@ EMU_API uint64_t emu_etc1s_optimize_cluster(const uint8_t* pBlocks, uint32_t nbl
 	if (pSelectors)
 	{
 		host_forced_src src; src.px = reinterpret_cast<const uint32_t*>(pBlocks); src.sels = pSelectors; src.n = (uint64_t)nblocks * 16;
-		if (pCur_err) *pCur_err = cluster_forced_error(&g_tables, perceptual != 0, src, team, cur4[0], cur4[1], cur4[2], cur4[3]);
+		if (pCur_err) *pCur_err = cluster_endpoint_error(&g_tables, perceptual != 0, src, team, cur4[0], cur4[1], cur4[2], cur4[3]);
 		packed = cluster_optimize(&g_tables, perceptual != 0, src, team, total_perms, flavour, &err);
 	}
 	else
 	{
 		host_blocks_src src; src.px = reinterpret_cast<const uint32_t*>(pBlocks); src.n = (uint64_t)nblocks * 16;
+		if (pCur_err && cur4) *pCur_err = cluster_endpoint_error(&g_tables, perceptual != 0, src, team, cur4[0], cur4[1], cur4[2], cur4[3]);
 		packed = cluster_optimize(&g_tables, perceptual != 0, src, team, total_perms, flavour, &err);
 	}
 	const uint32_t w = (uint32_t)packed;

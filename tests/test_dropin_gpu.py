@@ -191,3 +191,29 @@ def test_basisu_tool_cli_on_the_dropin(tmp_path):
     gpu, cpu = open(tmp_path / "e_gpu.basis", "rb").read(), open(tmp_path / "e_cpu.basis", "rb").read()
     print(f"basisu CLI ETC1S q128 kodim03: CPU {len(cpu)} B, B200 {len(gpu)} B")
     assert gpu == cpu
+
+
+@pytest.mark.parametrize("comp_level", [0, 3, 4, 5, 6])
+def test_basisu_tool_cli_etc1s_comp_levels_identical_to_cpu(tmp_path, comp_level):
+    """Every ETC1S effort level through the reference's CLI on the drop-in library: -comp_level 0 (no refinement), 3 / 5 / 6 (flat
+    codebooks), 4-6 (endpoint / selector refinement iterations: introduce_new_endpoint_clusters with the device's subblock errors,
+    generate_endpoint_codebook at steps >= 1 on the device, refine_block_endpoints_given_selectors on the host). The GPU file must equal
+    the CPU file of the same binary, byte for byte (except level 0, where the reference's own seam asks the GPU stage for more
+    permutations than its CPU path runs, frontend.cpp:745-783: PSNR gate there)."""
+    from PIL import Image
+    png = os.path.join(util.ROOT, "oracle", "_ref", "test_files", "kodim03.png")
+    if not os.path.exists(png):
+        pytest.skip("oracle/_ref/test_files/kodim03.png did not travel")
+    crop = tmp_path / "crop.png"
+    Image.open(png).convert("RGB").crop((256, 128, 256 + 320, 128 + 256)).save(crop)
+    out = _run_tool(["-basis", "-comp_level", str(comp_level), "-q", "200", "-opencl", "-debug", "-output_file", str(tmp_path / "gpu.basis"), str(crop)], tmp_path)
+    assert "OpenCL: 1" in out and "failed! Using CPU" not in out
+    if comp_level >= 4:
+        assert "opencl_b200_compute_subblock_errors" in out and out.count("opencl_b200_reoptimize_endpoint_clusters") >= 3
+    _run_tool(["-basis", "-comp_level", str(comp_level), "-q", "200", "-output_file", str(tmp_path / "cpu.basis"), str(crop)], tmp_path)
+    gpu, cpu = open(tmp_path / "gpu.basis", "rb").read(), open(tmp_path / "cpu.basis", "rb").read()
+    print(f"basisu CLI ETC1S comp_level {comp_level} q200 320x256: CPU {len(cpu)} B, B200 {len(gpu)} B")
+    if comp_level == 0:
+        assert abs(len(gpu) - len(cpu)) <= 0.045 * len(cpu)
+    else:
+        assert gpu == cpu

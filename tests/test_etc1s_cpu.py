@@ -218,3 +218,18 @@ def test_cluster_average_past_2_pow_24_follows_the_reference_float_sum(ref, emu)
         got4, got_err, _ = emu_optimize_cluster(emu, blocks, None, None, perceptual, perms)
         assert got4 == tuple(int(v) for v in want4) and got_err == want_err
     assert tuple(int(v) for v in want4)[0] in (30, 31)
+
+
+@pytest.mark.parametrize("perceptual", [0, 1])
+@pytest.mark.parametrize("comp_level,perms", [(1, 16), (4, 64)])
+def test_refit_cluster_with_free_selectors_matches_reference(ref, emu, perceptual, comp_level, perms):
+    """generate_endpoint_codebook at step >= 1: optimiser result + error of the previous endpoint (best of four colours per texel)."""
+    blocks, clusters, rng = _cluster_cases(41)
+    ref.lib.ref_etc1s_refit_cluster.restype = ctypes.c_uint64
+    for c in clusters:
+        blk = np.ascontiguousarray(blocks[c])
+        prev4 = rng.integers(0, [32, 32, 32, 8], 4).astype(np.uint8)
+        want4 = np.zeros(4, np.uint8); want_prev = ctypes.c_uint64(0)
+        want_new = ref.lib.ref_etc1s_refit_cluster(_ptr(blk), ctypes.c_uint32(len(c)), _ptr(prev4), perceptual, comp_level, _ptr(want4), ctypes.byref(want_prev))
+        got = emu_optimize_cluster(emu, blk, None, prev4, perceptual, perms)
+        assert got == (tuple(int(v) for v in want4), want_new, want_prev.value), len(c)

@@ -275,3 +275,49 @@ def test_endpoint_cluster_past_2_pow_24_follows_the_reference_float_sum(ctx, ref
             out4 = np.zeros(4, np.uint8)
             ref.lib.ref_etc1s_encode_cluster(_ptr(blk), ctypes.c_uint32(len(c) * 16), perceptual, comp_level, _ptr(out4))
             assert (got[i, 0] >> 3, got[i, 1] >> 3, got[i, 2] >> 3, got[i, 3] >> 5) == tuple(int(v) for v in out4), (i, perceptual)
+
+
+@pytest.mark.parametrize("perceptual", [0, 1])
+@pytest.mark.parametrize("comp_level,perms", [(1, 16), (4, 64), (6, 165)])
+def test_refit_endpoint_clusters_free_selectors_match_reference(ctx, ref, perceptual, comp_level, perms):
+    """generate_endpoint_codebook at step >= 1 (frontend.cpp:1493-1606): new endpoint, its error and the previous endpoint's error."""
+    img = util.synth(256, 47)
+    blocks = util.image_to_blocks(img)
+    n = blocks.shape[0]
+    ctx.set_pixel_blocks(blocks)
+    etc = np.zeros((n, 8), np.uint8)
+    ref.lib.ref_etc1s_encode_blocks(_ptr(blocks), ctypes.c_uint32(n), _ptr(etc), perceptual, 1)
+    rng = np.random.default_rng(53)
+    lum = blocks.reshape(n, 16, 4)[:, :, :3].astype(np.int64).sum(axis=(1, 2))
+    order = np.argsort(lum, kind="stable").astype(np.uint32)
+    cuts = np.sort(rng.choice(np.arange(1, n - 300), 50, replace=False))
+    clusters = [c for c in np.split(order[:n - 300], cuts)] + [order[n - 300:]]
+    prev = np.zeros((len(clusters), 4), np.uint8)
+    for i, c in enumerate(clusters):
+        e = etc[c[0]]
+        prev[i] = (e[0] >> 3, e[1] >> 3, e[2] >> 3, e[3] >> 5)
+    got4, got_new, got_prev = ctx.reoptimize_endpoint_clusters(clusters, None, prev, perceptual, perms)
+    ref.lib.ref_etc1s_refit_cluster.restype = ctypes.c_uint64
+    kept = 0
+    for i, c in enumerate(clusters):
+        blk = np.ascontiguousarray(blocks[c])
+        want4 = np.zeros(4, np.uint8); want_prev = ctypes.c_uint64(0)
+        want_new = ref.lib.ref_etc1s_refit_cluster(_ptr(blk), ctypes.c_uint32(len(c)), _ptr(prev[i]), perceptual, comp_level, _ptr(want4), ctypes.byref(want_prev))
+        assert (tuple(int(v) for v in got4[i]), int(got_new[i]), int(got_prev[i])) == (tuple(int(v) for v in want4), want_new, want_prev.value), (i, len(c))
+        kept += want_prev.value <= want_new
+    assert kept < len(clusters)
+
+
+@pytest.mark.parametrize("perceptual", [0, 1])
+def test_subblock_errors_match_reference(ctx, ref, perceptual):
+    """compute_endpoint_subblock_error_vec's per-subblock error (frontend.cpp:1022-1066), including its unscaled-base behaviour."""
+    img = util.synth(192, 59)
+    blocks = util.image_to_blocks(img)
+    n = blocks.shape[0]
+    ctx.set_pixel_blocks(blocks)
+    rng = np.random.default_rng(61)
+    c5i = np.stack([rng.integers(0, 32, n), rng.integers(0, 32, n), rng.integers(0, 32, n), rng.integers(0, 8, n)], -1).astype(np.uint8)
+    got = ctx.subblock_errors(c5i, perceptual)
+    want = np.zeros((n, 2), np.uint64)
+    ref.lib.ref_etc1s_subblock_errors(_ptr(blocks), ctypes.c_uint32(n), _ptr(c5i), perceptual, _ptr(want))
+    assert np.array_equal(got, want)
