@@ -820,3 +820,126 @@ extern "C" int b200_etc1s_subblock_errors(b200_context* ctx, const void* pBlock_
 	free(h);
 	return fin;
 }
+
+// ---- ETC1S backend, endpoint prediction (basisu_backend::create_encoder_blocks, encoder/basisu_backend.cpp:405-617) ------------------
+// Per block in raster order the reference either predicts the block's endpoint index from its left / upper / upper-left neighbour
+// (equal index), or -- endpoint RDO -- replaces it by a neighbour's index if that keeps the block's error within
+// endpoint_rdo_quality_thresh times its current error. The neighbours' indices are the ones ALREADY decided, so block (x, y)
+// depends on (x-1, y), (x, y-1), (x-1, y-1): blocks on one anti-diagonal x + y = d are independent. One CTA per slice walks the
+// diagonals with a barrier between them; the index array lives in global memory and is read back through L2 (__ldcg).
+//
+// pred_out: 0..2 = predictor, 3 = none (basist::NO_ENDPOINT_PRED_INDEX); bit 7 marks "none, and the block's error was zero" (the one
+// case the reference's hit / miss statistics do not count).
+struct backend_slice { uint32_t first_block, nbx, nby; };
+
+__device__ __forceinline__ uint32_t etc1s_texel_selector(uint2 etc, uint32_t x, uint32_t y)
+{
+	// bytes 4..7 = msb plane (hi, lo), lsb plane (hi, lo); bit x * 4 + y; raw code -> selector index {2, 3, 1, 0} (etc.h:91, g_etc1_to_selector_index)
+	const uint32_t msb = ((etc.y & 255u) << 8) | ((etc.y >> 8) & 255u), lsb = (((etc.y >> 16) & 255u) << 8) | (etc.y >> 24);
+	const uint32_t bit = x * 4 + y;
+	const uint32_t raw = ((lsb >> bit) & 1u) | (((msb >> bit) & 1u) << 1);
+	return (0x1Eu >> (raw * 2)) & 3u; // raw 0 -> 2, 1 -> 3, 2 -> 1, 3 -> 0
+}
+
+__device__ uint64_t etc1s_block_error_with_selectors(const bu_tables* T, bool perceptual, const uint32_t* px, uint2 etc, uint32_t r5, uint32_t g5, uint32_t b5, uint32_t inten, uint64_t give_up)
+{
+	uint32_t colors[4];
+	etc1s_block_colors(T, r5, g5, b5, inten, colors);
+	uint64_t total = 0;
+	for (uint32_t y = 0; y < 4; y++)
+	{
+		for (uint32_t x = 0; x < 4; x++)
+		{
+			const uint32_t s = etc1s_texel_selector(etc, x, y);
+			total += etc_color_distance(perceptual, px[x + y * 4], s == 0 ? colors[0] : (s == 1 ? colors[1] : (s == 2 ? colors[2] : colors[3])));
+		}
+		if (total > give_up) break; // the reference stops summing past the threshold; what it then compares is already too large
+	}
+	return total;
+}
+
+__global__ void __launch_bounds__(1024) k_etc1s_endpoint_prediction(const uint4* __restrict__ blocks, const uint2* __restrict__ etc_blocks, const backend_slice* __restrict__ slices,
+	const uint32_t* __restrict__ c5i, uint32_t* idx, uint8_t* __restrict__ pred_out, float thresh, int perceptual_i)
+{
+	const backend_slice sl = slices[blockIdx.x];
+	const bool perceptual = perceptual_i != 0;
+	const bu_tables* T = &d_tables;
+	const uint32_t diagonals = sl.nbx + sl.nby - 1;
+	for (uint32_t d = 0; d < diagonals; d++)
+	{
+		const uint32_t y_lo = d >= sl.nbx ? d - (sl.nbx - 1) : 0, y_hi = min(d, sl.nby - 1);
+		for (uint32_t y = y_lo + threadIdx.x; y <= y_hi; y += blockDim.x)
+		{
+			const uint32_t x = d - y, b = sl.first_block + x + y * sl.nbx;
+			const uint32_t own = __ldcg(idx + b);
+			const bool has[3] = { x > 0, y > 0, x > 0 && y > 0 };
+			uint32_t nb[3];
+			nb[0] = has[0] ? __ldcg(idx + b - 1) : 0xFFFFFFFFu;
+			nb[1] = has[1] ? __ldcg(idx + b - sl.nbx) : 0xFFFFFFFFu;
+			nb[2] = has[2] ? __ldcg(idx + b - sl.nbx - 1) : 0xFFFFFFFFu;
+			uint32_t pred = 3;
+			if (has[0] && nb[0] == own) pred = 0;
+			else if (has[1] && nb[1] == own) pred = 1;
+			else if (has[2] && nb[2] == own) pred = 2;
+			else if (thresh > 0.0f)
+			{
+				uint32_t px[16];
+				for (int q = 0; q < 4; q++) { const uint4 v = __ldg(blocks + (size_t)b * 4 + q); px[q * 4] = v.x; px[q * 4 + 1] = v.y; px[q * 4 + 2] = v.z; px[q * 4 + 3] = v.w; }
+				const uint2 etc = __ldg(etc_blocks + b);
+				// the block's own colour: bytes 0..3 = R5 << 3, G5 << 3, B5 << 3 (delta 0), table << 5 | table << 2 | diff | flip
+				const uint64_t cur_err = etc1s_block_error_with_selectors(T, perceptual, px, etc, (etc.x >> 3) & 31u, (etc.x >> 11) & 31u, (etc.x >> 19) & 31u, (etc.x >> 29) & 7u, UINT64_MAX);
+				if (cur_err)
+				{
+					const uint64_t thresh_err = (uint64_t)((float)cur_err * fmaxf(1.0f, thresh)); // uint64 -> float, float product, truncation: as written at backend.cpp:509
+					uint64_t best_err = UINT64_MAX;
+					uint32_t best_index = 0;
+					for (uint32_t p = 0; p < 3; p++)
+					{
+						if (!has[p]) continue;
+						const uint32_t e = __ldg(c5i + nb[p]);
+						const uint64_t trial = etc1s_block_error_with_selectors(T, perceptual, px, etc, e & 255u, (e >> 8) & 255u, (e >> 16) & 255u, e >> 24, thresh_err);
+						if (trial <= thresh_err && trial < best_err) { best_err = trial; best_index = nb[p]; pred = p; }
+					}
+					if (pred != 3) __stcg(idx + b, best_index);
+				}
+				else pred = 3 | 0x80u;
+			}
+			pred_out[b] = (uint8_t)pred;
+		}
+		__syncthreads();
+	}
+}
+
+extern "C" int b200_etc1s_backend_endpoint_prediction(b200_context* ctx, uint32_t num_slices, const uint32_t* pSlice_first_block_nbx_nby, const void* pEtc_blocks,
+	uint32_t total_endpoints, const void* pEndpoint_color5_inten, float endpoint_rdo_quality_thresh, int perceptual, uint32_t* pBlock_endpoint_indices, uint8_t* pOut_predictors)
+{
+	ETC_CHECK_BLOCKS(ctx, "b200_etc1s_backend_endpoint_prediction");
+	if (!num_slices || !pSlice_first_block_nbx_nby || !pEtc_blocks || !pEndpoint_color5_inten || !pBlock_endpoint_indices || !pOut_predictors || !total_endpoints)
+	{ ctx->fail("b200_etc1s_backend_endpoint_prediction: null or empty input"); return 0; }
+	const uint32_t n = ctx->etc_total_blocks;
+	for (uint32_t s = 0; s < num_slices; s++)
+	{
+		const uint32_t first = pSlice_first_block_nbx_nby[s * 3], nbx = pSlice_first_block_nbx_nby[s * 3 + 1], nby = pSlice_first_block_nbx_nby[s * 3 + 2];
+		if (!nbx || !nby || (uint64_t)first + (uint64_t)nbx * nby > n) { ctx->fail("b200_etc1s_backend_endpoint_prediction: slice outside the resident blocks"); return 0; }
+	}
+	for (uint32_t i = 0; i < n; i++)
+		if (pBlock_endpoint_indices[i] >= total_endpoints) { ctx->fail("b200_etc1s_backend_endpoint_prediction: endpoint index out of range"); return 0; }
+	if (!upload(ctx, 1, pEtc_blocks, (size_t)n * 8) || !upload(ctx, 2, pSlice_first_block_nbx_nby, (size_t)num_slices * 12) || !upload(ctx, 3, pEndpoint_color5_inten, (size_t)total_endpoints * 4) ||
+		!upload(ctx, 4, pBlock_endpoint_indices, (size_t)n * 4)) return 0;
+	if (!ctx->reserve(ctx->d_aux[0], ctx->aux_cap[0], (size_t)n)) return 0;
+	ctx->launches = 1; __atomic_add_fetch(&g_b200_total_launches, 1, __ATOMIC_RELAXED);
+	B200_CUDA_OK(ctx, cudaMemsetAsync(ctx->d_aux[0], 3, n, ctx->stream)); // blocks outside every slice: no predictor
+	B200_CUDA_OK(ctx, cudaEventRecord(ctx->ev0, ctx->stream));
+	k_etc1s_endpoint_prediction<<<num_slices, 1024, 0, ctx->stream>>>(static_cast<const uint4*>(ctx->d_etc_blocks), static_cast<const uint2*>(ctx->d_aux[1]),
+		static_cast<const backend_slice*>(ctx->d_aux[2]), static_cast<const uint32_t*>(ctx->d_aux[3]), static_cast<uint32_t*>(ctx->d_aux[4]), static_cast<uint8_t*>(ctx->d_aux[0]),
+		endpoint_rdo_quality_thresh, perceptual);
+	B200_CUDA_OK(ctx, cudaGetLastError());
+	B200_CUDA_OK(ctx, cudaEventRecord(ctx->ev1, ctx->stream));
+	// every rank of a communicator runs the whole (sequential-by-diagonal) pass: nothing to merge
+	B200_CUDA_OK(ctx, cudaMemcpyAsync(pBlock_endpoint_indices, ctx->d_aux[4], (size_t)n * 4, cudaMemcpyDeviceToHost, ctx->stream));
+	B200_CUDA_OK(ctx, cudaMemcpyAsync(pOut_predictors, ctx->d_aux[0], (size_t)n, cudaMemcpyDeviceToHost, ctx->stream));
+	B200_CUDA_OK(ctx, cudaStreamSynchronize(ctx->stream));
+	B200_CUDA_OK(ctx, cudaEventElapsedTime(&ctx->last_ms, ctx->ev0, ctx->ev1));
+	ctx->account(B200_STAT_ETC1S_BACKEND_PREDICTION);
+	return 1;
+}

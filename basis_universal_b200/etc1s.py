@@ -210,6 +210,22 @@ def _subblock_errors(self, block_color5_inten, perceptual):
     return out
 
 
+def _backend_endpoint_prediction(self, slices, etc_blocks, endpoint_color5_inten, block_endpoint_indices, thresh, perceptual):
+    """basisu_backend::create_encoder_blocks' endpoint prediction / endpoint RDO (backend.cpp:405-617). slices: list of
+    (first_block, blocks_x, blocks_y); -> (endpoint index per block (n,) uint32, predictor per block (n,) uint8; 3 = none)."""
+    sl = np.ascontiguousarray(np.asarray(slices, np.uint32).reshape(-1, 3))
+    etc = np.ascontiguousarray(etc_blocks, np.uint8)
+    assert etc.shape == (self.total_blocks, 8)
+    cb = np.ascontiguousarray(endpoint_color5_inten, np.uint8)
+    assert cb.ndim == 2 and cb.shape[1] == 4
+    idx = np.array(block_endpoint_indices, np.uint32, copy=True)
+    assert idx.shape == (self.total_blocks,)
+    pred = np.zeros(self.total_blocks, np.uint8)
+    self._check(self._lib.b200_etc1s_backend_endpoint_prediction(self._ctx, sl.shape[0], _p(sl), _p(etc), cb.shape[0], _p(cb), ctypes.c_float(thresh), int(bool(perceptual)),
+                                                                   _p(idx), _p(pred)), "b200_etc1s_backend_endpoint_prediction")
+    return idx, pred
+
+
 def comm_unique_id():
     """128-byte NCCL id (rank 0 calls this, then broadcasts the bytes to the other ranks)."""
     buf = np.zeros(128, np.uint8)
@@ -238,6 +254,7 @@ Etc1sContext.encode_endpoint_clusters = _encode_endpoint_clusters
 Etc1sContext.optimize_selector_codebook = _optimize_selector_codebook
 Etc1sContext.reoptimize_endpoint_clusters = _reoptimize_endpoint_clusters
 Etc1sContext.subblock_errors = _subblock_errors
+Etc1sContext.backend_endpoint_prediction = _backend_endpoint_prediction
 
 
 def merge_selector_training(keys, weights):

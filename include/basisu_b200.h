@@ -197,6 +197,20 @@ int b200_etc1s_reoptimize_endpoint_clusters(b200_context* ctx, uint32_t total_cl
  * against the UNSCALED 5-bit base colour plus the table's modifiers (it passes scaled = true, frontend.cpp:1043); so does this. */
 int b200_etc1s_subblock_errors(b200_context* ctx, const void* pBlock_color5_inten, uint64_t* pOut_errors, int perceptual);
 
+/* basisu_backend::create_encoder_blocks, the endpoint-prediction / endpoint-RDO pass (encoder/basisu_backend.cpp:405-617; non-video
+ * textures): in raster order per slice, a block whose endpoint index equals its left / upper / upper-left neighbour's gets that
+ * predictor (0 / 1 / 2); otherwise, if endpoint_rdo_quality_thresh > 0, its index is replaced by the neighbour's whose endpoint
+ * keeps the block's error (the block's selectors kept) within max(1, thresh) times its current error, lowest error first,
+ * lowest predictor on ties. Neighbour indices are the already-decided ones, exactly as in the reference's scan.
+ *   pSlice_first_block_nbx_nby: 3 u32 per slice (first block index into the array given to b200_etc1s_set_pixel_blocks, blocks
+ *     per row, rows);  pEtc_blocks: basisu_frontend::get_output_block for every block (8 B, ETC1S: differential mode, delta 0,
+ *     both tables equal);  pEndpoint_color5_inten: r5, g5, b5, table per endpoint cluster (4 B);
+ *   pBlock_endpoint_indices: in = the frontend's index per block, out = encoder_block::m_endpoint_index;
+ *   pOut_predictors: encoder_block::m_endpoint_predictor (3 = NO_ENDPOINT_PRED_INDEX); bit 7 set on a 3 means the block's current
+ *     error was zero (the reference's hit / miss statistics leave those out). */
+int b200_etc1s_backend_endpoint_prediction(b200_context* ctx, uint32_t num_slices, const uint32_t* pSlice_first_block_nbx_nby, const void* pEtc_blocks,
+	uint32_t total_endpoints, const void* pEndpoint_color5_inten, float endpoint_rdo_quality_thresh, int perceptual, uint32_t* pBlock_endpoint_indices, uint8_t* pOut_predictors);
+
 /* ---- ETC1S multi-GPU exchange point -------------------------------------------------------------------------------------- */
 
 /* Histogram of the 18-bit endpoint training keys (r5<<13 | g5<<8 | b5<<3 | inten) of `num_blocks` ETC1S blocks, each block
@@ -284,7 +298,7 @@ enum
 {
 	B200_STAT_ETC1S_ENCODE_BLOCKS = 0, B200_STAT_ETC1S_ENDPOINT_CLUSTERS = 1, B200_STAT_ETC1S_REFINE = 2, B200_STAT_ETC1S_DETERMINE_SELECTORS = 3,
 	B200_STAT_ETC1S_FIND_SELECTOR_CLUSTERS = 4, B200_STAT_ETC1S_SELECTOR_CODEBOOK = 5, B200_STAT_TSVQ = 6, B200_STAT_UASTC_ENCODE = 7, B200_STAT_UASTC_RDO = 8,
-	B200_STAT_ETC1S_REOPTIMIZE_CLUSTERS = 9, B200_STAT_COUNT = 10
+	B200_STAT_ETC1S_REOPTIMIZE_CLUSTERS = 9, B200_STAT_ETC1S_BACKEND_PREDICTION = 10, B200_STAT_COUNT = 11
 };
 int b200_stats_get(const b200_context* ctx, uint32_t stat_id, float* pKernel_ms, uint32_t* pLaunches, uint32_t* pCalls);
 void b200_stats_reset(b200_context* ctx);

@@ -55,6 +55,12 @@ namespace basisu
 	// the endpoint of the block's cluster (pBlock_color5_inten: color_rgba(r5, g5, b5, table) per block).
 	bool opencl_b200_compute_subblock_errors(opencl_context_ptr pContext, const color_rgba* pBlock_color5_inten, uint64_t* pOut_errors, bool perceptual);
 
+	// basisu_backend::create_encoder_blocks' endpoint prediction / endpoint RDO scan (backend.cpp:405-617, non-video): slices as
+	// (first block, blocks per row, rows) triples, the frontend's output blocks and endpoint codebook in, the decided endpoint index and
+	// predictor per block out (predictor 3 = none; bit 7 on a 3: the block's error was zero, which the statistics skip).
+	bool opencl_b200_backend_endpoint_prediction(opencl_context_ptr pContext, uint32_t num_slices, const uint32_t* pSlice_first_block_nbx_nby, const etc_block* pEtc_blocks,
+		uint32_t total_endpoints, const color_rgba* pEndpoint_color5_inten, float endpoint_rdo_quality_thresh, bool perceptual, uint32_t* pBlock_endpoint_indices, uint8_t* pOut_predictors);
+
 	// Stage clocks of the patched compressor (basis_compressor::process): name -> seconds of the last run, readable from outside
 	// through `extern "C" double b200_dropin_stage_secs(const char* name)` (benchmarks; no effect on the output).
 	void opencl_b200_note_stage_secs(const char* pName, double secs);

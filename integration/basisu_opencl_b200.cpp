@@ -209,6 +209,14 @@ namespace basisu
 		return report(p, b200_etc1s_subblock_errors(p->m_ctx, pBlock_color5_inten, pOut_errors, perceptual), "opencl_b200_compute_subblock_errors");
 	}
 
+	bool opencl_b200_backend_endpoint_prediction(opencl_context_ptr p, uint32_t num_slices, const uint32_t* pSlice_first_block_nbx_nby, const etc_block* pEtc_blocks,
+		uint32_t total_endpoints, const color_rgba* pEndpoint_color5_inten, float endpoint_rdo_quality_thresh, bool perceptual, uint32_t* pBlock_endpoint_indices, uint8_t* pOut_predictors)
+	{
+		if (!p) return false;
+		return report(p, b200_etc1s_backend_endpoint_prediction(p->m_ctx, num_slices, pSlice_first_block_nbx_nby, pEtc_blocks, total_endpoints, pEndpoint_color5_inten,
+			endpoint_rdo_quality_thresh, perceptual, pBlock_endpoint_indices, pOut_predictors), "opencl_b200_backend_endpoint_prediction");
+	}
+
 	static std::mutex g_stage_mutex;
 	static std::map<std::string, double> g_stage_secs;
 

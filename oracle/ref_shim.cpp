@@ -378,6 +378,57 @@ REF_API void ref_etc1s_subblock_errors(const uint8_t* pBlocks, uint32_t n, const
 	}
 }
 
+// basisu_backend::create_encoder_blocks' endpoint-prediction pass (backend.cpp:437-600, non-video) for one slice of nbx x nby blocks,
+// restated over plain arrays with the reference's own etc_block / color_distance primitives (the member function itself needs a live
+// frontend; the drop-in tests compare whole files for that). pIdx: in/out endpoint index per block; pPred: predictor per block,
+// 3 = none, 0x83 = none and zero current error.
+REF_API void ref_backend_endpoint_prediction(const uint8_t* pBlocks, const uint8_t* pEtc, uint32_t nbx, uint32_t nby, const uint8_t* pC5i, float thresh, uint32_t perceptual,
+	uint32_t* pIdx, uint8_t* pPred)
+{
+	ref_init();
+	static const int dx[3] = { -1, 0, -1 }, dy[3] = { 0, -1, -1 };
+	for (uint32_t by = 0; by < nby; by++)
+		for (uint32_t bx = 0; bx < nbx; bx++)
+		{
+			const uint32_t b = bx + by * nbx;
+			const uint32_t block_endpoint = pIdx[b];
+			uint32_t best_pred = UINT32_MAX;
+			for (uint32_t p = 0; p < 3; p++)
+			{
+				const int px = (int)bx + dx[p], py = (int)by + dy[p];
+				if (px < 0 || py < 0) continue;
+				if (pIdx[px + py * nbx] == block_endpoint && p < best_pred) best_pred = p;
+			}
+			pPred[b] = 3;
+			if (best_pred != UINT32_MAX) { pPred[b] = (uint8_t)best_pred; continue; }
+			if (!(thresh > 0.0f)) continue;
+			const color_rgba* src = reinterpret_cast<const color_rgba*>(pBlocks + (size_t)b * 64);
+			etc_block etc_blk(*reinterpret_cast<const etc_block*>(pEtc + (size_t)b * 8));
+			const uint64_t cur_err = etc_blk.evaluate_etc1_error(src, perceptual != 0);
+			if (!cur_err) { pPred[b] = 0x83; continue; }
+			const uint64_t thresh_err = (uint64_t)(cur_err * maximum(1.0f, thresh));
+			etc_block trial(etc_blk);
+			uint64_t best_err = UINT64_MAX;
+			uint32_t best_index = 0;
+			for (uint32_t p = 0; p < 3; p++)
+			{
+				const int px = (int)bx + dx[p], py = (int)by + dy[p];
+				if (px < 0 || py < 0) continue;
+				const uint32_t pi = pIdx[px + py * nbx];
+				const color_rgba pc(pC5i[pi * 4], pC5i[pi * 4 + 1], pC5i[pi * 4 + 2], 255);
+				trial.set_block_color5(pc, pc);
+				trial.set_inten_table(0, pC5i[pi * 4 + 3]);
+				trial.set_inten_table(1, pC5i[pi * 4 + 3]);
+				color_rgba tc[16];
+				unpack_etc1(trial, tc);
+				uint64_t trial_err = 0;
+				for (uint32_t i = 0; i < 16; i++) trial_err += color_distance(perceptual != 0, src[i], tc[i], false);
+				if (trial_err <= thresh_err && (trial_err < best_err || (trial_err == best_err && p < best_pred))) { best_pred = p; best_err = trial_err; best_index = pi; }
+			}
+			if (best_pred != UINT32_MAX) { pIdx[b] = best_index; pPred[b] = (uint8_t)best_pred; }
+		}
+}
+
 // ---- the steps either side of the per-block path -----------------------------------------------
 
 // basis_compressor::extract_source_blocks for one slice (comp.cpp:3207): image::extract_block_clamped per 4x4 block.

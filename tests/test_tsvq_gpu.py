@@ -321,3 +321,39 @@ def test_subblock_errors_match_reference(ctx, ref, perceptual):
     want = np.zeros((n, 2), np.uint64)
     ref.lib.ref_etc1s_subblock_errors(_ptr(blocks), ctypes.c_uint32(n), _ptr(c5i), perceptual, _ptr(want))
     assert np.array_equal(got, want)
+
+
+@pytest.mark.parametrize("perceptual,thresh", [(0, 1.5), (1, 1.5), (0, 0.375), (1, 3.0), (0, 0.0)])
+def test_backend_endpoint_prediction_matches_reference_scan(ctx, ref, perceptual, thresh):
+    """create_encoder_blocks' endpoint prediction / endpoint RDO (backend.cpp:437-600): the anti-diagonal wavefront on the device against
+    the reference's raster scan, on a quantised codebook where neighbours often share or nearly share endpoints. Two slices, odd sizes."""
+    img = util.synth(256, 67)
+    blocks_all = util.image_to_blocks(img)                       # 64 x 64 blocks
+    shapes = [(37, 23), (64, 40)]
+    n = sum(w * h for w, h in shapes)
+    blocks = np.ascontiguousarray(blocks_all[:n])
+    ctx.set_pixel_blocks(blocks)
+    etc = np.zeros((n, 8), np.uint8)
+    ref.lib.ref_etc1s_encode_blocks(_ptr(blocks), ctypes.c_uint32(n), _ptr(etc), perceptual, 1)
+    # a coarse endpoint codebook: colours quantised to 3 bits, so that many blocks share an endpoint and neighbours are near misses
+    key = ((etc[:, 0] >> 5).astype(np.uint32) << 9) | ((etc[:, 1] >> 5).astype(np.uint32) << 6) | ((etc[:, 2] >> 5).astype(np.uint32) << 3) | (etc[:, 3] >> 5)
+    uniq, idx0 = np.unique(key, return_inverse=True)
+    cb = np.stack([((uniq >> 9) & 7) * 4 + 2, ((uniq >> 6) & 7) * 4 + 2, ((uniq >> 3) & 7) * 4 + 2, uniq & 7], -1).astype(np.uint8)
+    # the blocks carry their cluster's endpoint, as the frontend's output blocks do
+    e = cb[idx0]
+    etc[:, 0] = e[:, 0] << 3; etc[:, 1] = e[:, 1] << 3; etc[:, 2] = e[:, 2] << 3; etc[:, 3] = (e[:, 3] << 5) | (e[:, 3] << 2) | 3
+    slices, first = [], 0
+    for w, h in shapes:
+        slices.append((first, w, h)); first += w * h
+    got_idx, got_pred = ctx.backend_endpoint_prediction(slices, etc, cb, idx0.astype(np.uint32), thresh, perceptual)
+    want_idx = idx0.astype(np.uint32).copy(); want_pred = np.zeros(n, np.uint8)
+    for first, w, h in slices:
+        wi = np.ascontiguousarray(want_idx[first:first + w * h]); wp = np.zeros(w * h, np.uint8)
+        ref.lib.ref_backend_endpoint_prediction(_ptr(np.ascontiguousarray(blocks[first:first + w * h])), _ptr(np.ascontiguousarray(etc[first:first + w * h])), w, h, _ptr(cb),
+                                                ctypes.c_float(thresh), perceptual, _ptr(wi), _ptr(wp))
+        want_idx[first:first + w * h] = wi; want_pred[first:first + w * h] = wp
+    assert np.array_equal(got_pred, want_pred)
+    assert np.array_equal(got_idx, want_idx)
+    if thresh > 0:
+        assert (want_idx != idx0).sum() > 50, "the fixture does not exercise endpoint RDO"
+    assert ((want_pred & 3) != 3).sum() > 100
