@@ -300,3 +300,152 @@ extern "C" int b200_etc1_unpack_blocks(b200_context* ctx, const void* pEtc1, uin
 	B200_CUDA_OK(ctx, cudaMemcpy(pRGBA_blocks, ctx->d_in, (size_t)num_blocks * 64, cudaMemcpyDeviceToHost)); // valid blocks are decoded even then
 	return ok;
 }
+
+// ---- mip generation: basisu::image_resample for 8-bit images (encoder/basisu_enc.cpp:1022-1171) over basisu::Resampler
+// (encoder/basisu_resampler.cpp:350-460) ------------------------------------------------------------------------------------
+// The reference filters separably with per-destination contributor lists (source index + float weight), one axis after the other,
+// in float: along X every output is `total = 0; total += s_j * w_j` in list order; along Y the first term is a plain product and the
+// rest are added in list order; the result is clamped to [0, 1] and converted to 8 bits (linear: (int)(255 v + .5), sRGB channels
+// through an 8192-entry table). Which axis goes first follows the reference's multiply-count estimate (resampler.cpp:772-806).
+// The kernels keep exactly those operation orders (the library is built with --fmad=false), so the output bytes are the reference's;
+// the contributor lists and the two sRGB tables are inputs (the caller gets them from Resampler / srgb_to_linear themselves).
+struct resample_args
+{
+	const uint32_t* offsets; const b200_resample_contrib* contribs; // contributor list of the axis being filtered
+	uint32_t out_w, out_h;          // size of this pass's output
+	uint32_t in_w;                  // row length of this pass's input (texels)
+	size_t in_pitch, out_pitch;     // bytes between rows of an 8-bit input / output
+	uint32_t first_comp, num_comps;
+	const float* s2l; const uint8_t* l2s; // sRGB tables or null
+};
+
+template<bool SRC_U8> __device__ __forceinline__ float resample_fetch(const void* in, const resample_args& a, uint32_t x, uint32_t y, uint32_t comp_index)
+{
+	if (SRC_U8)
+	{
+		const uint32_t v = static_cast<const uint8_t*>(in)[(size_t)y * a.in_pitch + (size_t)x * 4 + comp_index];
+		return (a.s2l && comp_index != 3) ? a.s2l[v] : (float)v * (1.0f / 255.0f);
+	}
+	return static_cast<const float*>(in)[((size_t)y * a.in_w + x) * 4 + comp_index];
+}
+
+template<bool DST_U8> __device__ __forceinline__ void resample_store(void* out, const resample_args& a, uint32_t x, uint32_t y, uint32_t comp_index, float v)
+{
+	if (!DST_U8) { static_cast<float*>(out)[((size_t)y * a.out_w + x) * 4 + comp_index] = v; return; }
+	if (v < 0.0f) v = 0.0f; else if (v > 1.0f) v = 1.0f; // Resampler::clamp with m_lo = 0, m_hi = 1
+	uint8_t b;
+	if (!a.l2s || comp_index == 3)
+	{
+		const int j = (int)(255.0f * v + .5f);
+		b = (uint8_t)(j < 0 ? 0 : (j > 255 ? 255 : j));
+	}
+	else
+	{
+		const int j = (int)(8191.0f * v + .5f);
+		b = a.l2s[j < 0 ? 0 : (j > 8191 ? 8191 : j)];
+	}
+	static_cast<uint8_t*>(out)[(size_t)y * a.out_pitch + (size_t)x * 4 + comp_index] = b;
+}
+
+template<bool SRC_U8, bool DST_U8> __global__ void __launch_bounds__(256) k_resample_x(const void* __restrict__ in, void* __restrict__ out, resample_args a)
+{
+	const uint32_t x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
+	if (x >= a.out_w) return;
+	const uint32_t c0 = a.offsets[x], c1 = a.offsets[x + 1];
+	for (uint32_t c = 0; c < a.num_comps; c++)
+	{
+		const uint32_t comp_index = a.first_comp + c;
+		float total = 0.0f;
+		for (uint32_t j = c0; j < c1; j++) total += resample_fetch<SRC_U8>(in, a, a.contribs[j].pixel, y, comp_index) * a.contribs[j].weight;
+		resample_store<DST_U8>(out, a, x, y, comp_index, total);
+	}
+}
+
+template<bool SRC_U8, bool DST_U8> __global__ void __launch_bounds__(256) k_resample_y(const void* __restrict__ in, void* __restrict__ out, resample_args a)
+{
+	const uint32_t x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
+	if (x >= a.out_w) return;
+	const uint32_t c0 = a.offsets[y], c1 = a.offsets[y + 1];
+	for (uint32_t c = 0; c < a.num_comps; c++)
+	{
+		const uint32_t comp_index = a.first_comp + c;
+		float total = 0.0f;
+		for (uint32_t j = c0; j < c1; j++)
+		{
+			const float t = resample_fetch<SRC_U8>(in, a, x, a.contribs[j].pixel, comp_index) * a.contribs[j].weight;
+			total = (j == c0) ? t : total + t; // scale_y_mov for the first contributor, scale_y_add after
+		}
+		resample_store<DST_U8>(out, a, x, y, comp_index, total);
+	}
+}
+
+extern "C" int b200_image_resample_rgba8(b200_context* ctx, const void* pSrc, uint32_t src_w, uint32_t src_h, size_t src_pitch_bytes, void* pDst, uint32_t dst_w, uint32_t dst_h,
+	size_t dst_pitch_bytes, const uint32_t* pClist_x_offsets, const b200_resample_contrib* pClist_x, const uint32_t* pClist_y_offsets, const b200_resample_contrib* pClist_y,
+	uint32_t first_comp, uint32_t num_comps, const float* pSrgb_to_linear, const uint8_t* pLinear_to_srgb)
+{
+	if (!ctx || !ctx->activate()) return 0;
+	if (!pSrc || !pDst || !src_w || !src_h || !dst_w || !dst_h || !pClist_x_offsets || !pClist_x || !pClist_y_offsets || !pClist_y) { ctx->fail("b200_image_resample_rgba8: null or empty input"); return 0; }
+	if (!num_comps || first_comp + num_comps > 4) { ctx->fail("b200_image_resample_rgba8: bad component range"); return 0; }
+	if ((pSrgb_to_linear != nullptr) != (pLinear_to_srgb != nullptr)) { ctx->fail("b200_image_resample_rgba8: both sRGB tables or neither"); return 0; }
+	if (!raster_pitch_ok(ctx, "b200_image_resample_rgba8", src_w, src_pitch_bytes) || !raster_pitch_ok(ctx, "b200_image_resample_rgba8", dst_w, dst_pitch_bytes)) return 0;
+	const uint32_t nx = pClist_x_offsets[dst_w], ny = pClist_y_offsets[dst_h];
+	for (uint32_t i = 0; i < nx; i++) if (pClist_x[i].pixel >= src_w) { ctx->fail("b200_image_resample_rgba8: X contributor outside the source"); return 0; }
+	for (uint32_t i = 0; i < ny; i++) if (pClist_y[i].pixel >= src_h) { ctx->fail("b200_image_resample_rgba8: Y contributor outside the source"); return 0; }
+
+	// Axis order: the reference's multiply-count estimate (resampler.cpp:772-806), ints as there.
+	const int x_ops = (int)nx, y_ops = (int)ny;
+	const int xy_ops = x_ops * (int)src_h + (4 * y_ops * (int)dst_w) / 3, yx_ops = (4 * y_ops * (int)src_w) / 3 + x_ops * (int)dst_h;
+	const bool delay_x = (xy_ops > yx_ops) || ((xy_ops == yx_ops) && (src_w < dst_w));
+
+	const size_t src_bytes = src_pitch_bytes * (src_h - 1) + (size_t)src_w * 4, dst_bytes = dst_pitch_bytes * (dst_h - 1) + (size_t)dst_w * 4;
+	const uint32_t mid_w = delay_x ? src_w : dst_w, mid_h = delay_x ? dst_h : src_h;
+	const size_t list_bytes = ((size_t)dst_w + 1 + (size_t)dst_h + 1) * 4 + ((size_t)nx + ny) * sizeof(b200_resample_contrib);
+	if (!ctx->reserve(ctx->d_aux[0], ctx->aux_cap[0], src_bytes) || !ctx->reserve(ctx->d_aux[1], ctx->aux_cap[1], dst_bytes) ||
+		!ctx->reserve(ctx->d_aux[2], ctx->aux_cap[2], (size_t)mid_w * mid_h * 16) || !ctx->reserve(ctx->d_aux[4], ctx->aux_cap[4], list_bytes) ||
+		!ctx->reserve(ctx->d_aux[5], ctx->aux_cap[5], 256 * 4 + 8192)) return 0;
+	uint8_t* d_lists = static_cast<uint8_t*>(ctx->d_aux[4]);
+	uint32_t* d_xo = reinterpret_cast<uint32_t*>(d_lists);
+	uint32_t* d_yo = d_xo + dst_w + 1;
+	b200_resample_contrib* d_xc = reinterpret_cast<b200_resample_contrib*>(d_yo + dst_h + 1);
+	b200_resample_contrib* d_yc = d_xc + nx;
+	B200_CUDA_OK(ctx, cudaMemcpyAsync(ctx->d_aux[0], pSrc, src_bytes, cudaMemcpyHostToDevice, ctx->stream));
+	B200_CUDA_OK(ctx, cudaMemcpyAsync(ctx->d_aux[1], pDst, dst_bytes, cudaMemcpyHostToDevice, ctx->stream)); // channels outside [first, first + num) keep their bytes
+	B200_CUDA_OK(ctx, cudaMemcpyAsync(d_xo, pClist_x_offsets, ((size_t)dst_w + 1) * 4, cudaMemcpyHostToDevice, ctx->stream));
+	B200_CUDA_OK(ctx, cudaMemcpyAsync(d_yo, pClist_y_offsets, ((size_t)dst_h + 1) * 4, cudaMemcpyHostToDevice, ctx->stream));
+	B200_CUDA_OK(ctx, cudaMemcpyAsync(d_xc, pClist_x, (size_t)nx * sizeof(b200_resample_contrib), cudaMemcpyHostToDevice, ctx->stream));
+	B200_CUDA_OK(ctx, cudaMemcpyAsync(d_yc, pClist_y, (size_t)ny * sizeof(b200_resample_contrib), cudaMemcpyHostToDevice, ctx->stream));
+	float* d_s2l = nullptr; uint8_t* d_l2s = nullptr;
+	if (pSrgb_to_linear)
+	{
+		d_s2l = static_cast<float*>(ctx->d_aux[5]); d_l2s = reinterpret_cast<uint8_t*>(d_s2l + 256);
+		B200_CUDA_OK(ctx, cudaMemcpyAsync(d_s2l, pSrgb_to_linear, 256 * 4, cudaMemcpyHostToDevice, ctx->stream));
+		B200_CUDA_OK(ctx, cudaMemcpyAsync(d_l2s, pLinear_to_srgb, 8192, cudaMemcpyHostToDevice, ctx->stream));
+	}
+	ctx->launches = 0;
+	if (!timed_begin(ctx)) return 0;
+	resample_args a;
+	a.first_comp = first_comp; a.num_comps = num_comps; a.s2l = d_s2l; a.l2s = d_l2s;
+	a.in_pitch = src_pitch_bytes; a.out_pitch = dst_pitch_bytes;
+	if (!delay_x)
+	{
+		a.offsets = d_xo; a.contribs = d_xc; a.out_w = dst_w; a.out_h = src_h; a.in_w = src_w;
+		k_resample_x<true, false><<<dim3((dst_w + 255) / 256, src_h), 256, 0, ctx->stream>>>(ctx->d_aux[0], ctx->d_aux[2], a);
+		count_launch(ctx);
+		a.offsets = d_yo; a.contribs = d_yc; a.out_w = dst_w; a.out_h = dst_h; a.in_w = dst_w;
+		k_resample_y<false, true><<<dim3((dst_w + 255) / 256, dst_h), 256, 0, ctx->stream>>>(ctx->d_aux[2], ctx->d_aux[1], a);
+		count_launch(ctx);
+	}
+	else
+	{
+		a.offsets = d_yo; a.contribs = d_yc; a.out_w = src_w; a.out_h = dst_h; a.in_w = src_w;
+		k_resample_y<true, false><<<dim3((src_w + 255) / 256, dst_h), 256, 0, ctx->stream>>>(ctx->d_aux[0], ctx->d_aux[2], a);
+		count_launch(ctx);
+		a.offsets = d_xo; a.contribs = d_xc; a.out_w = dst_w; a.out_h = dst_h; a.in_w = src_w;
+		k_resample_x<false, true><<<dim3((dst_w + 255) / 256, dst_h), 256, 0, ctx->stream>>>(ctx->d_aux[2], ctx->d_aux[1], a);
+		count_launch(ctx);
+	}
+	B200_CUDA_OK(ctx, cudaGetLastError());
+	if (!timed_end(ctx)) { ctx->fail("b200_image_resample_rgba8: kernel failed"); return 0; }
+	B200_CUDA_OK(ctx, cudaMemcpy(pDst, ctx->d_aux[1], dst_bytes, cudaMemcpyDeviceToHost));
+	return 1;
+}

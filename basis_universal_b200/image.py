@@ -68,6 +68,32 @@ class ImageOps:
             self._check(ok, "b200_etc1_unpack_blocks")
         return out
 
+    def resample(self, src, dst, clist_x, clist_y, first_comp=0, num_comps=4, srgb_tables=None):
+        """basisu::image_resample (enc.cpp:1022) with the reference's contributor lists: src (H, W, 4) uint8, dst (h, w, 4) uint8 holding
+        the destination's initial contents (modified in place and returned); clist_? = (offsets uint32 (n + 1,), weights float32, pixels
+        uint32) as Resampler::get_clist_x / _y give them; srgb_tables = (srgb_to_linear float32 (256,), linear_to_srgb uint8 (8192,)) or None."""
+        src = np.ascontiguousarray(src, np.uint8)
+        assert dst.dtype == np.uint8 and dst.flags.c_contiguous and dst.ndim == 3 and dst.shape[2] == 4 and src.ndim == 3 and src.shape[2] == 4
+
+        def pack(cl, n):
+            off, wts, pix = cl
+            off = np.ascontiguousarray(off, np.uint32)
+            assert off.shape == (n + 1,)
+            c = np.zeros(int(off[-1]), np.dtype([("weight", np.float32), ("pixel", np.uint32)]))
+            c["weight"] = wts; c["pixel"] = pix
+            return off, c
+
+        xo, xc = pack(clist_x, dst.shape[1])
+        yo, yc = pack(clist_y, dst.shape[0])
+        s2l = l2s = None
+        if srgb_tables is not None:
+            s2l = np.ascontiguousarray(srgb_tables[0], np.float32); l2s = np.ascontiguousarray(srgb_tables[1], np.uint8)
+            assert s2l.shape == (256,) and l2s.shape == (8192,)
+        self._check(self._lib.b200_image_resample_rgba8(self._ctx, _p(src), src.shape[1], src.shape[0], ctypes.c_size_t(src.shape[1] * 4), _p(dst), dst.shape[1], dst.shape[0],
+                                                         ctypes.c_size_t(dst.shape[1] * 4), _p(xo), _p(xc), _p(yo), _p(yc), int(first_comp), int(num_comps),
+                                                         _p(s2l) if s2l is not None else None, _p(l2s) if l2s is not None else None), "b200_image_resample_rgba8")
+        return dst
+
     def block_metrics_device(self, d_blocks_a, d_blocks_b, width, height):
         """Device pointers to two block arrays of a width x height image -> (hist (6, 256) uint64, sum_a (4,), sum_b (4,))."""
         m = _BlockMetrics()

@@ -318,6 +318,20 @@ float b200_last_stage_ms(const b200_context* ctx, uint32_t stage);
 int b200_timer_start(b200_context* ctx);
 float b200_timer_stop_ms(b200_context* ctx); /* synchronises the stream; < 0 on error */
 
+/* ---- mip generation --------------------------------------------------------------------------------------------------------- */
+
+/* basisu::image_resample for 8-bit images (encoder/basisu_enc.cpp:1022-1171), which basis_compressor::generate_mipmaps calls per
+ * level (encoder/basisu_comp.cpp:2146-2230): separable filtering of `num_comps` channels starting at `first_comp` with the
+ * reference's contributor lists -- pClist_?_offsets[i] .. [i + 1] index the contributors (source index, float weight) of
+ * destination column / row i, exactly Resampler::get_clist_x() / get_clist_y() (encoder/basisu_resampler.h:32-42) flattened --
+ * in the reference's operation order, axis order (resampler.cpp:772-806), [0, 1] clamp and 8-bit conversion, so pDst receives the
+ * bytes image_resample writes; the other channels of pDst keep their contents. sRGB filtering: pSrgb_to_linear[256] and
+ * pLinear_to_srgb[8192] are the two tables image_resample builds (enc.cpp:1061-1075), else both NULL. HOST pointers. */
+typedef struct b200_resample_contrib { float weight; uint32_t pixel; } b200_resample_contrib;
+int b200_image_resample_rgba8(b200_context* ctx, const void* pSrc, uint32_t src_w, uint32_t src_h, size_t src_pitch_bytes, void* pDst, uint32_t dst_w, uint32_t dst_h,
+	size_t dst_pitch_bytes, const uint32_t* pClist_x_offsets, const b200_resample_contrib* pClist_x, const uint32_t* pClist_y_offsets, const b200_resample_contrib* pClist_y,
+	uint32_t first_comp, uint32_t num_comps, const float* pSrgb_to_linear, const uint8_t* pLinear_to_srgb);
+
 #ifdef __cplusplus
 }
 #endif

@@ -61,6 +61,11 @@ namespace basisu
 	bool opencl_b200_backend_endpoint_prediction(opencl_context_ptr pContext, uint32_t num_slices, const uint32_t* pSlice_first_block_nbx_nby, const etc_block* pEtc_blocks,
 		uint32_t total_endpoints, const color_rgba* pEndpoint_color5_inten, float endpoint_rdo_quality_thresh, bool perceptual, uint32_t* pBlock_endpoint_indices, uint8_t* pOut_predictors);
 
+	// basisu::image_resample for 8-bit images (enc.cpp:1022-1171), as basis_compressor::generate_mipmaps calls it per mip level
+	// (comp.cpp:2203-2218): same arguments, same bytes in dst. The contributor lists come from the reference's own Resampler.
+	bool opencl_b200_image_resample(opencl_context_ptr pContext, const image& src, image& dst, bool srgb, const char* pFilter, float filter_scale, bool wrapping,
+		uint32_t first_comp, uint32_t num_comps);
+
 	// Stage clocks of the patched compressor (basis_compressor::process): name -> seconds of the last run, readable from outside
 	// through `extern "C" double b200_dropin_stage_secs(const char* name)` (benchmarks; no effect on the output).
 	void opencl_b200_note_stage_secs(const char* pName, double secs);

@@ -7,6 +7,7 @@
 // Failure semantics are the reference's: any call returning false makes the frontend null its context, set
 // m_opencl_failed and recompute that stage on the CPU (encoder/basisu_frontend.cpp:757-762).
 #include "basisu_b200_seam.h"
+#include "basisu_resampler.h"
 #include "basisu_b200.h"
 #include <map>
 #include <stdio.h>
@@ -215,6 +216,54 @@ namespace basisu
 		if (!p) return false;
 		return report(p, b200_etc1s_backend_endpoint_prediction(p->m_ctx, num_slices, pSlice_first_block_nbx_nby, pEtc_blocks, total_endpoints, pEndpoint_color5_inten,
 			endpoint_rdo_quality_thresh, perceptual, pBlock_endpoint_indices, pOut_predictors), "opencl_b200_backend_endpoint_prediction");
+	}
+
+	bool opencl_b200_image_resample(opencl_context_ptr p, const image& src, image& dst, bool srgb, const char* pFilter, float filter_scale, bool wrapping,
+		uint32_t first_comp, uint32_t num_comps)
+	{
+		if (!p) return false;
+		const uint32_t src_w = src.get_width(), src_h = src.get_height(), dst_w = dst.get_width(), dst_h = dst.get_height();
+		// image_resample's own argument checks (enc.cpp:1035-1059); anything it would reject or short-cut is left to it
+		if (!src_w || !src_h || !dst_w || !dst_h || (num_comps < 1) || (first_comp + num_comps > 4)) return false;
+		if ((maximum(src_w, src_h) > BASISU_RESAMPLER_MAX_DIMENSION) || (maximum(dst_w, dst_h) > BASISU_RESAMPLER_MAX_DIMENSION)) return false;
+		if ((src_w == dst_w) && (src_h == dst_h) && (filter_scale == 1.0f)) return false;
+
+		// The reference's contributor lists, from its own Resampler (what image_resample constructs for component 0, enc.cpp:1080-1083)
+		Resampler resampler(src_w, src_h, dst_w, dst_h, wrapping ? Resampler::BOUNDARY_WRAP : Resampler::BOUNDARY_CLAMP, 0.0f, 1.0f, pFilter, nullptr, nullptr,
+			filter_scale, filter_scale, 0, 0);
+		if (resampler.status() != Resampler::STATUS_OKAY) return false;
+		const Resampler::Contrib_List* pClist[2] = { resampler.get_clist_x(), resampler.get_clist_y() };
+		const uint32_t n[2] = { dst_w, dst_h };
+		std::vector<uint32_t> offsets[2];
+		std::vector<b200_resample_contrib> contribs[2];
+		for (int axis = 0; axis < 2; axis++)
+		{
+			offsets[axis].resize(n[axis] + 1);
+			for (uint32_t i = 0; i < n[axis]; i++)
+			{
+				offsets[axis][i] = (uint32_t)contribs[axis].size();
+				for (uint32_t j = 0; j < pClist[axis][i].n; j++)
+				{
+					b200_resample_contrib c;
+					c.weight = pClist[axis][i].p[j].weight; c.pixel = pClist[axis][i].p[j].pixel;
+					contribs[axis].push_back(c);
+				}
+			}
+			offsets[axis][n[axis]] = (uint32_t)contribs[axis].size();
+		}
+
+		// The two sRGB tables exactly as image_resample fills them (enc.cpp:1061-1075)
+		static float s_srgb_to_linear[256];
+		static uint8_t s_linear_to_srgb[8192];
+		static std::once_flag s_tables_once;
+		std::call_once(s_tables_once, [] {
+			for (int i = 0; i < 256; ++i) s_srgb_to_linear[i] = srgb_to_linear((float)i * (1.0f / 255.0f));
+			for (int i = 0; i < 8192; ++i) s_linear_to_srgb[i] = (uint8_t)clamp<int>((int)(255.0f * linear_to_srgb((float)i * (1.0f / (8192 - 1))) + .5f), 0, 255);
+		});
+
+		return report(p, b200_image_resample_rgba8(p->m_ctx, src.get_ptr(), src_w, src_h, (size_t)src.get_pitch() * sizeof(color_rgba), dst.get_ptr(), dst_w, dst_h,
+			(size_t)dst.get_pitch() * sizeof(color_rgba), offsets[0].data(), contribs[0].data(), offsets[1].data(), contribs[1].data(), first_comp, num_comps,
+			srgb ? s_srgb_to_linear : nullptr, srgb ? s_linear_to_srgb : nullptr), "opencl_b200_image_resample");
 	}
 
 	static std::mutex g_stage_mutex;

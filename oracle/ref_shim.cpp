@@ -19,6 +19,7 @@
 #include "encoder/basisu_frontend.h"
 #include "encoder/basisu_gpu_texture.h"
 #include "encoder/basisu_opencl.h"
+#include "encoder/basisu_resampler.h"
 #include "transcoder/basisu_transcoder.h"
 
 #include <atomic>
@@ -546,4 +547,51 @@ REF_API void ref_optimize_selector_codebook(const uint8_t* pPixel_blocks, const 
 				}
 		pOut[c] = packed;
 	}
+}
+
+// ---- mip generation ---------------------------------------------------------------------------------
+
+// basisu::image_resample (enc.cpp:1022) on RGBA8 rasters; pDst holds the destination's initial contents (channels outside the range keep them).
+REF_API int ref_image_resample(const uint8_t* pSrc, uint32_t sw, uint32_t sh, uint8_t* pDst, uint32_t dw, uint32_t dh, uint32_t srgb, const char* pFilter, float filter_scale,
+	uint32_t wrapping, uint32_t first_comp, uint32_t num_comps)
+{
+	ref_init();
+	image src(pSrc, sw, sh, 4), dst(pDst, dw, dh, 4);
+	if (!image_resample(src, dst, srgb != 0, pFilter, filter_scale, wrapping != 0, first_comp, num_comps)) return 0;
+	memcpy(pDst, dst.get_ptr(), (size_t)dw * dh * 4);
+	return 1;
+}
+
+// The contributor lists image_resample's Resampler builds for these sizes (resampler.h:32-42), flattened: offsets[n + 1] + (weight, pixel) pairs.
+// Call with pX / pY == NULL to get the counts first. Also the two sRGB tables of enc.cpp:1061-1075.
+REF_API int ref_resampler_clists(uint32_t sw, uint32_t sh, uint32_t dw, uint32_t dh, const char* pFilter, float filter_scale, uint32_t wrapping,
+	uint32_t* pX_offsets, float* pX_weights, uint32_t* pX_pixels, uint32_t* pY_offsets, float* pY_weights, uint32_t* pY_pixels)
+{
+	Resampler r(sw, sh, dw, dh, wrapping ? Resampler::BOUNDARY_WRAP : Resampler::BOUNDARY_CLAMP, 0.0f, 1.0f, pFilter, nullptr, nullptr, filter_scale, filter_scale, 0, 0);
+	const Resampler::Contrib_List* cx = r.get_clist_x();
+	const Resampler::Contrib_List* cy = r.get_clist_y();
+	if (!cx || !cy) return 0;
+	uint32_t n = 0;
+	for (uint32_t i = 0; i < dw; i++)
+	{
+		pX_offsets[i] = n;
+		for (uint32_t j = 0; j < cx[i].n; j++, n++)
+			if (pX_weights) { pX_weights[n] = cx[i].p[j].weight; pX_pixels[n] = cx[i].p[j].pixel; }
+	}
+	pX_offsets[dw] = n;
+	n = 0;
+	for (uint32_t i = 0; i < dh; i++)
+	{
+		pY_offsets[i] = n;
+		for (uint32_t j = 0; j < cy[i].n; j++, n++)
+			if (pY_weights) { pY_weights[n] = cy[i].p[j].weight; pY_pixels[n] = cy[i].p[j].pixel; }
+	}
+	pY_offsets[dh] = n;
+	return 1;
+}
+
+REF_API void ref_srgb_tables(float* pSrgb_to_linear256, uint8_t* pLinear_to_srgb8192)
+{
+	for (int i = 0; i < 256; ++i) pSrgb_to_linear256[i] = srgb_to_linear((float)i * (1.0f / 255.0f));
+	for (int i = 0; i < 8192; ++i) pLinear_to_srgb8192[i] = (uint8_t)clamp<int>((int)(255.0f * linear_to_srgb((float)i * (1.0f / (8192 - 1))) + .5f), 0, 255);
 }

@@ -217,3 +217,28 @@ def test_basisu_tool_cli_etc1s_comp_levels_identical_to_cpu(tmp_path, comp_level
         assert abs(len(gpu) - len(cpu)) <= 0.045 * len(cpu)
     else:
         assert gpu == cpu
+
+
+@pytest.mark.parametrize("mode", ["etc1s", "etc1s_linear_clamp_slow", "uastc"])
+def test_basisu_tool_cli_mipmaps_identical_to_cpu(tmp_path, mode):
+    """`basisu -mipmap`: every mip level filtered on the device (basis_compressor::generate_mipmaps -> image_resample, comp.cpp:2146-2230),
+    then the multi-slice texture through the ETC1S frontend + backend (one wavefront CTA per slice) or the UASTC encoder. The file must
+    equal the CPU run's, byte for byte."""
+    from PIL import Image
+    png = os.path.join(util.ROOT, "oracle", "_ref", "test_files", "kodim03.png")
+    if not os.path.exists(png):
+        pytest.skip("oracle/_ref/test_files/kodim03.png did not travel")
+    crop = tmp_path / "crop.png"
+    Image.open(png).convert("RGB").crop((200, 100, 200 + 300, 100 + 212)).save(crop)   # 300 x 212: odd mip sizes down to 1 x 1
+    args = ["-basis", "-mipmap"]
+    if mode == "uastc":
+        args += ["-uastc", "-uastc_level", "1"]
+    if mode == "etc1s_linear_clamp_slow":   # defaults are sRGB filtering, wrap addressing, each level from the previous one
+        args += ["-mip_linear", "-mip_clamp", "-mip_slow", "-mip_filter", "lanczos4"]
+    out = _run_tool(args + ["-opencl", "-debug", "-output_file", str(tmp_path / "gpu.basis"), str(crop)], tmp_path)
+    assert "OpenCL: 1" in out and "failed! Using CPU" not in out
+    assert out.count("opencl_b200_image_resample") >= 8, "the mip levels were not filtered on the device"
+    _run_tool(args + ["-output_file", str(tmp_path / "cpu.basis"), str(crop)], tmp_path)
+    gpu, cpu = open(tmp_path / "gpu.basis", "rb").read(), open(tmp_path / "cpu.basis", "rb").read()
+    print(f"basisu CLI -mipmap {mode} 300x212: CPU {len(cpu)} B, B200 {len(gpu)} B")
+    assert gpu == cpu
