@@ -49,6 +49,19 @@ def main():
     clusters = [c for c in np.split(order, np.sort(rng.choice(np.arange(1, n), 300, replace=False)))]
     checks["endpoint_clusters"] = np.array_equal(single.encode_endpoint_clusters(clusters, False, 16), sharded.encode_endpoint_clusters(clusters, False, 16))
     checks["selector_codebook"] = np.array_equal(single.optimize_selector_codebook(a, clusters, False), sharded.optimize_selector_codebook(a, clusters, False))
+    sels = rng.integers(0, 1 << 32, n, dtype=np.uint64).astype(np.uint32)
+    cur = np.stack([a[[c[0] for c in clusters], 0] >> 3, a[[c[0] for c in clusters], 1] >> 3, a[[c[0] for c in clusters], 2] >> 3, a[[c[0] for c in clusters], 3] >> 5], -1).astype(np.uint8)
+    for name, sw in (("reoptimize_forced", sels), ("reoptimize_free", None)):
+        ra, rb = single.reoptimize_endpoint_clusters(clusters, sw, cur, False, 64), sharded.reoptimize_endpoint_clusters(clusters, sw, cur, False, 64)
+        checks[name] = all(np.array_equal(x, y) for x, y in zip(ra, rb))
+    per_block = np.stack([a[:, 0] >> 3, a[:, 1] >> 3, a[:, 2] >> 3, a[:, 3] >> 5], -1).astype(np.uint8)
+    checks["subblock_errors"] = np.array_equal(single.subblock_errors(per_block, False), sharded.subblock_errors(per_block, False))
+    key = ((a[:, 0] >> 5).astype(np.uint32) << 9) | ((a[:, 1] >> 5).astype(np.uint32) << 6) | ((a[:, 2] >> 5).astype(np.uint32) << 3) | (a[:, 3] >> 5)
+    uniq, idx0 = np.unique(key, return_inverse=True)
+    cb = np.stack([((uniq >> 9) & 7) * 4 + 2, ((uniq >> 6) & 7) * 4 + 2, ((uniq >> 3) & 7) * 4 + 2, uniq & 7], -1).astype(np.uint8)
+    pa = single.backend_endpoint_prediction([(0, 256, 256)], a, cb, idx0.astype(np.uint32), 1.5, False)
+    pb = sharded.backend_endpoint_prediction([(0, 256, 256)], a, cb, idx0.astype(np.uint32), 1.5, False)
+    checks["backend_endpoint_prediction"] = np.array_equal(pa[0], pb[0]) and np.array_equal(pa[1], pb[1])
     cs = sharded.comm_stats()
     single.close()
     sharded.close()
