@@ -123,6 +123,8 @@ def lib():
         L.b200_etc1s_backend_endpoint_prediction.argtypes = [vp, u32, vp, vp, u32, vp, ctypes.c_float, i32, vp, vp]
         L.b200_image_resample_rgba8.restype = i32
         L.b200_image_resample_rgba8.argtypes = [vp, vp, u32, u32, sz, vp, u32, u32, sz, vp, vp, vp, vp, u32, u32, vp, vp]
+        L.b200_palette_reorder.restype = i32
+        L.b200_palette_reorder.argtypes = [vp, u32, vp, u32, vp]
         _lib = L
     return _lib
 
@@ -153,5 +155,5 @@ EXPORTS = [
     "b200_timer_start", "b200_timer_stop_ms", "b200_global_launch_count",
     "b200_comm_unique_id", "b200_comm_init", "b200_shard_range", "b200_comm_rank", "b200_comm_world", "b200_comm_allreduce_u32_device", "b200_comm_stats", "b200_comm_last_error",
     "b200_stats_get", "b200_stats_reset", "b200_global_stats_get", "b200_global_stats_reset", "b200_tsvq_generate", "b200_etc1s_encode_endpoint_clusters", "b200_etc1s_optimize_selector_codebook",
-    "b200_etc1s_reoptimize_endpoint_clusters", "b200_etc1s_subblock_errors", "b200_etc1s_backend_endpoint_prediction", "b200_image_resample_rgba8",
+    "b200_etc1s_reoptimize_endpoint_clusters", "b200_etc1s_subblock_errors", "b200_etc1s_backend_endpoint_prediction", "b200_image_resample_rgba8", "b200_palette_reorder",
 ]

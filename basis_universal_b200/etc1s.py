@@ -226,6 +226,14 @@ def _backend_endpoint_prediction(self, slices, etc_blocks, endpoint_color5_inten
     return idx, pred
 
 
+def _palette_reorder(self, indices, num_syms):
+    """palette_index_reorderer::init + get_remap_table (enc.cpp:1785), no distance function: index stream -> (num_syms,) uint32 old -> new."""
+    idx = np.ascontiguousarray(indices, np.uint32)
+    out = np.zeros(int(num_syms), np.uint32)
+    self._check(self._lib.b200_palette_reorder(self._ctx, idx.shape[0], _p(idx), int(num_syms), _p(out)), "b200_palette_reorder")
+    return out
+
+
 def comm_unique_id():
     """128-byte NCCL id (rank 0 calls this, then broadcasts the bytes to the other ranks)."""
     buf = np.zeros(128, np.uint8)
@@ -255,6 +263,7 @@ Etc1sContext.optimize_selector_codebook = _optimize_selector_codebook
 Etc1sContext.reoptimize_endpoint_clusters = _reoptimize_endpoint_clusters
 Etc1sContext.subblock_errors = _subblock_errors
 Etc1sContext.backend_endpoint_prediction = _backend_endpoint_prediction
+Etc1sContext.palette_reorder = _palette_reorder
 
 
 def merge_selector_training(keys, weights):

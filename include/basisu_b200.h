@@ -211,6 +211,13 @@ int b200_etc1s_subblock_errors(b200_context* ctx, const void* pBlock_color5_inte
 int b200_etc1s_backend_endpoint_prediction(b200_context* ctx, uint32_t num_slices, const uint32_t* pSlice_first_block_nbx_nby, const void* pEtc_blocks,
 	uint32_t total_endpoints, const void* pEndpoint_color5_inten, float endpoint_rdo_quality_thresh, int perceptual, uint32_t* pBlock_endpoint_indices, uint8_t* pOut_predictors);
 
+/* basisu::palette_index_reorderer::init(num_indices, pIndices, num_syms, nullptr, nullptr, 0) + get_remap_table()
+ * (encoder/basisu_enc.cpp:1785-1915), as basisu_backend::reoptimize_and_sort_endpoints_codebook orders the endpoint palette
+ * (encoder/basisu_backend.cpp:196-198): Zeng's greedy ordering over the adjacency counts of the index stream. Same ordering as the
+ * reference (same arg-max and tie rules, same float side decision), from sparse adjacency lists instead of the dense
+ * num_syms x num_syms table. pRemap_table receives num_syms entries (old index -> new index). HOST pointers. */
+int b200_palette_reorder(b200_context* ctx, uint32_t num_indices, const uint32_t* pIndices, uint32_t num_syms, uint32_t* pRemap_table);
+
 /* ---- ETC1S multi-GPU exchange point -------------------------------------------------------------------------------------- */
 
 /* Histogram of the 18-bit endpoint training keys (r5<<13 | g5<<8 | b5<<3 | inten) of `num_blocks` ETC1S blocks, each block

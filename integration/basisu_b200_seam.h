@@ -66,6 +66,10 @@ namespace basisu
 	bool opencl_b200_image_resample(opencl_context_ptr pContext, const image& src, image& dst, bool srgb, const char* pFilter, float filter_scale, bool wrapping,
 		uint32_t first_comp, uint32_t num_comps);
 
+	// palette_index_reorderer::init(num_indices, pIndices, num_syms, nullptr, nullptr, 0) + get_remap_table() (enc.cpp:1785-1915) for
+	// the endpoint palette (backend.cpp:196-198): remap_table gets the same old -> new table.
+	bool opencl_b200_palette_reorder(opencl_context_ptr pContext, uint32_t num_indices, const uint32_t* pIndices, uint32_t num_syms, uint_vec& remap_table);
+
 	// Stage clocks of the patched compressor (basis_compressor::process): name -> seconds of the last run, readable from outside
 	// through `extern "C" double b200_dropin_stage_secs(const char* name)` (benchmarks; no effect on the output).
 	void opencl_b200_note_stage_secs(const char* pName, double secs);

@@ -266,6 +266,15 @@ namespace basisu
 			srgb ? s_srgb_to_linear : nullptr, srgb ? s_linear_to_srgb : nullptr), "opencl_b200_image_resample");
 	}
 
+	bool opencl_b200_palette_reorder(opencl_context_ptr p, uint32_t num_indices, const uint32_t* pIndices, uint32_t num_syms, uint_vec& remap_table)
+	{
+		if (!p) return false;
+		uint_vec table(num_syms);
+		if (!report(p, b200_palette_reorder(p->m_ctx, num_indices, pIndices, num_syms, table.data()), "opencl_b200_palette_reorder")) return false;
+		remap_table.swap(table);
+		return true;
+	}
+
 	static std::mutex g_stage_mutex;
 	static std::map<std::string, double> g_stage_secs;
 

@@ -595,3 +595,12 @@ REF_API void ref_srgb_tables(float* pSrgb_to_linear256, uint8_t* pLinear_to_srgb
 	for (int i = 0; i < 256; ++i) pSrgb_to_linear256[i] = srgb_to_linear((float)i * (1.0f / 255.0f));
 	for (int i = 0; i < 8192; ++i) pLinear_to_srgb8192[i] = (uint8_t)clamp<int>((int)(255.0f * linear_to_srgb((float)i * (1.0f / (8192 - 1))) + .5f), 0, 255);
 }
+
+// palette_index_reorderer::init + get_remap_table (enc.cpp:1785), as the ETC1S backend uses it for the endpoint palette (no distance function).
+REF_API void ref_palette_reorder(uint32_t num_indices, const uint32_t* pIndices, uint32_t num_syms, uint32_t* pRemap)
+{
+	palette_index_reorderer r;
+	r.init(num_indices, pIndices, num_syms, nullptr, nullptr, 0);
+	const uint_vec& t = r.get_remap_table();
+	for (uint32_t i = 0; i < num_syms; i++) pRemap[i] = t[i];
+}

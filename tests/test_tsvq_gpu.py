@@ -357,3 +357,29 @@ def test_backend_endpoint_prediction_matches_reference_scan(ctx, ref, perceptual
     if thresh > 0:
         assert (want_idx != idx0).sum() > 50, "the fixture does not exercise endpoint RDO"
     assert ((want_pred & 3) != 3).sum() > 100
+
+
+def _index_stream(kind, n_syms, m, seed):
+    rng = np.random.default_rng(seed)
+    if kind == "walk":          # neighbours mostly close, occasional jumps: what a block stream of endpoint indices looks like
+        steps = np.where(rng.random(m) < 0.75, rng.integers(0, 48, m), rng.integers(0, n_syms, m))
+        return (np.cumsum(steps) % n_syms).astype(np.uint32)
+    if kind == "uniform":
+        return rng.integers(0, n_syms, m).astype(np.uint32)
+    if kind == "few":           # many symbols never used, long runs of equal indices, heavy ties
+        return np.repeat(rng.integers(0, max(n_syms // 50, 2), m // 7 + 1), 7)[:m].astype(np.uint32)
+    if kind == "constant":
+        return np.full(m, 3 % n_syms, np.uint32)
+    raise ValueError(kind)
+
+
+@pytest.mark.parametrize("kind,n_syms,m", [("walk", 2400, 16000), ("walk", 8080, 300000), ("uniform", 500, 20000), ("few", 3000, 50000),
+                                            ("constant", 40, 1000), ("uniform", 2, 50), ("walk", 1, 10), ("uniform", 700, 2)])
+def test_palette_reorder_matches_reference(ctx, ref, kind, n_syms, m):
+    """b200_palette_reorder against palette_index_reorderer::init (enc.cpp:1785-1915): identical remap table, including the degenerate
+    inputs (no two different indices adjacent; one symbol; two indices)."""
+    idx = _index_stream(kind, n_syms, m, n_syms + m)
+    want = np.zeros(n_syms, np.uint32)
+    ref.lib.ref_palette_reorder(ctypes.c_uint32(m), _ptr(idx), ctypes.c_uint32(n_syms), _ptr(want))
+    got = ctx.palette_reorder(idx, n_syms)
+    assert np.array_equal(got, want), int((got != want).sum())
