@@ -184,7 +184,7 @@ extern "C" int b200_palette_reorder(b200_context* ctx, uint32_t num_indices, con
 	PAL_OK(cudaMemcpyAsync(d_idx, pIndices, (size_t)m * 4, cudaMemcpyHostToDevice, st));
 	PAL_OK(cudaMemsetAsync(d_nruns, 0, 8, st));
 	PAL_OK(cudaMemsetAsync(d_total, 0, (size_t)n * 4, st)); PAL_OK(cudaMemsetAsync(d_vpos, 0, (size_t)n * 4, st)); PAL_OK(cudaMemsetAsync(d_placed, 0, n, st));
-	PAL_OK(cudaMemsetAsync(d_nback, 0, (size_t)n * 4, st)); PAL_OK(cudaMemsetAsync(d_nfront, 0, (size_t)n * 4, st));
+	PAL_OK(cudaMemsetAsync(d_nback, 0, (size_t)n * 4, st)); PAL_OK(cudaMemsetAsync(d_nfront, 0, (size_t)n * 4, st)); PAL_OK(cudaMemsetAsync(d_remap, 0, (size_t)n * 4, st));
 	PAL_OK(cub::DeviceRadixSort::SortKeys(nullptr, tmp_sort, d_keys, d_keys2, (int)npairs, 0, 64, st));
 	PAL_OK(cub::DeviceRunLengthEncode::Encode(nullptr, tmp_rle, d_keys2, d_ukeys, d_ucount, d_nruns, (int)npairs, st));
 	PAL_OK(cudaMallocAsync(&d_tmp, tmp_sort > tmp_rle ? tmp_sort : tmp_rle, st));
