@@ -17,7 +17,7 @@ out = torch.empty((n, 16), dtype=torch.uint8).pin_memory()
 d_in = blocks.cuda()
 d_out = torch.empty((n, 16), dtype=torch.uint8, device="cuda")
 torch.cuda.synchronize()
-for level in (0, 1, 2):
+for level in (0, 1, 2, 3):
     for _ in range(2):
         enc.encode_uastc_host_ptr(blocks.data_ptr(), n, out.data_ptr(), level)
         enc.encode_uastc_device(d_in.data_ptr(), n, d_out.data_ptr(), level)
