@@ -832,32 +832,6 @@ extern "C" int b200_etc1s_subblock_errors(b200_context* ctx, const void* pBlock_
 // case the reference's hit / miss statistics do not count).
 struct backend_slice { uint32_t first_block, nbx, nby; };
 
-__device__ __forceinline__ uint32_t etc1s_texel_selector(uint2 etc, uint32_t x, uint32_t y)
-{
-	// bytes 4..7 = msb plane (hi, lo), lsb plane (hi, lo); bit x * 4 + y; raw code -> selector index {2, 3, 1, 0} (etc.h:91, g_etc1_to_selector_index)
-	const uint32_t msb = ((etc.y & 255u) << 8) | ((etc.y >> 8) & 255u), lsb = (((etc.y >> 16) & 255u) << 8) | (etc.y >> 24);
-	const uint32_t bit = x * 4 + y;
-	const uint32_t raw = ((lsb >> bit) & 1u) | (((msb >> bit) & 1u) << 1);
-	return (0x1Eu >> (raw * 2)) & 3u; // raw 0 -> 2, 1 -> 3, 2 -> 1, 3 -> 0
-}
-
-__device__ uint64_t etc1s_block_error_with_selectors(const bu_tables* T, bool perceptual, const uint32_t* px, uint2 etc, uint32_t r5, uint32_t g5, uint32_t b5, uint32_t inten, uint64_t give_up)
-{
-	uint32_t colors[4];
-	etc1s_block_colors(T, r5, g5, b5, inten, colors);
-	uint64_t total = 0;
-	for (uint32_t y = 0; y < 4; y++)
-	{
-		for (uint32_t x = 0; x < 4; x++)
-		{
-			const uint32_t s = etc1s_texel_selector(etc, x, y);
-			total += etc_color_distance(perceptual, px[x + y * 4], s == 0 ? colors[0] : (s == 1 ? colors[1] : (s == 2 ? colors[2] : colors[3])));
-		}
-		if (total > give_up) break; // the reference stops summing past the threshold; what it then compares is already too large
-	}
-	return total;
-}
-
 __global__ void __launch_bounds__(1024) k_etc1s_endpoint_prediction(const uint4* __restrict__ blocks, const uint2* __restrict__ etc_blocks, const backend_slice* __restrict__ slices,
 	const uint32_t* __restrict__ c5i, uint32_t* idx, uint8_t* __restrict__ pred_out, float thresh, int perceptual_i)
 {
@@ -877,32 +851,17 @@ __global__ void __launch_bounds__(1024) k_etc1s_endpoint_prediction(const uint4*
 			nb[0] = has[0] ? __ldcg(idx + b - 1) : 0xFFFFFFFFu;
 			nb[1] = has[1] ? __ldcg(idx + b - sl.nbx) : 0xFFFFFFFFu;
 			nb[2] = has[2] ? __ldcg(idx + b - sl.nbx - 1) : 0xFFFFFFFFu;
-			uint32_t pred = 3;
-			if (has[0] && nb[0] == own) pred = 0;
-			else if (has[1] && nb[1] == own) pred = 1;
-			else if (has[2] && nb[2] == own) pred = 2;
-			else if (thresh > 0.0f)
+			uint32_t pred = etc1s_predict_from_neighbours(own, nb, has);
+			if (pred == 3 && thresh > 0.0f)
 			{
 				uint32_t px[16];
 				for (int q = 0; q < 4; q++) { const uint4 v = __ldg(blocks + (size_t)b * 4 + q); px[q * 4] = v.x; px[q * 4 + 1] = v.y; px[q * 4 + 2] = v.z; px[q * 4 + 3] = v.w; }
 				const uint2 etc = __ldg(etc_blocks + b);
-				// the block's own colour: bytes 0..3 = R5 << 3, G5 << 3, B5 << 3 (delta 0), table << 5 | table << 2 | diff | flip
-				const uint64_t cur_err = etc1s_block_error_with_selectors(T, perceptual, px, etc, (etc.x >> 3) & 31u, (etc.x >> 11) & 31u, (etc.x >> 19) & 31u, (etc.x >> 29) & 7u, UINT64_MAX);
-				if (cur_err)
-				{
-					const uint64_t thresh_err = (uint64_t)((float)cur_err * fmaxf(1.0f, thresh)); // uint64 -> float, float product, truncation: as written at backend.cpp:509
-					uint64_t best_err = UINT64_MAX;
-					uint32_t best_index = 0;
-					for (uint32_t p = 0; p < 3; p++)
-					{
-						if (!has[p]) continue;
-						const uint32_t e = __ldg(c5i + nb[p]);
-						const uint64_t trial = etc1s_block_error_with_selectors(T, perceptual, px, etc, e & 255u, (e >> 8) & 255u, (e >> 16) & 255u, e >> 24, thresh_err);
-						if (trial <= thresh_err && trial < best_err) { best_err = trial; best_index = nb[p]; pred = p; }
-					}
-					if (pred != 3) __stcg(idx + b, best_index);
-				}
-				else pred = 3 | 0x80u;
+				uint32_t nb_c5i[3];
+				for (uint32_t p = 0; p < 3; p++) nb_c5i[p] = has[p] ? __ldg(c5i + nb[p]) : 0u;
+				uint32_t new_index = own;
+				pred = etc1s_endpoint_rdo(T, perceptual, px, etc.x, etc.y, nb, nb_c5i, has, thresh, new_index);
+				if ((pred & 3u) != 3u) __stcg(idx + b, new_index);
 			}
 			pred_out[b] = (uint8_t)pred;
 		}

@@ -356,4 +356,68 @@ template<typename Src, typename Team> BU_HD inline uint64_t cluster_endpoint_err
 	return team.sum(total);
 }
 
+// ---- ETC1S backend, endpoint prediction (basisu_backend::create_encoder_blocks, backend.cpp:437-600): the per-block decision ----------
+// The kernel (b200_etc1s.cu) supplies the neighbours' already-decided indices; the host emulation runs the same functions in raster order.
+
+// Selector INDEX (0..3, darkest..brightest) of texel (x, y) of an etc_block given as two little-endian words: bytes 4..7 = msb plane
+// (hi, lo), lsb plane (hi, lo), bit x * 4 + y; raw code -> selector index {2, 3, 1, 0} (etc.h:91, g_etc1_to_selector_index).
+BU_FI uint32_t etc1s_texel_selector(uint32_t etc_hi, uint32_t x, uint32_t y)
+{
+	const uint32_t msb = ((etc_hi & 255u) << 8) | ((etc_hi >> 8) & 255u), lsb = (((etc_hi >> 16) & 255u) << 8) | (etc_hi >> 24);
+	const uint32_t bit = x * 4 + y;
+	const uint32_t raw = ((lsb >> bit) & 1u) | (((msb >> bit) & 1u) << 1);
+	return (0x1Eu >> (raw * 2)) & 3u; // raw 0 -> 2, 1 -> 3, 2 -> 1, 3 -> 0
+}
+
+// Error of a block decoded with endpoint (r5, g5, b5, inten) and the block's own selectors (etc_block::evaluate_etc1_error /
+// the unpack_etc1 + color_distance loop of backend.cpp:540-563). Sums row by row and stops once past `give_up`: the reference stops
+// per texel, and what it then compares is already too large either way.
+BU_HD inline uint64_t etc1s_block_error_with_selectors(const bu_tables* T, bool perceptual, const uint32_t* px, uint32_t etc_hi, uint32_t r5, uint32_t g5, uint32_t b5, uint32_t inten, uint64_t give_up)
+{
+	uint32_t colors[4];
+	etc1s_block_colors(T, r5, g5, b5, inten, colors);
+	uint64_t total = 0;
+	for (uint32_t y = 0; y < 4; y++)
+	{
+		for (uint32_t x = 0; x < 4; x++)
+		{
+			const uint32_t s = etc1s_texel_selector(etc_hi, x, y);
+			total += etc_color_distance(perceptual, px[x + y * 4], s == 0 ? colors[0] : (s == 1 ? colors[1] : (s == 2 ? colors[2] : colors[3])));
+		}
+		if (total > give_up) break;
+	}
+	return total;
+}
+
+// Predictor 0 / 1 / 2 = left / upper / upper-left neighbour with the block's own endpoint index, lowest first; 3 = none (backend.cpp:453-495).
+BU_FI uint32_t etc1s_predict_from_neighbours(uint32_t own, const uint32_t* nb, const bool* has)
+{
+	if (has[0] && nb[0] == own) return 0;
+	if (has[1] && nb[1] == own) return 1;
+	if (has[2] && nb[2] == own) return 2;
+	return 3;
+}
+
+// Endpoint RDO of a block no neighbour predicts (backend.cpp:497-590): the neighbour endpoint with the lowest error within
+// max(1, thresh) x the block's current error, lowest predictor on ties. Returns the predictor (new_index set), 3 if none qualifies,
+// 3 | 0x80 if the block's current error is zero (the reference then neither searches nor counts the block).
+// etc_lo / etc_hi: the block's 8 bytes as two little-endian words (bytes 0..3 = R5 << 3, G5 << 3, B5 << 3 with zero delta, table bits).
+BU_HD inline uint32_t etc1s_endpoint_rdo(const bu_tables* T, bool perceptual, const uint32_t* px, uint32_t etc_lo, uint32_t etc_hi, const uint32_t* nb, const uint32_t* nb_c5i, const bool* has,
+	float thresh, uint32_t& new_index)
+{
+	const uint64_t cur_err = etc1s_block_error_with_selectors(T, perceptual, px, etc_hi, (etc_lo >> 3) & 31u, (etc_lo >> 11) & 31u, (etc_lo >> 19) & 31u, (etc_lo >> 29) & 7u, UINT64_MAX);
+	if (!cur_err) return 3u | 0x80u;
+	const uint64_t thresh_err = (uint64_t)((float)cur_err * (thresh > 1.0f ? thresh : 1.0f)); // uint64 -> float, float product, truncation: as written at backend.cpp:509
+	uint64_t best_err = UINT64_MAX;
+	uint32_t pred = 3;
+	for (uint32_t p = 0; p < 3; p++)
+	{
+		if (!has[p]) continue;
+		const uint32_t e = nb_c5i[p];
+		const uint64_t trial = etc1s_block_error_with_selectors(T, perceptual, px, etc_hi, e & 255u, (e >> 8) & 255u, (e >> 16) & 255u, e >> 24, thresh_err);
+		if (trial <= thresh_err && trial < best_err) { best_err = trial; new_index = nb[p]; pred = p; }
+	}
+	return pred;
+}
+
 } // namespace bu

@@ -164,6 +164,32 @@ EMU_API uint64_t emu_etc1s_optimize_cluster(const uint8_t* pBlocks, uint32_t nbl
 	return err;
 }
 
+// basisu_backend::create_encoder_blocks' endpoint prediction for one slice, in the reference's raster order, with the per-block
+// decision functions the wavefront kernel runs (bu_etc1s.h). pIdx in/out; pPred: 0..2, 3 = none, 0x83 = none and zero current error.
+EMU_API void emu_backend_endpoint_prediction(const uint8_t* pBlocks, const uint8_t* pEtc, uint32_t nbx, uint32_t nby, const uint8_t* pC5i, float thresh, int perceptual, uint32_t* pIdx, uint8_t* pPred)
+{
+	const uint32_t* c5i = reinterpret_cast<const uint32_t*>(pC5i);
+	for (uint32_t y = 0; y < nby; y++)
+		for (uint32_t x = 0; x < nbx; x++)
+		{
+			const uint32_t b = x + y * nbx, own = pIdx[b];
+			const bool has[3] = { x > 0, y > 0, x > 0 && y > 0 };
+			const uint32_t nb[3] = { has[0] ? pIdx[b - 1] : 0xFFFFFFFFu, has[1] ? pIdx[b - nbx] : 0xFFFFFFFFu, has[2] ? pIdx[b - nbx - 1] : 0xFFFFFFFFu };
+			uint32_t pred = etc1s_predict_from_neighbours(own, nb, has);
+			if (pred == 3 && thresh > 0.0f)
+			{
+				const uint32_t* px = reinterpret_cast<const uint32_t*>(pBlocks + (size_t)b * 64);
+				const uint32_t* etc = reinterpret_cast<const uint32_t*>(pEtc + (size_t)b * 8);
+				uint32_t nb_c5i[3];
+				for (uint32_t p = 0; p < 3; p++) nb_c5i[p] = has[p] ? c5i[nb[p]] : 0u;
+				uint32_t new_index = own;
+				pred = etc1s_endpoint_rdo(&g_tables, perceptual != 0, px, etc[0], etc[1], nb, nb_c5i, has, thresh, new_index);
+				if ((pred & 3u) != 3u) pIdx[b] = new_index;
+			}
+			pPred[b] = (uint8_t)pred;
+		}
+}
+
 EMU_API void emu_etc1s_determine_selectors(const uint8_t* pBlocks, uint32_t n, const uint32_t* pColor5_inten, uint8_t* pOut, int perceptual)
 {
 	for (uint32_t i = 0; i < n; i++)

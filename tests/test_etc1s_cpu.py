@@ -233,3 +233,28 @@ def test_refit_cluster_with_free_selectors_matches_reference(ref, emu, perceptua
         want_new = ref.lib.ref_etc1s_refit_cluster(_ptr(blk), ctypes.c_uint32(len(c)), _ptr(prev4), perceptual, comp_level, _ptr(want4), ctypes.byref(want_prev))
         got = emu_optimize_cluster(emu, blk, None, prev4, perceptual, perms)
         assert got == (tuple(int(v) for v in want4), want_new, want_prev.value), len(c)
+
+
+@pytest.mark.parametrize("perceptual,thresh", [(0, 1.5), (1, 1.5), (0, 0.375), (1, 3.0), (0, 0.0)])
+def test_backend_endpoint_prediction_decisions_match_reference_scan(ref, emu, perceptual, thresh):
+    """The per-block decision functions of the endpoint-prediction wavefront kernel (bu_etc1s.h), run in raster order on the host,
+    against the restatement of basisu_backend::create_encoder_blocks' scan built from the reference's own primitives (backend.cpp:437-600)."""
+    img = util.synth(192, 67)
+    blocks = util.image_to_blocks(img)
+    w, h = 48, 37
+    n = w * h
+    blocks = np.ascontiguousarray(blocks[:n])
+    etc = np.zeros((n, 8), np.uint8)
+    ref.lib.ref_etc1s_encode_blocks(_ptr(blocks), ctypes.c_uint32(n), _ptr(etc), perceptual, 1)
+    key = ((etc[:, 0] >> 5).astype(np.uint32) << 9) | ((etc[:, 1] >> 5).astype(np.uint32) << 6) | ((etc[:, 2] >> 5).astype(np.uint32) << 3) | (etc[:, 3] >> 5)
+    uniq, idx0 = np.unique(key, return_inverse=True)
+    cb = np.stack([((uniq >> 9) & 7) * 4 + 2, ((uniq >> 6) & 7) * 4 + 2, ((uniq >> 3) & 7) * 4 + 2, uniq & 7], -1).astype(np.uint8)
+    e = cb[idx0]
+    etc[:, 0] = e[:, 0] << 3; etc[:, 1] = e[:, 1] << 3; etc[:, 2] = e[:, 2] << 3; etc[:, 3] = (e[:, 3] << 5) | (e[:, 3] << 2) | 3
+    want_idx = idx0.astype(np.uint32).copy(); want_pred = np.zeros(n, np.uint8)
+    ref.lib.ref_backend_endpoint_prediction(_ptr(blocks), _ptr(etc), w, h, _ptr(cb), ctypes.c_float(thresh), perceptual, _ptr(want_idx), _ptr(want_pred))
+    got_idx = idx0.astype(np.uint32).copy(); got_pred = np.zeros(n, np.uint8)
+    emu.lib.emu_backend_endpoint_prediction(_ptr(blocks), _ptr(etc), w, h, _ptr(cb), ctypes.c_float(thresh), perceptual, _ptr(got_idx), _ptr(got_pred))
+    assert np.array_equal(got_pred, want_pred) and np.array_equal(got_idx, want_idx)
+    if thresh > 0:
+        assert (want_idx != idx0).sum() > 20
