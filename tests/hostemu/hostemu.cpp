@@ -190,6 +190,68 @@ EMU_API void emu_backend_endpoint_prediction(const uint8_t* pBlocks, const uint8
 		}
 }
 
+// The sparse formulation of palette_index_reorderer::init that b200_backend.cu's k_pal_order walks (adjacency lists instead of the
+// dense table; every entry's placed neighbours kept in placed-list order by prepending / appending; the side decision as a float sum
+// of int products over that list), run serially: checks the formulation itself against the reference on the CPU.
+#include <algorithm>
+#include <vector>
+EMU_API void emu_palette_reorder(uint32_t num_indices, const uint32_t* pIndices, uint32_t num_syms, uint32_t* pRemap)
+{
+	const uint32_t n = num_syms;
+	for (uint32_t i = 0; i < n; i++) pRemap[i] = 0;
+	if (num_indices <= 1 || n == 1) return;
+	std::vector<unsigned long long> keys;
+	for (uint32_t i = 0; i + 1 < num_indices; i++)
+	{
+		const uint32_t a = pIndices[i], b = pIndices[i + 1];
+		if (a != b) { keys.push_back(((unsigned long long)a << 32) | b); keys.push_back(((unsigned long long)b << 32) | a); }
+	}
+	std::sort(keys.begin(), keys.end());
+	std::vector<unsigned long long> ukeys; std::vector<uint32_t> ucount;
+	for (size_t i = 0; i < keys.size(); i++)
+	{
+		if (ukeys.empty() || ukeys.back() != keys[i]) { ukeys.push_back(keys[i]); ucount.push_back(1); }
+		else ucount.back()++;
+	}
+	if (ukeys.empty()) { pRemap[0] = 1; for (uint32_t i = 2; i < n; i++) pRemap[i - 1] = i; return; }
+	std::vector<uint32_t> row_ptr(n + 1, 0);
+	for (size_t k = 0; k < ukeys.size(); k++) row_ptr[(uint32_t)(ukeys[k] >> 32) + 1]++;
+	for (uint32_t r = 0; r < n; r++) row_ptr[r + 1] += row_ptr[r];
+	size_t k0 = 0; uint32_t best_count = 0; bool have = false;
+	for (size_t k = 0; k < ukeys.size(); k++)
+		if ((uint32_t)(ukeys[k] >> 32) < (uint32_t)ukeys[k] && (!have || ucount[k] > best_count)) { k0 = k; best_count = ucount[k]; have = true; }
+	std::vector<uint32_t> total(n, 0), n_back(n, 0), n_front(n, 0), nb_count(ukeys.size());
+	std::vector<int> vpos(n, 0), nb_vpos(ukeys.size());
+	std::vector<uint8_t> placed(n, 0);
+	auto place = [&](uint32_t e, int vp, bool at_back) {
+		for (uint32_t k = row_ptr[e]; k < row_ptr[e + 1]; k++)
+		{
+			const uint32_t v = (uint32_t)ukeys[k], c = ucount[k];
+			if (placed[v]) continue;
+			total[v] += c;
+			const uint32_t slot = at_back ? (row_ptr[v] + n_back[v]++) : (row_ptr[v + 1] - 1 - n_front[v]++);
+			nb_vpos[slot] = vp; nb_count[slot] = c;
+		}
+		placed[e] = 1; vpos[e] = vp;
+	};
+	place((uint32_t)(ukeys[k0] >> 32), 0, true);
+	place((uint32_t)ukeys[k0], 1, true);
+	int lo = 0, hi = 2;
+	for (uint32_t step = 2; step < n; step++)
+	{
+		uint32_t e = 0; bool any = false;
+		for (uint32_t u = 0; u < n; u++)
+			if (!placed[u] && (!any || total[u] > total[e])) { e = u; any = true; }
+		const int P = hi - lo;
+		float which_side = 0.0f;
+		for (uint32_t q = row_ptr[e + 1] - n_front[e]; q < row_ptr[e + 1]; q++) { const int j = nb_vpos[q] - lo, r = P + 1 - 2 * (j + 1); which_side += (float)(int)((uint32_t)r * nb_count[q]); }
+		for (uint32_t q = row_ptr[e]; q < row_ptr[e] + n_back[e]; q++) { const int j = nb_vpos[q] - lo, r = P + 1 - 2 * (j + 1); which_side += (float)(int)((uint32_t)r * nb_count[q]); }
+		const bool back = which_side <= 0.0f;
+		place(e, back ? hi++ : --lo, back);
+	}
+	for (uint32_t u = 0; u < n; u++) pRemap[u] = (uint32_t)(vpos[u] - lo);
+}
+
 EMU_API void emu_etc1s_determine_selectors(const uint8_t* pBlocks, uint32_t n, const uint32_t* pColor5_inten, uint8_t* pOut, int perceptual)
 {
 	for (uint32_t i = 0; i < n; i++)

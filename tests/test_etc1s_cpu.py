@@ -258,3 +258,23 @@ def test_backend_endpoint_prediction_decisions_match_reference_scan(ref, emu, pe
     assert np.array_equal(got_pred, want_pred) and np.array_equal(got_idx, want_idx)
     if thresh > 0:
         assert (want_idx != idx0).sum() > 20
+
+
+@pytest.mark.parametrize("kind,n_syms,m", [("walk", 2400, 16000), ("walk", 5000, 120000), ("uniform", 500, 20000), ("few", 3000, 50000),
+                                            ("constant", 40, 1000), ("uniform", 2, 50), ("walk", 1, 10), ("uniform", 700, 2)])
+def test_sparse_palette_ordering_matches_reference(ref, emu, kind, n_syms, m):
+    """The sparse formulation of palette_index_reorderer::init that the device kernel walks (b200_backend.cu), run serially on the host."""
+    rng = np.random.default_rng(n_syms + m)
+    if kind == "walk":
+        steps = np.where(rng.random(m) < 0.75, rng.integers(0, 48, m), rng.integers(0, n_syms, m))
+        idx = (np.cumsum(steps) % n_syms).astype(np.uint32)
+    elif kind == "uniform":
+        idx = rng.integers(0, n_syms, m).astype(np.uint32)
+    elif kind == "few":
+        idx = np.repeat(rng.integers(0, max(n_syms // 50, 2), m // 7 + 1), 7)[:m].astype(np.uint32)
+    else:
+        idx = np.full(m, 3 % n_syms, np.uint32)
+    want = np.zeros(n_syms, np.uint32); got = np.zeros(n_syms, np.uint32)
+    ref.lib.ref_palette_reorder(ctypes.c_uint32(m), _ptr(idx), ctypes.c_uint32(n_syms), _ptr(want))
+    emu.lib.emu_palette_reorder(ctypes.c_uint32(m), _ptr(idx), ctypes.c_uint32(n_syms), _ptr(got))
+    assert np.array_equal(got, want), int((got != want).sum())
